@@ -1,0 +1,55 @@
+"""Shared test helpers: scene -> oracle/CUDA argument sets."""
+import numpy as np
+
+from oracle import ba_oracle as bo
+from vggsfm_b200.synthetic import make_scene, perturb
+
+
+def ba_case(S, N, camera_type, mode, seed=0, invisible_frac=0.2, noise_px=0.3):
+    sc = make_scene(S, N, camera_type, seed=seed, invisible_frac=invisible_frac, noise_px=noise_px)
+    model = bo.SIMPLE_RADIAL if camera_type == "SIMPLE_RADIAL" else bo.SIMPLE_PINHOLE
+    extr, K, extra, pts = perturb(sc, seed=seed + 1)
+    intr = np.zeros((S, 4))
+    intr[:, 0] = K[:, 0, 0]
+    intr[:, 1] = K[:, 0, 2]
+    intr[:, 2] = K[:, 1, 2]
+    if extra is not None:
+        intr[:, 3] = extra[:, 0]
+    if mode == bo.INTR_SHARED:
+        intr[:] = intr[0]
+    return dict(scene=sc, model=model, mode=mode, poses=extr, intr=intr, points=pts,
+                uv=sc.tracks.astype(np.float64), mask=sc.mask, K=K, extra=extra)
+
+
+def to_dev(a, dev, dtype=None):
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.to(dev).contiguous()
+
+
+def unpack_camrec(camrec, shared, S, dc, ns):
+    """camrec[S,KR] -> g_c[S,dc], H_cc[S,dc,dc], H_cs[S,6,ns]; shared[8] -> g_s[ns], H_ss[ns,ns]."""
+    g_c = camrec[:, :dc]
+    H = np.zeros((S, dc, dc))
+    idx = dc
+    for i in range(dc):
+        for j in range(i, dc):
+            H[:, i, j] = camrec[:, idx]
+            H[:, j, i] = camrec[:, idx]
+            idx += 1
+    H_cs = camrec[:, idx:idx + 6 * ns].reshape(S, 6, ns) if ns else None
+    g_s = shared[:ns]
+    H_ss = None
+    if ns:
+        full = np.array([[shared[2], shared[3]], [shared[3], shared[4]]])
+        H_ss = full[:ns, :ns]
+    return g_c, H, H_cs, g_s, H_ss
+
+
+def rotation_angle_deg(R1, R2):
+    """Geodesic rotation distance, definition of vggsfm/utils/metric.py:305-318."""
+    R = np.einsum("sij,skj->sik", R1, R2)
+    c = np.clip((np.trace(R, axis1=1, axis2=2) - 1.0) / 2.0, -1.0, 1.0)
+    return np.degrees(np.arccos(c))

@@ -1,0 +1,101 @@
+"""ctypes binding of libvggsfm_b200.so (the C ABI declared in include/vggsfm_b200.h).
+
+The product path has NO fallback: if the shared library is missing this raises, it never routes to
+PyTorch eager or to the CPU oracle.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvggsfm_b200.so")
+
+# every symbol include/vggsfm_b200.h declares (tests/test_abi.py checks the two lists agree)
+EXPORTS = [
+    "vgg_last_error", "vgg_version",
+    "vgg_ba_default_options", "vgg_ba_dims", "vgg_ba_workspace_bytes", "vgg_ba_camrec_len",
+    "vgg_ba_build_blocks", "vgg_ba_schur", "vgg_ba_solve",
+]
+
+
+class BAProblem(ctypes.Structure):
+    _fields_ = [
+        ("S", ctypes.c_int32), ("N", ctypes.c_int32),
+        ("camera_model", ctypes.c_int32), ("intr_mode", ctypes.c_int32),
+        ("uv", ctypes.c_void_p), ("mask", ctypes.c_void_p),
+        ("param_const", ctypes.c_void_p), ("point_const", ctypes.c_void_p),
+        ("poses", ctypes.c_void_p), ("intr", ctypes.c_void_p), ("points", ctypes.c_void_p),
+    ]
+
+
+class BAOptions(ctypes.Structure):
+    _fields_ = [
+        ("max_num_iterations", ctypes.c_int32),
+        ("max_num_consecutive_invalid_steps", ctypes.c_int32),
+        ("jacobi_scaling", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("function_tolerance", ctypes.c_double),
+        ("gradient_tolerance", ctypes.c_double),
+        ("parameter_tolerance", ctypes.c_double),
+        ("initial_trust_region_radius", ctypes.c_double),
+        ("max_trust_region_radius", ctypes.c_double),
+        ("min_trust_region_radius", ctypes.c_double),
+        ("min_relative_decrease", ctypes.c_double),
+        ("min_lm_diagonal", ctypes.c_double),
+        ("max_lm_diagonal", ctypes.c_double),
+    ]
+
+
+class BASummary(ctypes.Structure):
+    _fields_ = [
+        ("iterations", ctypes.c_int32), ("successful", ctypes.c_int32),
+        ("termination", ctypes.c_int32), ("reserved", ctypes.c_int32),
+        ("initial_cost", ctypes.c_double), ("final_cost", ctypes.c_double),
+        ("final_radius", ctypes.c_double), ("device_ms", ctypes.c_double),
+        ("kernel_launches", ctypes.c_int64),
+    ]
+
+
+ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
+                                ctypes.c_int, ctypes.c_void_p)
+
+_lib = None
+
+
+class NativeLibraryMissing(RuntimeError):
+    pass
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and return the shared library; raises NativeLibraryMissing if it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryMissing(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make`. vggsfm_b200 has no CPU/PyTorch fallback.")
+    L = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    L.vgg_last_error.restype = ctypes.c_char_p
+    L.vgg_version.restype = ctypes.c_int
+    L.vgg_ba_default_options.argtypes = [ctypes.POINTER(BAOptions)]
+    L.vgg_ba_default_options.restype = None
+    L.vgg_ba_dims.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]
+    L.vgg_ba_workspace_bytes.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.POINTER(ctypes.c_size_t)]
+    L.vgg_ba_camrec_len.argtypes = [ctypes.c_int, ctypes.c_int]
+    L.vgg_ba_build_blocks.argtypes = [ctypes.POINTER(BAProblem)] + [ctypes.c_void_p] * 6 + [ctypes.c_int, ctypes.c_void_p]
+    L.vgg_ba_schur.argtypes = ([ctypes.POINTER(BAProblem)] + [ctypes.c_void_p] * 6 +
+                               [ctypes.c_double] * 3 + [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p,
+                                                        ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.c_void_p])
+    L.vgg_ba_solve.argtypes = [ctypes.POINTER(BAProblem), ctypes.POINTER(BAOptions), ctypes.c_void_p, ctypes.c_size_t,
+                               ALLREDUCE_FN, ctypes.c_void_p, ctypes.POINTER(BASummary), ctypes.c_void_p,
+                               ctypes.c_void_p]
+    _lib = L
+    return L
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (rc={rc}): {lib().vgg_last_error().decode(errors='replace')}")

@@ -1,0 +1,566 @@
+// Schur-complement reduce, reduced-system preparation and back-substitution kernels.
+//
+// Replaces the Ceres SchurEliminator + DENSE_SCHUR/SPARSE_SCHUR Cholesky that
+// pycolmap.bundle_adjustment runs on the host (vggsfm/utils/triangulation.py:1050,1142).
+//
+//   point_prep      per point: V = Dp H_pp Dp + diag(clamp(diag))/radius, 3x3 Cholesky,
+//                   M = Dp L^-T, q = M^T g_p
+//   assemble_hc     camera Hessian/gradient from the per-frame records into the dense reduced system
+//   z_transpose     Zt[3n+c][row] = (W[row][n][:] M_n)[c]   (k-major operand for the SYRK),
+//                   rhs[row] += Z[row] . q
+//   syrk            Sraw -= Zt^T Zt on the lower-triangular 128x128 tiles: FP64 FMA pipe, 8x8 register
+//                   tiles, cp.async double-buffered k-slabs, split-K with f64 RED epilogue
+//   scale_damp      A = Dc Sraw Dc + diag(clamp(diag(Dc Hcc Dc)))/radius, constant parameters pinned
+//   cam_step / backsub_partial / point_step / cam_update   back-substitution and the candidate state
+#include "common.cuh"
+
+namespace vgg {
+
+// ------------------------------------------------------------------------------------------------
+__global__ void jacobi_scale_points_kernel(int N, const double* __restrict__ H_pp, double* __restrict__ sc_p, int enable) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const double* h = H_pp + (size_t)n * 6;
+  sc_p[n * 3 + 0] = enable ? 1.0 / (1.0 + sqrt(h[0])) : 1.0;
+  sc_p[n * 3 + 1] = enable ? 1.0 / (1.0 + sqrt(h[3])) : 1.0;
+  sc_p[n * 3 + 2] = enable ? 1.0 / (1.0 + sqrt(h[5])) : 1.0;
+}
+
+__global__ void jacobi_scale_cams_kernel(int D, const double* __restrict__ hdiag, double* __restrict__ sc_c, int enable) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= D) return;
+  sc_c[i] = enable ? 1.0 / (1.0 + sqrt(hdiag[i])) : 1.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per point: M (3x3 row-major) = Dp L^-T, q = M^T g_p, dpp = clamped scaled diagonal
+__global__ void point_prep_kernel(int N, const double* __restrict__ H_pp, const double* __restrict__ g_p,
+                                  const double* __restrict__ sc_p, const uint8_t* __restrict__ point_const,
+                                  double radius, double min_diag, double max_diag, double* __restrict__ M,
+                                  double* __restrict__ q, double* __restrict__ dpp, double* __restrict__ scal) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double* Mo = M + (size_t)n * 9;
+  if (point_const && point_const[n]) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Mo[i] = 0.0;
+    q[n * 3] = q[n * 3 + 1] = q[n * 3 + 2] = 0.0;
+    dpp[n * 3] = dpp[n * 3 + 1] = dpp[n * 3 + 2] = 0.0;
+    return;
+  }
+  const double* h = H_pp + (size_t)n * 6;
+  const double s0 = sc_p[n * 3], s1 = sc_p[n * 3 + 1], s2 = sc_p[n * 3 + 2];
+  double v00 = h[0] * s0 * s0, v01 = h[1] * s0 * s1, v02 = h[2] * s0 * s2;
+  double v11 = h[3] * s1 * s1, v12 = h[4] * s1 * s2, v22 = h[5] * s2 * s2;
+  const double d0 = fmin(fmax(v00, min_diag), max_diag);
+  const double d1 = fmin(fmax(v11, min_diag), max_diag);
+  const double d2 = fmin(fmax(v22, min_diag), max_diag);
+  dpp[n * 3] = d0; dpp[n * 3 + 1] = d1; dpp[n * 3 + 2] = d2;
+  v00 += d0 / radius; v11 += d1 / radius; v22 += d2 / radius;
+  // Cholesky V = L L^T
+  bool bad = !(v00 > 0.0);
+  const double l00 = sqrt(v00);
+  const double l10 = v01 / l00, l20 = v02 / l00;
+  const double t11 = v11 - l10 * l10;
+  bad = bad || !(t11 > 0.0);
+  const double l11 = sqrt(t11);
+  const double l21 = (v12 - l20 * l10) / l11;
+  const double t22 = v22 - l20 * l20 - l21 * l21;
+  bad = bad || !(t22 > 0.0);
+  const double l22 = sqrt(t22);
+  if (bad) {
+    atomicAdd(&scal[6], 1.0);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) Mo[i] = 0.0;
+    q[n * 3] = q[n * 3 + 1] = q[n * 3 + 2] = 0.0;
+    return;
+  }
+  // Linv (lower)
+  const double i00 = 1.0 / l00, i11 = 1.0 / l11, i22 = 1.0 / l22;
+  const double i10 = -l10 * i00 * i11;
+  const double i21 = -l21 * i11 * i22;
+  const double i20 = -(l20 * i00 + l21 * i10) * i22;
+  // M = Dp Linv^T : M[r][c] = s_r * Linv[c][r]
+  const double m00 = s0 * i00, m01 = s0 * i10, m02 = s0 * i20;
+  const double m11 = s1 * i11, m12 = s1 * i21;
+  const double m22 = s2 * i22;
+  Mo[0] = m00; Mo[1] = m01; Mo[2] = m02;
+  Mo[3] = 0.0; Mo[4] = m11; Mo[5] = m12;
+  Mo[6] = 0.0; Mo[7] = 0.0; Mo[8] = m22;
+  const double g0 = g_p[n * 3], g1 = g_p[n * 3 + 1], g2 = g_p[n * 3 + 2];
+  q[n * 3 + 0] = m00 * g0;
+  q[n * 3 + 1] = m01 * g0 + m11 * g1;
+  q[n * 3 + 2] = m02 * g0 + m12 * g1 + m22 * g2;
+}
+
+// ------------------------------------------------------------------------------------------------
+// camera records -> dense reduced system (both triangles of the diagonal blocks and borders),
+// rhs = -g, hdiag, gvec.  One CTA per frame, plus one for the shared-intrinsics block.
+__global__ void assemble_hc_kernel(int S, int dc, int ns, int KR, int Dpad, const double* __restrict__ camrec,
+                                   const double* __restrict__ shared_in, double* __restrict__ Sraw,
+                                   double* __restrict__ rhs, double* __restrict__ hdiag, double* __restrict__ gvec) {
+  const int s = blockIdx.x;
+  const int tid = threadIdx.x;
+  if (s < S) {
+    const double* rec = camrec + (size_t)s * KR;
+    const int base = s * dc;
+    if (tid < dc) {
+      gvec[base + tid] = rec[tid];
+      rhs[base + tid] = -rec[tid];
+    }
+    if (tid < dc * dc) {
+      const int i = tid / dc, j = tid % dc;
+      const int a = i < j ? i : j, b = i < j ? j : i;
+      const int idx = dc + a * dc - a * (a - 1) / 2 + (b - a);
+      const double val = rec[idx];
+      Sraw[(size_t)(base + i) * Dpad + base + j] = val;
+      if (i == j) hdiag[base + i] = val;
+    }
+    if (tid < 6 * ns) {
+      const int i = tid / ns, j = tid % ns;
+      const double val = rec[dc + dc * (dc + 1) / 2 + tid];
+      Sraw[(size_t)(S * dc + j) * Dpad + base + i] = val;
+      Sraw[(size_t)(base + i) * Dpad + S * dc + j] = val;
+    }
+  } else if (ns > 0) {
+    const int base = S * dc;
+    if (tid < ns) {
+      gvec[base + tid] = shared_in[tid];
+      rhs[base + tid] = -shared_in[tid];
+    }
+    if (tid < ns * ns) {
+      const int i = tid / ns, j = tid % ns;
+      const int a = i < j ? i : j, b = i < j ? j : i;
+      const double val = shared_in[2 + (a == 0 ? b : 2)];
+      Sraw[(size_t)(base + i) * Dpad + base + j] = val;
+      if (i == j) hdiag[base + i] = val;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Zt[(3n+c)*Dpad + row] = sum_c' W[row][n][c'] M[n][c'][c];  rhs[row] += sum_{n,c} Z q
+// tile: 32 rows x 32 points; block (32, 8)
+__global__ void __launch_bounds__(256) z_transpose_kernel(int D, int N, int Dpad, const double* __restrict__ W,
+                                                          const double* __restrict__ M, const double* __restrict__ q,
+                                                          double* __restrict__ Zt, double* __restrict__ rhs) {
+  __shared__ double T[96][33];
+  const int nx = threadIdx.x, ry = threadIdx.y;
+  const int n = blockIdx.y * 32 + nx;
+  const int row0 = blockIdx.x * 32;
+  double m[9], qq[3];
+  if (n < N) {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) m[i] = M[(size_t)n * 9 + i];
+    qq[0] = q[n * 3]; qq[1] = q[n * 3 + 1]; qq[2] = q[n * 3 + 2];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 9; ++i) m[i] = 0.0;
+    qq[0] = qq[1] = qq[2] = 0.0;
+  }
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int rl = ry + it * 8;
+    const int row = row0 + rl;
+    double z0 = 0, z1 = 0, z2 = 0;
+    if (row < D && n < N) {
+      const double* w = W + ((size_t)row * N + n) * 3;
+      const double w0 = w[0], w1 = w[1], w2 = w[2];
+      z0 = w0 * m[0];                            // M upper triangular (row-major)
+      z1 = w0 * m[1] + w1 * m[4];
+      z2 = w0 * m[2] + w1 * m[5] + w2 * m[8];
+    }
+    T[3 * nx + 0][rl] = z0;
+    T[3 * nx + 1][rl] = z1;
+    T[3 * nx + 2][rl] = z2;
+    const double zq = warp_sum(z0 * qq[0] + z1 * qq[1] + z2 * qq[2]);
+    if (nx == 0 && row < D && zq != 0.0) atomicAdd(&rhs[row], zq);
+  }
+  __syncthreads();
+  const int k0 = blockIdx.y * 96;
+  for (int kk = ry; kk < 96; kk += 8) {
+    const int k = k0 + kk;
+    if (k < 3 * N && row0 + nx < Dpad) Zt[(size_t)k * Dpad + row0 + nx] = T[kk][nx];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SYRK on lower-triangular tiles: C[bi,bj] -= Zt[:, bi]^T Zt[:, bj]
+constexpr int SY_BM = 128, SY_BK = 16, SY_THREADS = 256, SY_STAGES = 3;
+
+__global__ void __launch_bounds__(SY_THREADS) syrk_kernel(int Kpad, int Dpad, int k_per_split,
+                                                          const double* __restrict__ Zt, double* __restrict__ Cmat) {
+  extern __shared__ __align__(16) double sy_smem[];
+  // tile decode: blockIdx.x -> (bi >= bj)
+  int t = blockIdx.x;
+  int bi = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+  while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+  while (bi * (bi + 1) / 2 > t) --bi;
+  const int bj = t - bi * (bi + 1) / 2;
+  const bool diag = (bi == bj);
+  const int kbeg = blockIdx.y * k_per_split;
+  const int kend = min(Kpad, kbeg + k_per_split);
+  const int nslab = (kend - kbeg + SY_BK - 1) / SY_BK;
+  if (nslab <= 0) return;
+
+  double* As = sy_smem;                                   // [STAGES][BK][BM]
+  double* Bs = sy_smem + SY_STAGES * SY_BK * SY_BM;       // [STAGES][BK][BM]
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+
+  auto load_slab = [&](int slab, int stage) {
+    const int k0 = kbeg + slab * SY_BK;
+    // each operand slab: BK x BM doubles = 1024 x 16B chunks; 256 threads x 4
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int chunk = tid + i * SY_THREADS;          // 0..1023
+      const int kk = chunk >> 6;                       // 64 chunks of 16 B per k-row
+      const int cc = (chunk & 63) * 2;
+      const size_t grow = (size_t)(k0 + kk) * Dpad;
+      cp_async16(As + (stage * SY_BK + kk) * SY_BM + cc, Zt + grow + bi * SY_BM + cc);
+      if (!diag) cp_async16(Bs + (stage * SY_BK + kk) * SY_BM + cc, Zt + grow + bj * SY_BM + cc);
+    }
+    cp_async_commit();
+  };
+
+  double acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
+
+  // prologue
+#pragma unroll
+  for (int s = 0; s < SY_STAGES - 1; ++s) {
+    if (s < nslab) load_slab(s, s);
+    else cp_async_commit();
+  }
+  for (int slab = 0; slab < nslab; ++slab) {
+    cp_async_wait<SY_STAGES - 2>();
+    __syncthreads();
+    {
+      const int nxt = slab + SY_STAGES - 1;
+      if (nxt < nslab) load_slab(nxt, nxt % SY_STAGES);
+      else cp_async_commit();
+    }
+    const int stage = slab % SY_STAGES;
+    const double* as = As + stage * SY_BK * SY_BM;
+    const double* bs = diag ? as : (Bs + stage * SY_BK * SY_BM);
+#pragma unroll
+    for (int kk = 0; kk < SY_BK; ++kk) {
+      double a[8], b[8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const double2 av = *reinterpret_cast<const double2*>(as + kk * SY_BM + ty * 2 + 32 * i);
+        a[2 * i] = av.x; a[2 * i + 1] = av.y;
+        const double2 bv = *reinterpret_cast<const double2*>(bs + kk * SY_BM + tx * 2 + 32 * i);
+        b[2 * i] = bv.x; b[2 * i + 1] = bv.y;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+  }
+  cp_async_wait<0>();
+  // epilogue: C -= acc  (f64 RED; split-K partials and H_cc already in C)
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = bi * SY_BM + ty * 2 + (i & 1) + 32 * (i >> 1);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = bj * SY_BM + tx * 2 + (j & 1) + 32 * (j >> 1);
+      if (acc[i][j] != 0.0 && (!diag || c <= r)) atomicAdd(&Cmat[(size_t)r * Dpad + c], -acc[i][j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// A (lower, in place) = sc_i sc_j Sraw + diag; constant parameters pinned; b = sc * rhs
+__global__ void scale_damp_kernel(int D, int Dpad, double* __restrict__ A, const double* __restrict__ rhs,
+                                  const double* __restrict__ hdiag, const double* __restrict__ sc,
+                                  const uint8_t* __restrict__ pconst, double radius, double min_diag, double max_diag,
+                                  double* __restrict__ bvec) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.y;
+  if (j >= D || j > i) return;
+  const bool ci = pconst[i] != 0, cj = pconst[j] != 0;
+  double v;
+  if (ci || cj) {
+    v = (i == j) ? 1.0 : 0.0;
+  } else {
+    v = A[(size_t)i * Dpad + j] * sc[i] * sc[j];
+    if (i == j) v += fmin(fmax(hdiag[i] * sc[i] * sc[i], min_diag), max_diag) / radius;
+  }
+  A[(size_t)i * Dpad + j] = v;
+  if (i == j) bvec[i] = ci ? 0.0 : rhs[i] * sc[i];
+}
+
+// d_c = sc * dcs ; scal[0] += sum dcs^2 dcc/r (free) - d_c.g ; scal[1] += |d_c|^2 ; scal[7] non-finite flag
+__global__ void cam_step_kernel(int D, const double* __restrict__ dcs, const double* __restrict__ sc,
+                                const double* __restrict__ hdiag, const double* __restrict__ gvec,
+                                const uint8_t* __restrict__ pconst, double radius, double min_diag, double max_diag,
+                                double* __restrict__ d_c, double* __restrict__ scal) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double a = 0, b = 0, bad = 0;
+  if (i < D) {
+    const double x = pconst[i] ? 0.0 : dcs[i];
+    const double dc = x * sc[i];
+    d_c[i] = dc;
+    if (!isfinite(x)) bad = 1.0;
+    const double dcc = fmin(fmax(hdiag[i] * sc[i] * sc[i], min_diag), max_diag);
+    a = pconst[i] ? 0.0 : (x * x * dcc / radius - dc * gvec[i]);
+    b = dc * dc;
+  }
+  a = warp_sum(a); b = warp_sum(b); bad = warp_sum(bad);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&scal[0], a);
+    atomicAdd(&scal[1], b);
+    if (bad > 0) atomicAdd(&scal[7], bad);
+  }
+}
+
+// wacc[n][c] += sum_{row in chunk} W[row][n][c] d_c[row]
+__global__ void __launch_bounds__(128) backsub_partial_kernel(int D, int N, int rows_per_cta,
+                                                              const double* __restrict__ W,
+                                                              const double* __restrict__ d_c,
+                                                              double* __restrict__ wacc) {
+  extern __shared__ double dsm[];
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(D, r0 + rows_per_cta);
+  for (int i = threadIdx.x; i < r1 - r0; i += blockDim.x) dsm[i] = d_c[r0 + i];
+  __syncthreads();
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double w0 = 0, w1 = 0, w2 = 0;
+  const double* wp = W + ((size_t)r0 * N + n) * 3;
+#pragma unroll 4
+  for (int r = r0; r < r1; ++r, wp += (size_t)N * 3) {
+    const double d = dsm[r - r0];
+    w0 = fma(wp[0], d, w0);
+    w1 = fma(wp[1], d, w1);
+    w2 = fma(wp[2], d, w2);
+  }
+  atomicAdd(&wacc[(size_t)n * 3 + 0], w0);
+  atomicAdd(&wacc[(size_t)n * 3 + 1], w1);
+  atomicAdd(&wacc[(size_t)n * 3 + 2], w2);
+}
+
+// d_p = M M^T (-(g_p + w)); candidate = X + d_p; scal[2] += sum dps^2 dpp/r - d_p.g_p; scal[3] += |d_p|^2
+__global__ void point_step_kernel(int N, const double* __restrict__ M, const double* __restrict__ g_p,
+                                  const double* __restrict__ wacc, const double* __restrict__ sc_p,
+                                  const double* __restrict__ dpp, const double* __restrict__ X, double radius,
+                                  double* __restrict__ Xc, double* __restrict__ scal) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  double a = 0, b = 0;
+  if (n < N) {
+    const double* m = M + (size_t)n * 9;
+    const double g0 = g_p[n * 3], g1 = g_p[n * 3 + 1], g2 = g_p[n * 3 + 2];
+    const double y0 = -(g0 + wacc[n * 3]), y1 = -(g1 + wacc[n * 3 + 1]), y2 = -(g2 + wacc[n * 3 + 2]);
+    // t = M^T y (M upper triangular)
+    const double t0 = m[0] * y0;
+    const double t1 = m[1] * y0 + m[4] * y1;
+    const double t2 = m[2] * y0 + m[5] * y1 + m[8] * y2;
+    const double d0 = m[0] * t0 + m[1] * t1 + m[2] * t2;
+    const double d1 = m[4] * t1 + m[5] * t2;
+    const double d2 = m[8] * t2;
+    Xc[n * 3] = X[n * 3] + d0;
+    Xc[n * 3 + 1] = X[n * 3 + 1] + d1;
+    Xc[n * 3 + 2] = X[n * 3 + 2] + d2;
+    const double s0 = sc_p[n * 3], s1 = sc_p[n * 3 + 1], s2 = sc_p[n * 3 + 2];
+    const double e0 = d0 / s0, e1 = d1 / s1, e2 = d2 / s2;
+    a = (e0 * e0 * dpp[n * 3] + e1 * e1 * dpp[n * 3 + 1] + e2 * e2 * dpp[n * 3 + 2]) / radius -
+        (d0 * g0 + d1 * g1 + d2 * g2);
+    b = d0 * d0 + d1 * d1 + d2 * d2;
+  }
+  a = warp_sum(a); b = warp_sum(b);
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(&scal[2], a);
+    atomicAdd(&scal[3], b);
+  }
+}
+
+// candidate cameras: R <- Exp(2 delta) R, t <- t + dt, intrinsics
+__global__ void cam_update_kernel(int S, int dc, int ns, int model, const double* __restrict__ d_c,
+                                  const double* __restrict__ poses, const double* __restrict__ intr,
+                                  double* __restrict__ poses_c, double* __restrict__ intr_c) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  const double* d = d_c + (size_t)s * dc;
+  const double p0 = 2.0 * d[0], p1 = 2.0 * d[1], p2 = 2.0 * d[2];
+  const double th2 = p0 * p0 + p1 * p1 + p2 * p2;
+  const double th = sqrt(th2);
+  double a, b;
+  if (th < 1e-12) {
+    a = 1.0 - th2 / 6.0;
+    b = 0.5 - th2 / 24.0;
+  } else {
+    a = sin(th) / th;
+    b = (1.0 - cos(th)) / th2;
+  }
+  // E = I + a K + b K^2
+  double E[9];
+  E[0] = 1.0 + b * (-(p1 * p1 + p2 * p2)); E[1] = -a * p2 + b * p0 * p1;           E[2] = a * p1 + b * p0 * p2;
+  E[3] = a * p2 + b * p0 * p1;             E[4] = 1.0 + b * (-(p0 * p0 + p2 * p2)); E[5] = -a * p0 + b * p1 * p2;
+  E[6] = -a * p1 + b * p0 * p2;            E[7] = a * p0 + b * p1 * p2;            E[8] = 1.0 + b * (-(p0 * p0 + p1 * p1));
+  const double* P = poses + (size_t)s * 12;
+  double* Q = poses_c + (size_t)s * 12;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) Q[i * 4 + j] = E[i * 3] * P[j] + E[i * 3 + 1] * P[4 + j] + E[i * 3 + 2] * P[8 + j];
+  Q[3] = P[3] + d[3];
+  Q[7] = P[7] + d[4];
+  Q[11] = P[11] + d[5];
+  const int ni = (model == VGG_SIMPLE_PINHOLE) ? 1 : 2;
+  double f = intr[s * 4], k = intr[s * 4 + 3];
+  if (dc > 6) {
+    f += d[6];
+    if (ni > 1) k += d[7];
+  } else if (ns > 0) {
+    const double* dsh = d_c + (size_t)S * dc;
+    f += dsh[0];
+    if (ni > 1) k += dsh[1];
+  }
+  intr_c[s * 4] = f;
+  intr_c[s * 4 + 1] = intr[s * 4 + 1];
+  intr_c[s * 4 + 2] = intr[s * 4 + 2];
+  intr_c[s * 4 + 3] = k;
+}
+
+// gradient of the candidate camera block out of its records
+__global__ void extract_gvec_kernel(int S, int dc, int ns, int KR, const double* __restrict__ camrec,
+                                    const double* __restrict__ shared_in, double* __restrict__ gvec) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int D = S * dc + ns;
+  if (i >= D) return;
+  gvec[i] = (i < S * dc) ? camrec[(size_t)(i / dc) * KR + (i % dc)] : shared_in[i - S * dc];
+}
+
+// scal[4] = max |gvec| over free parameters, scal[5] = max |g_p| over variable points
+__global__ void gradmax_kernel(int D, int N, const double* __restrict__ gvec, const uint8_t* __restrict__ pconst,
+                               const double* __restrict__ g_p, const uint8_t* __restrict__ point_const,
+                               double* __restrict__ scal) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double mc = 0, mp = 0;
+  if (i < D && !pconst[i]) mc = fabs(gvec[i]);
+  if (i < N * 3 && !(point_const && point_const[i / 3])) mp = fabs(g_p[i]);
+  mc = warp_max(mc); mp = warp_max(mp);
+  if ((threadIdx.x & 31) == 0) {
+    // non-negative doubles order like their bit patterns
+    atomicMax(reinterpret_cast<unsigned long long*>(&scal[4]), (unsigned long long)__double_as_longlong(mc));
+    atomicMax(reinterpret_cast<unsigned long long*>(&scal[5]), (unsigned long long)__double_as_longlong(mp));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host-side launch helpers used by ba_solve.cu
+// ------------------------------------------------------------------------------------------------
+int launch_jacobi_scale_points(int N, const double* H_pp, double* sc_p, int enable, cudaStream_t st) {
+  jacobi_scale_points_kernel<<<(N + 255) / 256, 256, 0, st>>>(N, H_pp, sc_p, enable);
+  VGG_LAUNCH_CHECK();
+  return VGG_OK;
+}
+int launch_jacobi_scale_cams(int D, const double* hdiag, double* sc_c, int enable, cudaStream_t st) {
+  jacobi_scale_cams_kernel<<<(D + 255) / 256, 256, 0, st>>>(D, hdiag, sc_c, enable);
+  VGG_LAUNCH_CHECK();
+  return VGG_OK;
+}
+int launch_point_prep(int N, const double* H_pp, const double* g_p, const double* sc_p, const uint8_t* point_const,
+                      double radius, double min_diag, double max_diag, double* M, double* q, double* dpp,
+                      double* scal, cudaStream_t st) {
+  point_prep_kernel<<<(N + 127) / 128, 128, 0, st>>>(N, H_pp, g_p, sc_p, point_const, radius, min_diag, max_diag, M, q,
+                                                     dpp, scal);
+  VGG_LAUNCH_CHECK();
+  return VGG_OK;
+}
+int launch_assemble_hc(int S, int dc, int ns, int KR, int Dpad, const double* camrec, const double* shared_in,
+                       double* Sraw, double* rhs, double* hdiag, double* gvec, cudaStream_t st) {
+  assemble_hc_kernel<<<S + (ns > 0 ? 1 : 0), 64, 0, st>>>(S, dc, ns, KR, Dpad, camrec, shared_in, Sraw, rhs, hdiag, gvec);
+  VGG_LAUNCH_CHECK();
+  return VGG_OK;
+}
+int launch_z_transpose(int D, int N, int Dpad, const double* W, const double* M, const double* q, double* Zt,
+                       double* rhs, cudaStream_t st) {
+  dim3 grid((D + 31) / 32, (N + 31) / 32), block(32, 8);
+  z_transpose_kernel<<<grid, block, 0, st>>>(D, N, Dpad, W, M, q, Zt, rhs);
+  VGG_LAUNCH_CHECK();
+  return VGG_OK;
+}
+int launch_syrk(int Kpad, int Dpad, const double* Zt, double* Cmat, cudaStream_t st) {
+  const int nb = Dpad / SY_BM;
+  const int ntiles = nb * (nb + 1) / 2;
+  const int nslab = Kpad / SY_BK;
+  // split K so that the grid covers the 148 SMs a few times over
+  int splits = (148 * 3 + ntiles - 1) / ntiles;
+  if (splits < 1) splits = 1;
+  if (splits > nslab) splits = nslab;
+  int slabs_per = (nslab + splits - 1) / splits;
+  splits = (nslab + slabs_per - 1) / slabs_per;
+  const size_t smem = sizeof(double) * 2 * SY_STAGES * SY_BK * SY_BM;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VGG_CUDA_CHECK(cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  dim3 grid(ntiles, splits);
+  syrk_kernel<<<grid, SY_THREADS, smem, st>>>(Kpad, Dpad, slabs_per * SY_BK, Zt, Cmat);
+  VGG_LAUNCH_CHECK();
+  return VGG_OK;
+}
+int launch_scale_damp(int D, int Dpad, double* A, const double* rhs, const double* hdiag, const double* sc,
+                      const uint8_t* pconst, double radius, double min_diag, double max_diag, double* bvec,
+                      cudaStream_t st) {
+  dim3 grid((D + 255) / 256, D);
+  scale_damp_kernel<<<grid, 256, 0, st>>>(D, Dpad, A, rhs, hdiag, sc, pconst, radius, min_diag, max_diag, bvec);
+  VGG_LAUNCH_CHECK();
+  return VGG_OK;
+}
+int launch_cam_step(int D, const double* dcs, const double* sc, const double* hdiag, const double* gvec,
+                    const uint8_t* pconst, double radius, double min_diag, double max_diag, double* d_c, double* scal,
+                    cudaStream_t st) {
+  cam_step_kernel<<<(D + 255) / 256, 256, 0, st>>>(D, dcs, sc, hdiag, gvec, pconst, radius, min_diag, max_diag, d_c, scal);
+  VGG_LAUNCH_CHECK();
+  return VGG_OK;
+}
+int launch_backsub(int D, int N, const double* W, const double* d_c, double* wacc, cudaStream_t st) {
+  VGG_CUDA_CHECK(cudaMemsetAsync(wacc, 0, sizeof(double) * (size_t)N * 3, st));
+  const int nb = (N + 127) / 128;
+  int chunks = (148 * 4 + nb - 1) / nb;
+  if (chunks > D) chunks = D;
+  if (chunks < 1) chunks = 1;
+  int rows_per = (D + chunks - 1) / chunks;
+  chunks = (D + rows_per - 1) / rows_per;
+  dim3 grid(nb, chunks);
+  backsub_partial_kernel<<<grid, 128, sizeof(double) * rows_per, st>>>(D, N, rows_per, W, d_c, wacc);
+  VGG_LAUNCH_CHECK();
+  return VGG_OK;
+}
+int launch_point_step(int N, const double* M, const double* g_p, const double* wacc, const double* sc_p,
+                      const double* dpp, const double* X, double radius, double* Xc, double* scal, cudaStream_t st) {
+  point_step_kernel<<<(N + 127) / 128, 128, 0, st>>>(N, M, g_p, wacc, sc_p, dpp, X, radius, Xc, scal);
+  VGG_LAUNCH_CHECK();
+  return VGG_OK;
+}
+int launch_cam_update(int S, int dc, int ns, int model, const double* d_c, const double* poses, const double* intr,
+                      double* poses_c, double* intr_c, cudaStream_t st) {
+  cam_update_kernel<<<(S + 127) / 128, 128, 0, st>>>(S, dc, ns, model, d_c, poses, intr, poses_c, intr_c);
+  VGG_LAUNCH_CHECK();
+  return VGG_OK;
+}
+int launch_extract_gvec(int S, int dc, int ns, int KR, const double* camrec, const double* shared_in, double* gvec,
+                        cudaStream_t st) {
+  const int D = S * dc + ns;
+  extract_gvec_kernel<<<(D + 255) / 256, 256, 0, st>>>(S, dc, ns, KR, camrec, shared_in, gvec);
+  VGG_LAUNCH_CHECK();
+  return VGG_OK;
+}
+int launch_gradmax(int D, int N, const double* gvec, const uint8_t* pconst, const double* g_p,
+                   const uint8_t* point_const, double* scal, cudaStream_t st) {
+  const int n = D > N * 3 ? D : N * 3;
+  gradmax_kernel<<<(n + 255) / 256, 256, 0, st>>>(D, N, gvec, pconst, g_p, point_const, scal);
+  VGG_LAUNCH_CHECK();
+  return VGG_OK;
+}
+
+}  // namespace vgg

@@ -1,0 +1,477 @@
+// Levenberg-Marquardt driver (Ceres TrustRegionMinimizer + LevenbergMarquardtStrategy semantics) and
+// the C-ABI entry points of the bundle-adjustment path.  The loop body is ~14 kernel launches per
+// iteration on one stream and ONE small device->host read (accept/reject scalars); track shards on
+// other GPUs join through the caller's all-reduce hook (NCCL over NVLink, see vggsfm_b200/dist.py).
+#include <cusolverDn.h>
+#include <math.h>
+#include <string.h>
+#include <vector>
+#include "common.cuh"
+
+namespace vgg {
+
+static thread_local char g_err[512] = "";
+thread_local long long g_launch_count = 0;
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+// kernels (ba_blocks.cu / ba_schur.cu)
+int ba_build_blocks(const vgg_ba_problem* p, double* cost, double* camrec, double* g_p, double* H_pp, double* W,
+                    double* shared_out, int frames_per_cta, cudaStream_t stream);
+int launch_jacobi_scale_points(int N, const double* H_pp, double* sc_p, int enable, cudaStream_t st);
+int launch_jacobi_scale_cams(int D, const double* hdiag, double* sc_c, int enable, cudaStream_t st);
+int launch_point_prep(int N, const double* H_pp, const double* g_p, const double* sc_p, const uint8_t* point_const,
+                      double radius, double min_diag, double max_diag, double* M, double* q, double* dpp,
+                      double* scal, cudaStream_t st);
+int launch_assemble_hc(int S, int dc, int ns, int KR, int Dpad, const double* camrec, const double* shared_in,
+                       double* Sraw, double* rhs, double* hdiag, double* gvec, cudaStream_t st);
+int launch_z_transpose(int D, int N, int Dpad, const double* W, const double* M, const double* q, double* Zt,
+                       double* rhs, cudaStream_t st);
+int launch_syrk(int Kpad, int Dpad, const double* Zt, double* Cmat, cudaStream_t st);
+int launch_scale_damp(int D, int Dpad, double* A, const double* rhs, const double* hdiag, const double* sc,
+                      const uint8_t* pconst, double radius, double min_diag, double max_diag, double* bvec,
+                      cudaStream_t st);
+int launch_cam_step(int D, const double* dcs, const double* sc, const double* hdiag, const double* gvec,
+                    const uint8_t* pconst, double radius, double min_diag, double max_diag, double* d_c, double* scal,
+                    cudaStream_t st);
+int launch_backsub(int D, int N, const double* W, const double* d_c, double* wacc, cudaStream_t st);
+int launch_point_step(int N, const double* M, const double* g_p, const double* wacc, const double* sc_p,
+                      const double* dpp, const double* X, double radius, double* Xc, double* scal, cudaStream_t st);
+int launch_cam_update(int S, int dc, int ns, int model, const double* d_c, const double* poses, const double* intr,
+                      double* poses_c, double* intr_c, cudaStream_t st);
+int launch_extract_gvec(int S, int dc, int ns, int KR, const double* camrec, const double* shared_in, double* gvec,
+                        cudaStream_t st);
+int launch_gradmax(int D, int N, const double* gvec, const uint8_t* pconst, const double* g_p,
+                   const uint8_t* point_const, double* scal, cudaStream_t st);
+
+static int dims_of(int model, int mode, int* dc, int* ns, int* KR) {
+  if (model != VGG_SIMPLE_PINHOLE && model != VGG_SIMPLE_RADIAL) return VGG_EINVAL;
+  const int ni = model == VGG_SIMPLE_PINHOLE ? 1 : 2;
+  int d, n;
+  if (mode == VGG_INTR_CONST) { d = 6; n = 0; }
+  else if (mode == VGG_INTR_PER_FRAME) { d = 6 + ni; n = 0; }
+  else if (mode == VGG_INTR_SHARED) { d = 6; n = ni; }
+  else return VGG_EINVAL;
+  if (dc) *dc = d;
+  if (ns) *ns = n;
+  if (KR) *KR = d + d * (d + 1) / 2 + 6 * n;
+  return VGG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// workspace layout
+// ------------------------------------------------------------------------------------------------
+struct BlockSet {
+  double *cost, *camrec, *g_p, *H_pp, *W, *shared;
+};
+struct Layout {
+  int S, N, dc, ns, KR, D, Dpad, Kpad;
+  BlockSet blk[2];
+  double *poses[2], *intr[2], *points[2];
+  double *sc_c, *sc_p, *M, *q, *dpp, *wacc, *d_c, *bvec, *Zt;
+  double *AR;        // [D*Dpad | rhs Dpad | hdiag Dpad | gvec Dpad]  (one all-reduce)
+  double *small;     // [8 scalars | gvec_candidate Dpad]           (one small all-reduce)
+  double *scal;      // [16]
+  double *potrf_work;
+  int *dev_info;
+  size_t potrf_lwork;
+  size_t bytes;
+};
+
+static int make_layout(int S, int N, int model, int mode, void* base, size_t cap, size_t potrf_lwork, Layout* L) {
+  int dc, ns, KR;
+  if (dims_of(model, mode, &dc, &ns, &KR) != VGG_OK) {
+    set_error("bad camera_model/intr_mode");
+    return VGG_EINVAL;
+  }
+  L->S = S; L->N = N; L->dc = dc; L->ns = ns; L->KR = KR;
+  L->D = S * dc + ns;
+  L->Dpad = (int)align_up(L->D, 128);
+  L->Kpad = (int)align_up((size_t)3 * N, 16);
+  Carver c(base, cap);
+  for (int b = 0; b < 2; ++b) {
+    L->blk[b].cost = c.take<double>(8);
+    L->blk[b].shared = c.take<double>(8);
+    L->blk[b].camrec = c.take<double>((size_t)S * KR);
+    L->blk[b].g_p = c.take<double>((size_t)N * 3);
+    L->blk[b].H_pp = c.take<double>((size_t)N * 6);
+    L->blk[b].W = c.take<double>((size_t)L->D * N * 3);
+    L->poses[b] = c.take<double>((size_t)S * 12);
+    L->intr[b] = c.take<double>((size_t)S * 4);
+    L->points[b] = c.take<double>((size_t)N * 3);
+  }
+  L->sc_c = c.take<double>(L->Dpad);
+  L->sc_p = c.take<double>((size_t)N * 3);
+  L->M = c.take<double>((size_t)N * 9);
+  L->q = c.take<double>((size_t)N * 3);
+  L->dpp = c.take<double>((size_t)N * 3);
+  L->wacc = c.take<double>((size_t)N * 3);
+  L->d_c = c.take<double>(L->Dpad);
+  L->bvec = c.take<double>(L->Dpad);
+  L->Zt = c.take<double>((size_t)L->Kpad * L->Dpad);
+  L->AR = c.take<double>((size_t)L->D * L->Dpad + 3 * (size_t)L->Dpad);
+  L->small = c.take<double>(8 + (size_t)L->Dpad);
+  L->scal = c.take<double>(16);
+  L->potrf_lwork = potrf_lwork;
+  L->potrf_work = c.take<double>(potrf_lwork);
+  L->dev_info = c.take<int>(4);
+  L->bytes = align_up(c.off, 256);
+  if (base && c.off > cap) {
+    set_error("workspace too small: need %zu bytes, have %zu", c.off, cap);
+    return VGG_EWORKSPACE;
+  }
+  return VGG_OK;
+}
+
+static cusolverDnHandle_t get_cusolver() {
+  static thread_local cusolverDnHandle_t h = nullptr;
+  if (!h) {
+    if (cusolverDnCreate(&h) != CUSOLVER_STATUS_SUCCESS) h = nullptr;
+  }
+  return h;
+}
+
+static int potrf_lwork(int D, int Dpad, size_t* lwork) {
+  cusolverDnHandle_t h = get_cusolver();
+  if (!h) {
+    set_error("cusolverDnCreate failed");
+    return VGG_ESOLVER;
+  }
+  int lw = 0;
+  if (cusolverDnDpotrf_bufferSize(h, CUBLAS_FILL_MODE_UPPER, D, nullptr, Dpad, &lw) != CUSOLVER_STATUS_SUCCESS) {
+    set_error("cusolverDnDpotrf_bufferSize failed");
+    return VGG_ESOLVER;
+  }
+  *lwork = (size_t)lw;
+  return VGG_OK;
+}
+
+// Schur complement of blk onto AR (Sraw, rhs, hdiag, gvec) at the given radius
+static int schur_build(const Layout& L, const BlockSet& b, const uint8_t* point_const, double radius, double min_diag,
+                       double max_diag, cudaStream_t st) {
+  int rc;
+  double* Sraw = L.AR;
+  double* rhs = L.AR + (size_t)L.D * L.Dpad;
+  double* hdiag = rhs + L.Dpad;
+  double* gvec = hdiag + L.Dpad;
+  if ((rc = launch_point_prep(L.N, b.H_pp, b.g_p, L.sc_p, point_const, radius, min_diag, max_diag, L.M, L.q, L.dpp,
+                              L.scal, st)))
+    return rc;
+  VGG_CUDA_CHECK(cudaMemsetAsync(L.AR, 0, sizeof(double) * ((size_t)L.D * L.Dpad + 3 * (size_t)L.Dpad), st));
+  if ((rc = launch_assemble_hc(L.S, L.dc, L.ns, L.KR, L.Dpad, b.camrec, b.shared, Sraw, rhs, hdiag, gvec, st))) return rc;
+  if ((rc = launch_z_transpose(L.D, L.N, L.Dpad, b.W, L.M, L.q, L.Zt, rhs, st))) return rc;
+  if ((rc = launch_syrk(L.Kpad, L.Dpad, L.Zt, Sraw, st))) return rc;
+  return VGG_OK;
+}
+
+}  // namespace vgg
+
+using namespace vgg;
+
+extern "C" {
+
+const char* vgg_last_error(void) { return g_err; }
+int vgg_version(void) { return 100; }
+
+void vgg_ba_default_options(vgg_ba_options* o) {
+  memset(o, 0, sizeof(*o));
+  o->max_num_iterations = 100;
+  o->max_num_consecutive_invalid_steps = 10;
+  o->jacobi_scaling = 1;
+  o->function_tolerance = 0.0;
+  o->gradient_tolerance = 1e-4;
+  o->parameter_tolerance = 0.0;
+  o->initial_trust_region_radius = 1e4;
+  o->max_trust_region_radius = 1e16;
+  o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6;
+  o->max_lm_diagonal = 1e32;
+}
+
+int vgg_ba_dims(int camera_model, int intr_mode, int* dc, int* ns) {
+  return dims_of(camera_model, intr_mode, dc, ns, nullptr);
+}
+
+int vgg_ba_camrec_len(int camera_model, int intr_mode) {
+  int KR = 0;
+  if (dims_of(camera_model, intr_mode, nullptr, nullptr, &KR) != VGG_OK) return VGG_EINVAL;
+  return KR;
+}
+
+int vgg_ba_workspace_bytes(int S, int N, int camera_model, int intr_mode, size_t* bytes) {
+  VGG_REQUIRE(S > 0 && N > 0 && bytes, "S, N must be positive");
+  int dc, ns;
+  if (dims_of(camera_model, intr_mode, &dc, &ns, nullptr) != VGG_OK) {
+    set_error("bad camera_model/intr_mode");
+    return VGG_EINVAL;
+  }
+  const int D = S * dc + ns;
+  size_t lwork = 0;
+  int rc = potrf_lwork(D, (int)align_up(D, 128), &lwork);
+  if (rc) return rc;
+  Layout L;
+  rc = make_layout(S, N, camera_model, intr_mode, nullptr, 0, lwork, &L);
+  if (rc) return rc;
+  *bytes = L.bytes;
+  return VGG_OK;
+}
+
+int vgg_ba_build_blocks(const vgg_ba_problem* prob, double* cost, double* camrec, double* g_p, double* H_pp, double* W,
+                        double* shared_out, int frames_per_cta, void* stream) {
+  VGG_REQUIRE(prob && cost && camrec && g_p && H_pp && W && shared_out, "null pointer");
+  g_launch_count = 0;
+  return ba_build_blocks(prob, cost, camrec, g_p, H_pp, W, shared_out, frames_per_cta, (cudaStream_t)stream);
+}
+
+int vgg_ba_schur(const vgg_ba_problem* prob, const double* camrec, const double* g_p, const double* H_pp,
+                 const double* W, const double* shared_in, const double* scale_p, double radius, double min_diag,
+                 double max_diag, void* workspace, size_t ws_bytes, double* Sraw, double* rhs, int* Dpad_out,
+                 void* stream) {
+  VGG_REQUIRE(prob && workspace && Sraw && rhs, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  g_launch_count = 0;
+  size_t lwork = 0;
+  int dc, ns;
+  dims_of(prob->camera_model, prob->intr_mode, &dc, &ns, nullptr);
+  int rc = potrf_lwork(prob->S * dc + ns, (int)align_up(prob->S * dc + ns, 128), &lwork);
+  if (rc) return rc;
+  Layout L;
+  rc = make_layout(prob->S, prob->N, prob->camera_model, prob->intr_mode, workspace, ws_bytes, lwork, &L);
+  if (rc) return rc;
+  BlockSet b;
+  b.cost = nullptr;
+  b.camrec = const_cast<double*>(camrec);
+  b.g_p = const_cast<double*>(g_p);
+  b.H_pp = const_cast<double*>(H_pp);
+  b.W = const_cast<double*>(W);
+  b.shared = const_cast<double*>(shared_in);
+  VGG_CUDA_CHECK(cudaMemcpyAsync(L.sc_p, scale_p, sizeof(double) * (size_t)L.N * 3, cudaMemcpyDeviceToDevice, st));
+  VGG_CUDA_CHECK(cudaMemsetAsync(L.Zt, 0, sizeof(double) * (size_t)L.Kpad * L.Dpad, st));
+  VGG_CUDA_CHECK(cudaMemsetAsync(L.scal, 0, sizeof(double) * 16, st));
+  rc = schur_build(L, b, prob->point_const, radius, min_diag, max_diag, st);
+  if (rc) return rc;
+  VGG_CUDA_CHECK(cudaMemcpyAsync(Sraw, L.AR, sizeof(double) * (size_t)L.D * L.Dpad, cudaMemcpyDeviceToDevice, st));
+  VGG_CUDA_CHECK(cudaMemcpyAsync(rhs, L.AR + (size_t)L.D * L.Dpad, sizeof(double) * L.Dpad, cudaMemcpyDeviceToDevice, st));
+  if (Dpad_out) *Dpad_out = L.Dpad;
+  return VGG_OK;
+}
+
+int vgg_ba_solve(const vgg_ba_problem* prob, const vgg_ba_options* opt_in, void* workspace, size_t ws_bytes,
+                 vgg_allreduce_fn allreduce, void* ar_user, vgg_ba_summary* summary, double* trace, void* stream) {
+  VGG_REQUIRE(prob && workspace && summary, "null pointer");
+  VGG_REQUIRE(prob->uv && prob->mask && prob->param_const && prob->poses && prob->intr && prob->points, "null problem array");
+  cudaStream_t st = (cudaStream_t)stream;
+  g_launch_count = 0;
+  vgg_ba_options opt;
+  if (opt_in) opt = *opt_in;
+  else vgg_ba_default_options(&opt);
+  const int S = prob->S, N = prob->N;
+  int dc, ns;
+  if (dims_of(prob->camera_model, prob->intr_mode, &dc, &ns, nullptr) != VGG_OK) {
+    set_error("bad camera_model/intr_mode");
+    return VGG_EINVAL;
+  }
+  const int D = S * dc + ns;
+  size_t lwork = 0;
+  int rc = potrf_lwork(D, (int)align_up(D, 128), &lwork);
+  if (rc) return rc;
+  Layout L;
+  rc = make_layout(S, N, prob->camera_model, prob->intr_mode, workspace, ws_bytes, lwork, &L);
+  if (rc) return rc;
+  cusolverDnHandle_t cs = get_cusolver();
+  if (cusolverDnSetStream(cs, st) != CUSOLVER_STATUS_SUCCESS) {
+    set_error("cusolverDnSetStream failed");
+    return VGG_ESOLVER;
+  }
+  double* Sraw = L.AR;
+  double* rhs = L.AR + (size_t)D * L.Dpad;
+  double* hdiag = rhs + L.Dpad;
+  double* gvec = hdiag + L.Dpad;
+  const size_t ar_count = (size_t)D * L.Dpad + 3 * (size_t)L.Dpad;
+
+  cudaEvent_t ev0, ev1;
+  VGG_CUDA_CHECK(cudaEventCreate(&ev0));
+  VGG_CUDA_CHECK(cudaEventCreate(&ev1));
+  VGG_CUDA_CHECK(cudaEventRecord(ev0, st));
+
+  int cur = 0;
+  VGG_CUDA_CHECK(cudaMemcpyAsync(L.poses[0], prob->poses, sizeof(double) * (size_t)S * 12, cudaMemcpyDeviceToDevice, st));
+  VGG_CUDA_CHECK(cudaMemcpyAsync(L.intr[0], prob->intr, sizeof(double) * (size_t)S * 4, cudaMemcpyDeviceToDevice, st));
+  VGG_CUDA_CHECK(cudaMemcpyAsync(L.points[0], prob->points, sizeof(double) * (size_t)N * 3, cudaMemcpyDeviceToDevice, st));
+  VGG_CUDA_CHECK(cudaMemsetAsync(L.Zt, 0, sizeof(double) * (size_t)L.Kpad * L.Dpad, st));
+  VGG_CUDA_CHECK(cudaMemsetAsync(L.d_c, 0, sizeof(double) * L.Dpad, st));
+
+  auto eval = [&](int which) -> int {
+    vgg_ba_problem p = *prob;
+    p.poses = L.poses[which];
+    p.intr = L.intr[which];
+    p.points = L.points[which];
+    const BlockSet& b = L.blk[which];
+    return ba_build_blocks(&p, b.cost, b.camrec, b.g_p, b.H_pp, b.W, b.shared, 0, st);
+  };
+  // global cost + gradient max-norm of block set `which`; result lands in host h[0..2] = cost, gmax_c, gmax_p
+  double h_scal[16];
+  auto cost_and_gradient = [&](int which, double* cost_out, double* gmax_out) -> int {
+    const BlockSet& b = L.blk[which];
+    int r;
+    VGG_CUDA_CHECK(cudaMemsetAsync(L.small, 0, sizeof(double) * (8 + (size_t)L.Dpad), st));
+    VGG_CUDA_CHECK(cudaMemcpyAsync(L.small, b.cost, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if ((r = launch_extract_gvec(S, dc, ns, L.KR, b.camrec, b.shared, L.small + 8, st))) return r;
+    if (allreduce && (r = allreduce(ar_user, L.small, 8 + (size_t)L.Dpad, 0, st))) return r;
+    VGG_CUDA_CHECK(cudaMemsetAsync(L.scal + 4, 0, sizeof(double) * 2, st));
+    if ((r = launch_gradmax(D, N, L.small + 8, prob->param_const, b.g_p, prob->point_const, L.scal, st))) return r;
+    if (allreduce && (r = allreduce(ar_user, L.scal + 5, 1, 1, st))) return r;
+    VGG_CUDA_CHECK(cudaMemcpyAsync(h_scal, L.scal, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
+    VGG_CUDA_CHECK(cudaMemcpyAsync(h_scal + 8, L.small, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
+    VGG_CUDA_CHECK(cudaStreamSynchronize(st));
+    *cost_out = h_scal[8];
+    *gmax_out = fmax(h_scal[4], h_scal[5]);
+    return VGG_OK;
+  };
+
+  if ((rc = eval(cur))) return rc;
+  if ((rc = launch_jacobi_scale_points(N, L.blk[cur].H_pp, L.sc_p, opt.jacobi_scaling, st))) return rc;
+  double cost = 0, gmax = 0;
+  if ((rc = cost_and_gradient(cur, &cost, &gmax))) return rc;
+
+  memset(summary, 0, sizeof(*summary));
+  summary->initial_cost = cost;
+  summary->termination = VGG_BA_NO_CONVERGENCE;
+  double radius = opt.initial_trust_region_radius;
+  double decrease_factor = 2.0;
+  int it = 0, invalid_steps = 0;
+  bool have_scale_c = false;
+  bool done = gmax <= opt.gradient_tolerance;
+  if (done) summary->termination = VGG_BA_CONVERGENCE_GRADIENT;
+
+  while (!done) {
+    if (it >= opt.max_num_iterations) break;
+    if (radius < opt.min_trust_region_radius) {
+      summary->termination = VGG_BA_MIN_TRUST_REGION;
+      break;
+    }
+    ++it;
+    const int cand = cur ^ 1;
+    VGG_CUDA_CHECK(cudaMemsetAsync(L.scal, 0, sizeof(double) * 16, st));
+    if ((rc = schur_build(L, L.blk[cur], prob->point_const, radius, opt.min_lm_diagonal, opt.max_lm_diagonal, st))) return rc;
+    if (allreduce && (rc = allreduce(ar_user, L.AR, ar_count, 0, st))) return rc;
+    if (!have_scale_c) {
+      if ((rc = launch_jacobi_scale_cams(D, hdiag, L.sc_c, opt.jacobi_scaling, st))) return rc;
+      have_scale_c = true;
+    }
+    if ((rc = launch_scale_damp(D, L.Dpad, Sraw, rhs, hdiag, L.sc_c, prob->param_const, radius, opt.min_lm_diagonal,
+                                opt.max_lm_diagonal, L.bvec, st)))
+      return rc;
+    // row-major lower == column-major upper
+    if (cusolverDnDpotrf(cs, CUBLAS_FILL_MODE_UPPER, D, Sraw, L.Dpad, L.potrf_work, (int)L.potrf_lwork, L.dev_info) !=
+        CUSOLVER_STATUS_SUCCESS) {
+      set_error("cusolverDnDpotrf failed to launch");
+      return VGG_ESOLVER;
+    }
+    if (cusolverDnDpotrs(cs, CUBLAS_FILL_MODE_UPPER, D, 1, Sraw, L.Dpad, L.bvec, L.Dpad, L.dev_info + 1) !=
+        CUSOLVER_STATUS_SUCCESS) {
+      set_error("cusolverDnDpotrs failed to launch");
+      return VGG_ESOLVER;
+    }
+    g_launch_count += 2;
+    if ((rc = launch_cam_step(D, L.bvec, L.sc_c, hdiag, gvec, prob->param_const, radius, opt.min_lm_diagonal,
+                              opt.max_lm_diagonal, L.d_c, L.scal, st)))
+      return rc;
+    if ((rc = launch_backsub(D, N, L.blk[cur].W, L.d_c, L.wacc, st))) return rc;
+    if ((rc = launch_point_step(N, L.M, L.blk[cur].g_p, L.wacc, L.sc_p, L.dpp, L.points[cur], radius, L.points[cand],
+                                L.scal, st)))
+      return rc;
+    if ((rc = launch_cam_update(S, dc, ns, prob->camera_model, L.d_c, L.poses[cur], L.intr[cur], L.poses[cand],
+                                L.intr[cand], st)))
+      return rc;
+    if ((rc = eval(cand))) return rc;
+    // point-side model terms join the candidate cost in the small all-reduce
+    VGG_CUDA_CHECK(cudaMemsetAsync(L.small, 0, sizeof(double) * (8 + (size_t)L.Dpad), st));
+    VGG_CUDA_CHECK(cudaMemcpyAsync(L.small, L.blk[cand].cost, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    VGG_CUDA_CHECK(cudaMemcpyAsync(L.small + 1, L.scal + 2, sizeof(double) * 2, cudaMemcpyDeviceToDevice, st));
+    VGG_CUDA_CHECK(cudaMemcpyAsync(L.small + 3, L.scal + 6, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    if ((rc = launch_extract_gvec(S, dc, ns, L.KR, L.blk[cand].camrec, L.blk[cand].shared, L.small + 8, st))) return rc;
+    if (allreduce && (rc = allreduce(ar_user, L.small, 8 + (size_t)L.Dpad, 0, st))) return rc;
+    if ((rc = launch_gradmax(D, N, L.small + 8, prob->param_const, L.blk[cand].g_p, prob->point_const, L.scal, st))) return rc;
+    if (allreduce && (rc = allreduce(ar_user, L.scal + 5, 1, 1, st))) return rc;
+    int h_info[2] = {0, 0};
+    VGG_CUDA_CHECK(cudaMemcpyAsync(h_scal, L.scal, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
+    VGG_CUDA_CHECK(cudaMemcpyAsync(h_scal + 8, L.small, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
+    VGG_CUDA_CHECK(cudaMemcpyAsync(h_info, L.dev_info, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
+    VGG_CUDA_CHECK(cudaStreamSynchronize(st));
+
+    const double c_cost = h_scal[8];
+    const double quad = h_scal[0] + h_scal[9];
+    const double step_norm = sqrt(h_scal[1] + h_scal[10]);
+    const double model_change = 0.5 * quad;
+    const bool solver_bad = h_info[0] != 0 || h_info[1] != 0 || h_scal[7] > 0 || h_scal[11] > 0;
+    double* tr = trace ? trace + (size_t)(it - 1) * 8 : nullptr;
+    if (tr) {
+      tr[0] = it; tr[1] = cost; tr[2] = c_cost; tr[3] = model_change; tr[4] = 0; tr[5] = radius; tr[6] = step_norm; tr[7] = 0;
+    }
+    if (solver_bad || !(model_change > 0.0) || !isfinite(c_cost)) {
+      // Ceres: invalid step -> LevenbergMarquardtStrategy::StepIsInvalid
+      ++invalid_steps;
+      if (tr) tr[7] = 2;
+      if (invalid_steps >= opt.max_num_consecutive_invalid_steps) {
+        summary->termination = VGG_BA_FAILURE;
+        break;
+      }
+      radius *= 0.5;
+      continue;
+    }
+    invalid_steps = 0;
+    const double cost_change = cost - c_cost;
+    const double rho = cost_change / model_change;
+    if (tr) tr[4] = rho;
+    if (step_norm <= opt.parameter_tolerance * opt.parameter_tolerance) {
+      summary->termination = VGG_BA_CONVERGENCE_PARAMETER;
+      break;
+    }
+    const bool success = rho > opt.min_relative_decrease;
+    if (fabs(cost_change) <= opt.function_tolerance * cost) {
+      if (success) { cur = cand; cost = c_cost; }
+      summary->termination = VGG_BA_CONVERGENCE_FUNCTION;
+      break;
+    }
+    if (success) {
+      cur = cand;
+      cost = c_cost;
+      summary->successful++;
+      if (tr) tr[7] = 1;
+      radius = fmin(opt.max_trust_region_radius, radius / fmax(1.0 / 3.0, 1.0 - pow(2.0 * rho - 1.0, 3.0)));
+      decrease_factor = 2.0;
+      gmax = fmax(h_scal[4], h_scal[5]);
+      if (gmax <= opt.gradient_tolerance) {
+        summary->termination = VGG_BA_CONVERGENCE_GRADIENT;
+        break;
+      }
+    } else {
+      radius = radius / decrease_factor;
+      decrease_factor *= 2.0;
+    }
+  }
+
+  VGG_CUDA_CHECK(cudaMemcpyAsync(prob->poses, L.poses[cur], sizeof(double) * (size_t)S * 12, cudaMemcpyDeviceToDevice, st));
+  VGG_CUDA_CHECK(cudaMemcpyAsync(prob->intr, L.intr[cur], sizeof(double) * (size_t)S * 4, cudaMemcpyDeviceToDevice, st));
+  VGG_CUDA_CHECK(cudaMemcpyAsync(prob->points, L.points[cur], sizeof(double) * (size_t)N * 3, cudaMemcpyDeviceToDevice, st));
+  VGG_CUDA_CHECK(cudaEventRecord(ev1, st));
+  VGG_CUDA_CHECK(cudaEventSynchronize(ev1));
+  float ms = 0;
+  VGG_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  summary->iterations = it;
+  summary->final_cost = cost;
+  summary->final_radius = radius;
+  summary->device_ms = ms;
+  summary->kernel_launches = g_launch_count;
+  return VGG_OK;
+}
+
+}  // extern "C"

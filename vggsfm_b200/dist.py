@@ -1,0 +1,76 @@
+"""Track sharding and the per-iteration all-reduce of the reduced camera system.
+
+The reference has no distributed code; this is new.  One process per GPU:
+every rank holds all S cameras and a contiguous slice of the N tracks; point blocks, coupling blocks
+and the Schur products are local; the reduced system [D x Dpad | rhs | diag | g] is summed across
+ranks once per LM iteration (NCCL over NVLink 5 / NVSwitch), after which every rank factors the same
+small system redundantly and back-substitutes its own points.  A second, tiny all-reduce carries the
+candidate cost and gradient so all ranks take the same accept/reject decision.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _lib
+
+
+def shard_range(N: int, rank: int, world: int, multiple: int = 16):
+    """Contiguous [lo, hi) slice of the track axis for `rank`; slices are multiples of `multiple`
+    (TMA alignment) except the last.  Mirrors torch.chunk's contiguous split of
+    vggsfm/utils/triangulation.py:721-733."""
+    per = (N + world - 1) // world
+    per = (per + multiple - 1) // multiple * multiple
+    lo = min(N, rank * per)
+    hi = min(N, lo + per)
+    return lo, hi
+
+
+class AllReduceHook:
+    """vgg_allreduce_fn implemented with torch.distributed on views of the solver workspace."""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.calls = 0
+        self.bytes = 0
+        self._ws = None
+        self._cb = None
+
+    def bind(self, ws: torch.Tensor):
+        self._ws = ws
+        base = ws.data_ptr()
+
+        def _fn(user, buf, count, op, stream):
+            try:
+                off = buf - base
+                view = self._ws[off:off + count * 8].view(torch.float64)
+                dist.all_reduce(view, op=dist.ReduceOp.SUM if op == 0 else dist.ReduceOp.MAX, group=self.group)
+                self.calls += 1
+                self.bytes += count * 8
+                return 0
+            except Exception as e:  # surfaces as rc != 0 -> RuntimeError on the Python side
+                print(f"[vggsfm_b200.dist] all_reduce failed: {e}", flush=True)
+                return -2
+
+        self._cb = _lib.ALLREDUCE_FN(_fn)
+        return self._cb
+
+
+class HostAllReduce:
+    """numpy all-reduce with .sum/.max for the oracle's lm_solve (gloo tests of the sharding algebra)."""
+
+    def __init__(self, group=None):
+        self.group = group
+
+    def sum(self, arr):
+        import numpy as np
+        t = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float64).copy())
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t.numpy().reshape(arr.shape)
+
+    def max(self, value):
+        t = torch.tensor([float(value)], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+        return float(t[0])
