@@ -117,6 +117,53 @@ int vgg_ba_solve(const vgg_ba_problem* prob, const vgg_ba_options* opt, void* wo
                  size_t ws_bytes, vgg_allreduce_fn allreduce, void* allreduce_user,
                  vgg_ba_summary* summary, double* trace, void* stream);
 
+/* ------------------------------------------------------------------------------------------- */
+/* Triangulation side (float64, like the reference's real pipeline: models/triangulator.py:91) */
+/* ------------------------------------------------------------------------------------------- */
+
+/* triangulate_tracks / triangulate_tracks_single_chunk (vggsfm/utils/triangulation.py:677-956):
+ * fused LORANSAC.  extrinsics [S,12]; tracks_normalized double [S,N,2]; track_vis/track_score float
+ * [S,N] (score may be NULL); pairs int32 [H0,2] = the hypothesis frame pairs drawn on the host exactly
+ * like triangulation.py:804-813 (CPU torch.randperm).  Outputs: points double [N,3], inlier_num
+ * int64 [N], inlier_mask uint8 [N,S]. */
+int vgg_tri_workspace_bytes(int S, int N, int H0, int lo_num, size_t* bytes);
+int vgg_triangulate_tracks(int S, int N, const double* extrinsics, const double* tracks_normalized,
+                           const float* track_vis, const float* track_score, const int32_t* pairs, int H0,
+                           int lo_num, double max_angular_error_deg, double min_tri_angle_deg, double* out_points,
+                           int64_t* out_inlier_num, uint8_t* out_inlier_mask, void* workspace, size_t ws_bytes,
+                           void* stream);
+
+/* triangulate_by_pair (triangulation.py:45-135): frame 0 against frames 1..S-1.  Outputs [S-1,N,3],
+ * cheirality uint8 [S-1,N] (1 = in front of both), angle double [S-1,N] degrees.  workspace >= S*24 B. */
+int vgg_triangulate_by_pair(int S, int N, const double* extrinsics, const double* tracks_normalized,
+                            double* out_points, uint8_t* out_cheirality, double* out_angle_deg, void* workspace,
+                            size_t ws_bytes, void* stream);
+
+/* filter_all_points3D / _single_chunk (vggsfm/utils/triangulation_helpers.py:133-307).  points2d is
+ * float or double [S,P,2]; intrinsics9 [S,9] row-major K; extra_params [S] SIMPLE_RADIAL k or NULL;
+ * out_valid uint8 [P]; out_detail uint8 [S,P] or NULL (return_detail).  workspace >= S*24 B. */
+int vgg_filter_points3d(int S, int P, const double* points3d, const void* points2d, int points2d_is_f64,
+                        const double* extrinsics, const double* intrinsics9, const double* extra_params,
+                        double max_reproj_error, double min_tri_angle_deg, int check_triangle, double hard_max,
+                        uint8_t* out_valid, uint8_t* out_detail, void* workspace, size_t ws_bytes, void* stream);
+
+/* project_3D_points / img_from_cam (triangulation_helpers.py:311-395): out_points2d [S,P,2] and/or
+ * out_points_cam [S,3,P] (either may be NULL). */
+int vgg_project_points(int S, int P, const double* points3d, const double* extrinsics, const double* intrinsics9,
+                       const double* extra_params, double* out_points2d, double* out_points_cam, void* stream);
+
+/* cam_from_img without distortion (triangulation_helpers.py:398-428): (uv - pp)/f in the input
+ * precision (is_f64 selects float/double for tracks, focal2 [S,2], pp2 [S,2] and out). */
+int vgg_normalize_tracks(int S, int N, const void* tracks, const void* focal2, const void* pp2, int is_f64, void* out,
+                         void* stream);
+
+/* iterative_undistortion (vggsfm/utils/distortion.py:27-99) for SIMPLE_RADIAL, with the reference's
+ * semantics: damped Newton with a central-difference Jacobian and ONE global stop when the largest
+ * squared step over all observations is < max_step_norm.  workspace >= 16 B. */
+int vgg_undistort_simple_radial(int S, int N, const double* tracks_normalized, const double* extra_params,
+                                int max_iterations, double max_step_norm, double rel_step_size, double* out,
+                                int* iterations_run, void* workspace, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
