@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py -- BA iterations/sec and tracks-triangulated/sec at 400 frames x 4096 tracks (BASELINE.json).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --steps 2 --warmup 1      # CPU arm (oracle port of the reference's BA)
+
+One "step" = one bundle-adjustment solve of ITERS Levenberg-Marquardt iterations (residual/Jacobian ->
+Schur -> Cholesky -> back-substitution -> candidate evaluation -> accept/reject) on configuration C3
+(400 x 4096, SIMPLE_RADIAL, shared camera), starting from the same perturbed state every step.
+value = steps*ITERS / seconds.  Tracks/s of the fused LORANSAC triangulation is timed in a second region
+of the same run and reported as `tracks_per_s`.  With N>1 ranks the tracks are sharded and the reduced
+camera system is all-reduced over NCCL once per iteration (strong scaling: total problem fixed).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+S_FRAMES, N_TRACKS = 400, 4096
+CAMERA = "SIMPLE_RADIAL"
+ITERS = 10                      # LM iterations per step
+WORKLOAD = "C3: 400 frames x 4096 tracks, SIMPLE_RADIAL shared_camera, dense visibility (SURVEY 8d)"
+METRIC = "BA iterations/sec"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nm, v in zip(names, r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_problem():
+    from vggsfm_b200.synthetic import make_scene, perturb
+    sc = make_scene(S_FRAMES, N_TRACKS, CAMERA, seed=0)
+    extr, K, extra, pts = perturb(sc, seed=1)
+    return sc, extr, K, extra, pts
+
+
+# --------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's BA (pycolmap/Ceres are absent -> "port"), all host threads
+# --------------------------------------------------------------------------------------------------
+
+def cpu_ba_sample(sc, extr, K, extra, pts, iters):
+    """`iters` LM iterations of oracle.ba_oracle.lm_solve at the full C3 size; returns it/s."""
+    from oracle import ba_oracle as bo
+    S = extr.shape[0]
+    intr = np.zeros((S, 4))
+    intr[:, 0], intr[:, 1], intr[:, 2], intr[:, 3] = K[:, 0, 0], K[:, 0, 2], K[:, 1, 2], extra[:, 0]
+    intr[:] = intr[0]
+    opt = bo.LMOptions()
+    opt.max_num_iterations = iters
+    opt.gradient_tolerance = 0.0
+    t0 = time.perf_counter()
+    _, _, _, summ = bo.lm_solve(extr, intr, pts, sc.tracks.astype(np.float64), sc.mask, bo.SIMPLE_RADIAL,
+                                bo.INTR_SHARED, options=opt)
+    dt = time.perf_counter() - t0
+    return summ["iterations"] / dt, dt
+
+
+def cpu_tri_sample(sc, ntracks):
+    """oracle triangulate_tracks (256 hypotheses) on the first `ntracks` tracks of C3; returns tracks/s."""
+    import torch
+    from oracle import tri_oracle as to
+    tn = to.cam_from_img(sc.tracks[:, :ntracks].astype(np.float64), sc.intrinsics, None)
+    torch.manual_seed(0)
+    pairs = to.draw_pairs(S_FRAMES, 256)
+    t0 = time.perf_counter()
+    to.triangulate_tracks(sc.extrinsics, tn, pairs, sc.vis[:, :ntracks], sc.score[:, :ntracks])
+    dt = time.perf_counter() - t0
+    return ntracks / dt, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sc, extr, K, extra, pts = make_problem()
+    cores = os.cpu_count()
+    for _ in range(args.warmup):
+        cpu_ba_sample(sc, extr, K, extra, pts, 1)
+    t0 = time.perf_counter()
+    its = 0
+    for _ in range(args.steps):
+        v, _ = cpu_ba_sample(sc, extr, K, extra, pts, 1)
+        its += 1
+    dt = time.perf_counter() - t0
+    value = its / dt
+    tri_v, _ = cpu_tri_sample(sc, 16)
+    sample = "each step = 1 LM iteration of oracle/ba_oracle.lm_solve (numpy float64, BLAS threads) at full C3 size"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "it/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "pycolmap/pyceres absent: oracle port of COLMAP/Ceres BA on host cores"},
+        "cpu_baseline": {"value": value, "unit": "it/s", "cores": cores, "kind": "port", "sample": sample},
+        "tracks_per_s": tri_v,
+        "e2e": {"value": value, "unit": "it/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------------
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from vggsfm_b200 import bundle_adjustment as ba
+    from vggsfm_b200 import triangulation as tri
+    from vggsfm_b200 import _lib
+    from vggsfm_b200.dist import AllReduceHook, shard_range
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a GPU (no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+
+    sc, extr, K, extra, pts = make_problem()
+    lo, hi = shard_range(N_TRACKS, rank, world)
+    n_loc = hi - lo
+    model, mode = ba.SIMPLE_RADIAL, ba.INTR_SHARED
+    intr_np = np.zeros((S_FRAMES, 4))
+    intr_np[:, 0], intr_np[:, 1], intr_np[:, 2], intr_np[:, 3] = K[0, 0, 0], K[0, 0, 2], K[0, 1, 2], extra[0, 0]
+    t = lambda a, dt=None: (torch.from_numpy(np.ascontiguousarray(a)).to(dt) if dt else torch.from_numpy(np.ascontiguousarray(a))).to(dev).contiguous()
+    uv = t(sc.tracks[:, lo:hi], torch.float32)
+    mask = t(sc.mask[:, lo:hi].astype(np.uint8))
+    poses0, intr0, pts0 = t(extr), t(intr_np), t(pts[lo:hi])
+    param_const = ba.default_param_const(S_FRAMES, model, mode, dev)
+    opt = ba.default_options()
+    opt.max_num_iterations = ITERS
+    opt.gradient_tolerance = 0.0          # run exactly ITERS iterations every step
+    hook = AllReduceHook() if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def ba_step():
+        poses, intr, X = poses0.clone(), intr0.clone(), pts0.clone()
+        return ba.lm_solve(uv, mask, poses, intr, X, model, mode, param_const, None, opt, hook)
+
+    # ---- timed region 1: BA
+    launches = 0
+    for _ in range(args.warmup):
+        ba_step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    its = 0
+    for _ in range(args.steps):
+        flush.fill_(1.0)
+        s = ba_step()
+        its += s.iterations
+        launches += s.kernel_launches
+    e1.record()
+    barrier()
+    ba_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    tms = torch.tensor([ba_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ba_ms = float(tms.item())
+    value = its / (ba_ms * 1e-3)
+    final_cost = s.final_cost
+
+    # ---- timed region 2: triangulation (tracks sharded, no collective)
+    E = t(sc.extrinsics)
+    Kt = t(sc.intrinsics)
+    tn = tri.cam_from_img(t(sc.tracks[:, lo:hi]), Kt).contiguous()
+    vis, score = t(sc.vis[:, lo:hi]), t(sc.score[:, lo:hi])
+    torch.manual_seed(0)
+    pairs = tri.draw_ransac_pairs(S_FRAMES, 256)
+    for _ in range(args.warmup):
+        tri.triangulate_tracks(E, tn, track_vis=vis, track_score=score, ransac_pairs=pairs)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        flush.fill_(1.0)
+        p3, num, _ = tri.triangulate_tracks(E, tn, track_vis=vis, track_score=score, ransac_pairs=pairs)
+        launches += 4
+    e1.record()
+    barrier()
+    tms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    tri_ms = float(tms.item())
+    tracks_per_s = N_TRACKS * args.steps / (tri_ms * 1e-3)
+    tri_median_err = float(np.median(np.linalg.norm(p3.cpu().numpy() - sc.points3d[lo:hi], axis=1)))
+
+    # ---- e2e: public API with host (pinned) buffers, copies inside the timed region
+    h_tracks = torch.from_numpy(sc.tracks[:, lo:hi].copy()).pin_memory()
+    h_masks = torch.from_numpy(sc.mask[:, lo:hi].copy()).pin_memory()
+    h_pts = torch.from_numpy(pts[lo:hi].copy()).pin_memory()
+    h_extr = torch.from_numpy(extr.copy()).pin_memory()
+    h_K = torch.from_numpy(K.copy()).pin_memory()
+    h_extra = torch.from_numpy(extra.copy()).pin_memory()
+    h2d = sum(x.numel() * x.element_size() for x in (h_tracks, h_masks, h_pts, h_extr, h_K, h_extra))
+
+    def e2e_step():
+        out = ba.bundle_adjustment(h_pts.to(dev, non_blocking=True), h_extr.to(dev, non_blocking=True),
+                                   h_K.to(dev, non_blocking=True), h_extra.to(dev, non_blocking=True),
+                                   h_tracks.to(dev, non_blocking=True), h_masks.to(dev, non_blocking=True),
+                                   shared_camera=True, camera_type=CAMERA, options=opt, allreduce=hook)
+        res = [out[0].cpu(), out[1].cpu(), out[2].cpu(), out[3].cpu()]
+        return out[5], sum(x.numel() * x.element_size() for x in res)
+
+    for _ in range(min(args.warmup, 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_its = 0
+    d2h = 0
+    for _ in range(args.steps):
+        s2, d2h = e2e_step()
+        e2e_its += s2.iterations
+        launches += s2.kernel_launches
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    ts = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(ts, op=dist.ReduceOp.MAX)
+    e2e_value = e2e_its / float(ts.item())
+
+    # ---- roofline of the fused residual+Jacobian+block kernel (the HBM-bound kernel of the path), live
+    roof = None
+    cpu_base = None
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        dc, ns = ba.dims(model, mode)
+        obs = S_FRAMES * n_loc
+
+        def algo_bytes(S, N):
+            KR = _lib.lib().vgg_ba_camrec_len(model, mode)
+            return S * N * (8 + 1) + S * (12 + 4) * 8 + N * 3 * 8 + S * KR * 8 + N * 9 * 8 + (S * dc + ns) * N * 3 * 8
+
+        def time_blocks(uv_, mask_, poses_, intr_, X_, reps):
+            for _ in range(3):
+                ba.build_blocks(uv_, mask_, poses_, intr_, X_, model, mode)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            tot = 0.0
+            for _ in range(reps):
+                flush.fill_(1.0)
+                a.record()
+                out = ba.build_blocks(uv_, mask_, poses_, intr_, X_, model, mode)
+                b.record()
+                torch.cuda.synchronize()
+                tot += a.elapsed_time(b)
+                del out
+            return tot / reps
+
+        ms = time_blocks(uv, mask, poses0, intr0, pts0, 10)
+        ab = algo_bytes(S_FRAMES, n_loc)
+        ach = ab / (ms * 1e-3) / 1e9
+        roof = {"kernel": "ba_blocks_kernel<SIMPLE_RADIAL,INTR_SHARED,TMA>", "bound": "hbm", "achieved": ach,
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "bytes_per_launch": ab, "ms_per_launch": ms, "observations": obs,
+                "note": "event time includes 6 cudaMemsetAsync of the accumulators"}
+        # scaled synthetic: 400 x 131072 tracks = 52 M observations, 8 GB of coupling blocks
+        try:
+            NS_ = 131072
+            rng = np.random.default_rng(0)
+            rep = NS_ // n_loc + 1
+            uv_s = uv.repeat(1, rep, 1)[:, :NS_].contiguous()
+            mk_s = mask.repeat(1, rep)[:, :NS_].contiguous()
+            X_s = pts0.repeat(rep, 1)[:NS_].contiguous()
+            ms_s = time_blocks(uv_s, mk_s, poses0, intr0, X_s, 5)
+            ab_s = algo_bytes(S_FRAMES, NS_)
+            ach_s = ab_s / (ms_s * 1e-3) / 1e9
+            roof["scaled"] = {"workload": "400 x 131072 tracks", "achieved": ach_s, "frac": ach_s / peak,
+                              "bytes_per_launch": ab_s, "ms_per_launch": ms_s}
+            del uv_s, mk_s, X_s
+        except Exception as e:     # out of memory on a shared box: keep the C3-size number
+            roof["scaled"] = {"error": str(e)[:200]}
+        if world == 1:
+            v, dt = cpu_ba_sample(sc, extr, K, extra, pts, 2)
+            tv, tdt = cpu_tri_sample(sc, 16)
+            cpu_base = {"value": v, "unit": "it/s", "cores": os.cpu_count(), "kind": "port",
+                        "sample": f"2 LM iterations of oracle/ba_oracle.lm_solve (numpy float64 + BLAS) at full C3 size, {dt:.1f} s; "
+                                  f"triangulation: oracle on 16 of 4096 tracks, {tdt:.1f} s",
+                        "tracks_per_s": tv}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "it/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ba_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "lm_iterations_per_step": ITERS, "parallelism": f"track-shard x{world}",
+                       "tracks_per_rank": n_loc, "l2": "256 MB flush write between steps; working set ~0.8 GB > 126 MB L2",
+                       "final_cost": final_cost},
+            "tracks_per_s": tracks_per_s, "tri_ms_per_pass": tri_ms / args.steps, "tri_median_point_error": tri_median_err,
+            "e2e": {"value": e2e_value, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
+        }
+        if hook is not None:
+            line["config"]["allreduce_calls"] = hook.calls
+            line["config"]["allreduce_bytes"] = hook.bytes
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -49,7 +49,7 @@ def unpack_camrec(camrec, shared, S, dc, ns):
 
 
 def rotation_angle_deg(R1, R2):
-    """Geodesic rotation distance, definition of vggsfm/utils/metric.py:305-318."""
-    R = np.einsum("sij,skj->sik", R1, R2)
-    c = np.clip((np.trace(R, axis1=1, axis2=2) - 1.0) / 2.0, -1.0, 1.0)
-    return np.degrees(np.arccos(c))
+    """Geodesic rotation distance in degrees (the quantity of vggsfm/utils/metric.py:305-318), evaluated as
+    2*asin(|R1-R2|_F / (2*sqrt(2))) so that it stays accurate near zero (acos((tr-1)/2) bottoms out at ~1e-6 deg)."""
+    d = np.linalg.norm((R1 - R2).reshape(R1.shape[0], -1), axis=1)
+    return np.degrees(2.0 * np.arcsin(np.clip(d / (2.0 * np.sqrt(2.0)), 0.0, 1.0)))
