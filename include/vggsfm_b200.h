@@ -164,6 +164,25 @@ int vgg_undistort_simple_radial(int S, int N, const double* tracks_normalized, c
                                 int max_iterations, double max_step_norm, double rel_step_size, double* out,
                                 int* iterations_run, void* workspace, size_t ws_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------- */
+/* Tracker correlation inner loop (float32 math on float or half feature pyramids)             */
+/* ------------------------------------------------------------------------------------------- */
+
+/* CorrBlock.__init__ (vggsfm/models/track_modules/blocks.py:339-361): feature pyramid by repeated
+ * avg_pool2d(2,2), stored channels-last [BS,H_l,W_l,C] per level in `elem_size` bytes per element
+ * (4 = float, 2 = half as under the reference's fp16 autocast, runners/runner.py:418).
+ * fmaps_nchw is float [BS,C,H,W].  The half pyramid needs a float scratch (sizes from *_bytes). */
+int vgg_corr_pyramid_bytes(int BS, int C, int H, int W, int num_levels, int elem_size, size_t* pyramid_bytes,
+                           size_t* scratch_bytes);
+int vgg_corr_build_pyramid(int BS, int C, int H, int W, int num_levels, const float* fmaps_nchw, int elem_size,
+                           void* pyramid, void* scratch, void* stream);
+
+/* CorrBlock.corr + CorrBlock.sample fused (blocks.py:363-416; border_padding=1 gives
+ * EfficientCorrBlock.sample, :433-471).  targets float [BS,N,C], coords float [BS,N,2] (x,y) in level-0
+ * pixels, out float [BS,N,num_levels*(2r+1)^2] with out[a*(2r+1)+b] sampled at (x+a-r, y+b-r). */
+int vgg_corr_sample(int BS, int N, int C, int H, int W, int num_levels, int radius, const void* pyramid, int elem_size,
+                    const float* targets, const float* coords, int border_padding, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

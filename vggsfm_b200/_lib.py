@@ -18,6 +18,7 @@ EXPORTS = [
     "vgg_ba_build_blocks", "vgg_ba_schur", "vgg_ba_solve",
     "vgg_tri_workspace_bytes", "vgg_triangulate_tracks", "vgg_triangulate_by_pair", "vgg_filter_points3d",
     "vgg_project_points", "vgg_normalize_tracks", "vgg_undistort_simple_radial",
+    "vgg_corr_pyramid_bytes", "vgg_corr_build_pyramid", "vgg_corr_sample",
 ]
 
 
@@ -102,6 +103,9 @@ def lib() -> ctypes.CDLL:
     L.vgg_project_points.argtypes = [ci, ci, vp, vp, vp, vp, vp, vp, vp]
     L.vgg_normalize_tracks.argtypes = [ci, ci, vp, vp, vp, ci, vp, vp]
     L.vgg_undistort_simple_radial.argtypes = [ci, ci, vp, vp, ci, cd, cd, vp, ctypes.POINTER(ci), vp, cs, vp]
+    L.vgg_corr_pyramid_bytes.argtypes = [ci, ci, ci, ci, ci, ci, ctypes.POINTER(cs), ctypes.POINTER(cs)]
+    L.vgg_corr_build_pyramid.argtypes = [ci, ci, ci, ci, ci, vp, ci, vp, vp, vp]
+    L.vgg_corr_sample.argtypes = [ci, ci, ci, ci, ci, ci, ci, vp, ci, vp, vp, ci, vp, vp]
     _lib = L
     return L
 

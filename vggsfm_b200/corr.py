@@ -1,0 +1,96 @@
+"""CorrBlock / EfficientCorrBlock with the reference's interface (vggsfm/models/track_modules/blocks.py:338-471),
+backed by the fused correlation+sampling kernel (csrc/corr.cu).  The correlation volume is never built.
+
+Drop-in: `vggsfm.models.track_modules.base_track_predictor.CorrBlock = vggsfm_b200.corr.CorrBlock`
+(the class is looked up at base_track_predictor.py:117-124)."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _stream(dev):
+    return torch.cuda.current_stream(dev).cuda_stream
+
+
+class _Pyramid:
+    def __init__(self, fmaps, num_levels, radius, half=None):
+        if not fmaps.is_cuda:
+            raise RuntimeError("vggsfm_b200.CorrBlock needs CUDA tensors (no CPU fallback)")
+        B, S, C, H, W = fmaps.shape
+        self.B, self.S, self.C, self.H, self.W = B, S, C, H, W
+        self.num_levels, self.radius = num_levels, radius
+        # half pyramid when the reference would have run its matmul under fp16 autocast (runner.py:418)
+        if half is None:
+            half = fmaps.dtype in (torch.float16, torch.bfloat16) or torch.is_autocast_enabled()
+        self.elem = 2 if half else 4
+        L = _lib.lib()
+        dev = fmaps.device
+        pb, sb = ctypes.c_size_t(), ctypes.c_size_t()
+        _lib.check(L.vgg_corr_pyramid_bytes(B * S, C, H, W, num_levels, self.elem, ctypes.byref(pb), ctypes.byref(sb)),
+                   "vgg_corr_pyramid_bytes")
+        self.pyr = torch.empty(pb.value, dtype=torch.uint8, device=dev)
+        scratch = torch.empty(max(sb.value, 1), dtype=torch.uint8, device=dev)
+        src = fmaps.reshape(B * S, C, H, W).float().contiguous()
+        with torch.cuda.device(dev):
+            _lib.check(L.vgg_corr_build_pyramid(B * S, C, H, W, num_levels, src.data_ptr(), self.elem, self.pyr.data_ptr(),
+                                                scratch.data_ptr() if sb.value else None, _stream(dev)),
+                       "vgg_corr_build_pyramid")
+        self.dev = dev
+
+    def sample(self, coords, targets, border):
+        B, S, N, D = coords.shape
+        assert D == 2
+        assert targets.shape == (B, S, N, self.C)
+        assert S == self.S
+        r = self.radius
+        K = 2 * r + 1
+        out = torch.empty(B, S, N, self.num_levels * K * K, dtype=torch.float32, device=self.dev)
+        tg = targets.float().contiguous()
+        co = coords.float().contiguous()
+        with torch.cuda.device(self.dev):
+            _lib.check(_lib.lib().vgg_corr_sample(B * S, N, self.C, self.H, self.W, self.num_levels, r, self.pyr.data_ptr(),
+                                                  self.elem, tg.data_ptr(), co.data_ptr(), 1 if border else 0,
+                                                  out.data_ptr(), _stream(self.dev)), "vgg_corr_sample")
+        return out
+
+
+class CorrBlock:
+    """blocks.py:338-416.  corr(targets) records the targets; sample(coords) runs the fused kernel."""
+
+    def __init__(self, fmaps, num_levels=4, radius=4, multiple_track_feats=False, padding_mode="zeros", half=None):
+        if multiple_track_feats:
+            raise NotImplementedError("multiple_track_feats=True is not used by the reference configs")
+        if padding_mode not in ("zeros", "border"):
+            raise ValueError(f"unsupported padding_mode {padding_mode}")
+        self.padding_mode = padding_mode
+        self.num_levels, self.radius = num_levels, radius
+        B, S, C, H, W = fmaps.shape
+        self.S, self.C, self.H, self.W = S, C, H, W
+        self._pyr = _Pyramid(fmaps, num_levels, radius, half)
+        self._targets = None
+
+    def corr(self, targets):
+        B, S, N, C = targets.shape
+        assert C == self.C
+        assert S == self.S
+        self._targets = targets
+
+    def sample(self, coords):
+        if self._targets is None:
+            raise RuntimeError("CorrBlock.sample called before CorrBlock.corr")
+        return self._pyr.sample(coords, self._targets, self.padding_mode == "border")
+
+
+class EfficientCorrBlock:
+    """blocks.py:419-471: sample(coords, target) with border padding."""
+
+    def __init__(self, fmaps, num_levels=4, radius=4, half=None):
+        self.num_levels, self.radius = num_levels, radius
+        self._pyr = _Pyramid(fmaps, num_levels, radius, half)
+
+    def sample(self, coords, target):
+        return self._pyr.sample(coords, target, True)
