@@ -17,8 +17,8 @@ from vggsfm.models.track_modules.blocks import CorrBlock, EfficientCorrBlock   #
 
 CASES = {
     # name: (B, S, C, H, W, N, levels, radius, coordinate range)
-    "corr_coarse_small": (1, 3, 128, 40, 48, 20, 5, 4, (-6.0, 52.0)),     # 5 levels r=4 like the coarse tracker, borders hit
-    "corr_fine_patch": (6, 4, 32, 31, 31, 1, 3, 3, (1.0, 29.0)),          # fine tracker: one query per 31x31 patch
+    "corr_coarse_small": (1, 2, 128, 32, 40, 24, 5, 4, (-6.0, 44.0)),     # 5 levels r=4 like the coarse tracker, borders hit
+    "corr_fine_patch": (3, 2, 32, 31, 31, 1, 3, 3, (1.0, 29.0)),          # fine tracker: one query per 31x31 patch
 }
 
 
