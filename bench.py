@@ -113,7 +113,7 @@ def cpu_ba_sample(sc, extr, K, extra, pts, iters):
     opt.gradient_tolerance = 0.0
     t0 = time.perf_counter()
     _, _, _, summ = bo.lm_solve(extr, intr, pts, sc.tracks.astype(np.float64), sc.mask, bo.SIMPLE_RADIAL,
-                                bo.INTR_SHARED, options=opt)
+                                bo.INTR_SHARED, options=opt, use_c=bo._load_c() is not None)
     dt = time.perf_counter() - t0
     return summ["iterations"] / dt, dt
 
@@ -147,7 +147,7 @@ def run_reference(args):
     dt = time.perf_counter() - t0
     value = its / dt
     tri_v, _ = cpu_tri_sample(sc, 16)
-    sample = "each step = 1 LM iteration of oracle/ba_oracle.lm_solve (numpy float64, BLAS threads) at full C3 size"
+    sample = "each step = 1 LM iteration of oracle/ba_oracle.lm_solve (C/OpenMP Jacobians + numpy/BLAS Schur and Cholesky, float64) at full C3 size"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "it/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True, "scaling": "strong",
@@ -349,7 +349,7 @@ def run_gpu(args):
             v, dt = cpu_ba_sample(sc, extr, K, extra, pts, 2)
             tv, tdt = cpu_tri_sample(sc, 16)
             cpu_base = {"value": v, "unit": "it/s", "cores": os.cpu_count(), "kind": "port",
-                        "sample": f"2 LM iterations of oracle/ba_oracle.lm_solve (numpy float64 + BLAS) at full C3 size, {dt:.1f} s; "
+                        "sample": f"2 LM iterations of oracle/ba_oracle.lm_solve (C/OpenMP Jacobians + numpy/BLAS Schur and Cholesky, float64) at full C3 size, {dt:.1f} s; "
                                   f"triangulation: oracle on 16 of 4096 tracks, {tdt:.1f} s",
                         "tracks_per_s": tv}
 

@@ -182,6 +182,53 @@ def build_blocks(poses, intr, points, uv, mask, model, mode, point_const=None):
     return out
 
 
+_C_LIB = None
+
+
+def _load_c():
+    """oracle/_build/libba_blocks_ref.so (oracle/ba_blocks_ref.c) if it has been built, else None."""
+    global _C_LIB
+    if _C_LIB is None:
+        import ctypes
+        import os
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_build", "libba_blocks_ref.so")
+        _C_LIB = ctypes.CDLL(path) if os.path.exists(path) else False
+    return _C_LIB or None
+
+
+def build_blocks_c(poses, intr, points, uv, mask, model, mode, point_const=None):
+    """Same outputs as build_blocks(), evaluated by the C/OpenMP restatement (oracle/ba_blocks_ref.c)."""
+    import ctypes
+    lib = _load_c()
+    if lib is None:
+        raise RuntimeError("oracle/_build/libba_blocks_ref.so not built (make -C oracle)")
+    S, N = mask.shape
+    dc, ns = dims(model, mode)
+    c = lambda a, dt=np.float64: np.ascontiguousarray(a, dtype=dt)
+    uvc, mk, po, it, pt = c(uv), c(mask, np.uint8), c(poses), c(intr), c(points)
+    pcn = c(point_const, np.uint8) if point_const is not None else None
+    Wfull = np.empty((S * dc + max(ns, 1), N, 3))        # camera rows then shared rows, one allocation
+    out = {"g_c": np.empty((S, dc)), "H_cc": np.empty((S, dc, dc)), "g_p": np.empty((N, 3)), "H_pp": np.empty((N, 3, 3)),
+           "W": Wfull[:S * dc].reshape(S, dc, N, 3), "W_full": Wfull[:S * dc + ns]}
+    cost = np.zeros(1)
+    g_s, H_ss = np.zeros(2), np.zeros(4)
+    H_cs = np.zeros((S, 6, max(ns, 1)))
+    W_s = Wfull[S * dc:]
+    P = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    rc = lib.ba_blocks_ref(S, N, P(uvc), P(mk), P(po), P(it), P(pt), P(pcn) if pcn is not None else None, model, mode,
+                           P(cost), P(out["g_c"]), P(out["H_cc"]), P(out["g_p"]), P(out["H_pp"]), P(out["W"]), P(g_s),
+                           P(H_ss), P(H_cs), P(W_s))
+    if rc != 0:
+        raise RuntimeError("ba_blocks_ref failed")
+    out["cost"] = float(cost[0])
+    if mode == INTR_SHARED:
+        out["g_s"] = g_s[:ns].copy()
+        out["H_ss"] = H_ss[:ns * ns].reshape(ns, ns).copy()
+        out["H_cs"] = H_cs
+        out["W_s"] = W_s
+    return out
+
+
 def cost_only(poses, intr, points, uv, mask, model):
     uvh, _ = project(poses, intr, points, model)
     r = (uvh - uv) * mask[..., None]
@@ -275,6 +322,8 @@ def _assemble_camera_system(blk, S, dc, ns):
 
 def _full_W(blk, S, dc, ns):
     """[D, N, 3] coupling blocks (camera rows then shared rows)."""
+    if "W_full" in blk:
+        return blk["W_full"]
     W = blk["W"].reshape(S * dc, *blk["W"].shape[2:])
     if ns:
         W = np.concatenate([W, blk["W_s"]], axis=0)
@@ -282,7 +331,7 @@ def _full_W(blk, S, dc, ns):
 
 
 def lm_solve(poses, intr, points, uv, mask, model, mode, param_const=None, point_const=None,
-             options: LMOptions | None = None, trace: list | None = None, allreduce=None):
+             options: LMOptions | None = None, trace: list | None = None, allreduce=None, use_c=False):
     """Ceres-style trust-region LM (TrustRegionMinimizer + LevenbergMarquardtStrategy) with the
     points eliminated by a Schur complement and the reduced camera system solved by Cholesky.
 
@@ -301,7 +350,7 @@ def lm_solve(poses, intr, points, uv, mask, model, mode, param_const=None, point
     free_c = ~param_const
 
     def evaluate(poses, intr, points):
-        blk = build_blocks(poses, intr, points, uv, mask, model, mode, point_const)
+        blk = (build_blocks_c if use_c else build_blocks)(poses, intr, points, uv, mask, model, mode, point_const)
         Hc, gc = _assemble_camera_system(blk, S, dc, ns)
         return blk, Hc, gc
 
@@ -350,7 +399,7 @@ def lm_solve(poses, intr, points, uv, mask, model, mode, param_const=None, point
         q = np.einsum("nji,nj->ni", M, blk["g_p"])                # L^-1 Dp g_p = M^T g_p
         # ---- Schur complement (local shard), then sum over shards
         W = _full_W(blk, S, dc, ns)                               # [D,N,3]
-        Z = np.einsum("dnj,njk->dnk", W, M).reshape(D, N * 3)
+        Z = (W[:, :, 0:1] * M[None, :, 0, :] + W[:, :, 1:2] * M[None, :, 1, :] + W[:, :, 2:3] * M[None, :, 2, :]).reshape(D, N * 3)
         S_raw = Hc - Z @ Z.T
         rhs_raw = -(gc - Z @ q.reshape(-1))
         S_raw = ar(S_raw)
@@ -383,7 +432,7 @@ def lm_solve(poses, intr, points, uv, mask, model, mode, param_const=None, point
             continue
         d_c = dcs * sc_c                                           # unscaled camera step
         # ---- back-substitution: dp = M M^T (-(g_p + W^T d_c))
-        w = np.einsum("dnj,d->nj", W, d_c)
+        w = np.tensordot(d_c, W, axes=(0, 0))
         ypt = -(blk["g_p"] + w)
         d_p = np.einsum("nij,nj->ni", M, np.einsum("nji,nj->ni", M, ypt))
         # ---- model cost change: 0.5*(delta^T D^2 delta - delta^T g)  (== -(J d)^T (f + J d/2))

@@ -76,3 +76,19 @@ def test_negative_depth_and_normalize():
     uv0, _ = bo.project(c["poses"], c["intr"], pts, c["model"])
     uv1, _ = bo.project(poses, c["intr"], X, c["model"])
     assert np.abs(uv0 - uv1).max() < 1e-8
+
+
+@pytest.mark.parametrize("cam,mode", [("SIMPLE_PINHOLE", bo.INTR_PER_FRAME), ("SIMPLE_RADIAL", bo.INTR_SHARED),
+                                      ("SIMPLE_RADIAL", bo.INTR_CONST)])
+def test_c_restatement_matches_numpy(cam, mode):
+    if bo._load_c() is None:
+        pytest.skip("oracle/_build/libba_blocks_ref.so not built")
+    c = ba_case(7, 50, cam, mode, seed=8)
+    pc = np.zeros(50, dtype=bool)
+    pc[::5] = True
+    a = bo.build_blocks(c["poses"], c["intr"], c["points"], c["uv"], c["mask"], c["model"], mode, pc)
+    b = bo.build_blocks_c(c["poses"], c["intr"], c["points"], c["uv"], c["mask"], c["model"], mode, pc)
+    assert abs(a["cost"] - b["cost"]) <= 1e-12 * a["cost"]
+    for k in a:
+        if k != "cost":
+            assert np.abs(a[k] - b[k]).max() <= 1e-11 * max(1.0, np.abs(a[k]).max()), k
