@@ -111,6 +111,11 @@ int vgg_ba_schur(const vgg_ba_problem* prob, const double* camrec, const double*
                  double radius, double min_diag, double max_diag, void* workspace, size_t ws_bytes,
                  double* Sraw, double* rhs, int* Dpad_out, void* stream);
 
+/* Blocked Cholesky of the reduced camera system (csrc/chol.cu): in-place factorisation of the row-major
+ * lower triangle of A [n x n], leading dimension lda (even), replacing the potrf inside Ceres' DENSE_SCHUR.
+ * workspace >= ceil(n/64)*32768 + 256 bytes; *info_host = 0 or the 1-based index of the failing pivot. */
+int vgg_cholesky_lower(int n, int lda, double* A, void* workspace, size_t ws_bytes, int* info_host, void* stream);
+
 /* Whole Levenberg-Marquardt solve (Ceres trust-region semantics).  `trace` is a HOST array
  * [max_num_iterations, 8] (it, cost, candidate_cost, model_change, rho, radius, step_norm, flags) or NULL. */
 int vgg_ba_solve(const vgg_ba_problem* prob, const vgg_ba_options* opt, void* workspace,

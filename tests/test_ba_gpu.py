@@ -171,3 +171,33 @@ def test_c2_full_size_properties(cuda_dev):
     M = int(c["mask"].sum())
     rms = np.sqrt(2.0 * s.final_cost / M)
     assert 0.25 < rms < 0.5, rms            # 0.3 px noise per coordinate -> ~0.42 px per observation
+
+
+@pytest.mark.parametrize("n", [64, 100, 343, 2402])
+def test_cholesky_matches_lapack(cuda_dev, n):
+    """csrc/chol.cu against numpy.linalg.cholesky (float64; 1e-10 of the factor's scale), plus failure reporting."""
+    import ctypes
+    import torch
+    from vggsfm_b200 import _lib
+    rng = np.random.default_rng(n)
+    B = rng.normal(size=(n, n + 8))
+    A = B @ B.T + n * 1e-3 * np.eye(n)
+    lda = (n + 127) // 128 * 128
+    buf = torch.zeros(n, lda, dtype=torch.float64, device=cuda_dev)
+    buf[:, :n] = torch.from_numpy(np.tril(A)).to(cuda_dev)
+    ws = torch.empty(((n + 63) // 64) * 32768 + 256, dtype=torch.uint8, device=cuda_dev)
+    info = ctypes.c_int(-1)
+    L = _lib.lib()
+    _lib.check(L.vgg_cholesky_lower(n, lda, buf.data_ptr(), ws.data_ptr(), ws.numel(), ctypes.byref(info),
+                                    torch.cuda.current_stream().cuda_stream), "vgg_cholesky_lower")
+    assert info.value == 0
+    ref = np.linalg.cholesky(A)
+    got = np.tril(buf.cpu().numpy()[:, :n])
+    assert np.abs(got - ref).max() <= 1e-10 * np.abs(ref).max()
+    # not positive definite -> info reports the failing pivot (1-based)
+    A2 = A.copy()
+    A2[70 % n, 70 % n] = -1.0
+    buf[:, :n] = torch.from_numpy(np.tril(A2)).to(cuda_dev)
+    _lib.check(L.vgg_cholesky_lower(n, lda, buf.data_ptr(), ws.data_ptr(), ws.numel(), ctypes.byref(info),
+                                    torch.cuda.current_stream().cuda_stream), "vgg_cholesky_lower")
+    assert info.value == (70 % n) + 1

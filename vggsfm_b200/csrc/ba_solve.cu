@@ -48,6 +48,9 @@ int launch_extract_gvec(int S, int dc, int ns, int KR, const double* camrec, con
 int launch_gradmax(int D, int N, const double* gvec, const uint8_t* pconst, const double* g_p,
                    const uint8_t* point_const, double* scal, cudaStream_t st);
 
+size_t chol_workspace_doubles(int n);
+int chol_lower_inplace(int n, int lda, double* A, double* Ldiag, int* info, cudaStream_t st);
+
 static int dims_of(int model, int mode, int* dc, int* ns, int* KR) {
   if (model != VGG_SIMPLE_PINHOLE && model != VGG_SIMPLE_RADIAL) return VGG_EINVAL;
   const int ni = model == VGG_SIMPLE_PINHOLE ? 1 : 2;
@@ -77,6 +80,7 @@ struct Layout {
   double *small;     // [8 scalars | gvec_candidate Dpad]           (one small all-reduce)
   double *scal;      // [16]
   double *potrf_work;
+  double *chol_diag;
   int *dev_info;
   size_t potrf_lwork;
   size_t bytes;
@@ -118,6 +122,7 @@ static int make_layout(int S, int N, int model, int mode, void* base, size_t cap
   L->scal = c.take<double>(16);
   L->potrf_lwork = potrf_lwork;
   L->potrf_work = c.take<double>(potrf_lwork);
+  L->chol_diag = c.take<double>(chol_workspace_doubles(L->D));
   L->dev_info = c.take<int>(4);
   L->bytes = align_up(c.off, 256);
   if (base && c.off > cap) {
@@ -261,6 +266,26 @@ int vgg_ba_schur(const vgg_ba_problem* prob, const double* camrec, const double*
   return VGG_OK;
 }
 
+int vgg_cholesky_lower(int n, int lda, double* A, void* workspace, size_t ws_bytes, int* info_host, void* stream) {
+  VGG_REQUIRE(A && workspace && n > 0 && lda >= n, "bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  g_launch_count = 0;
+  const size_t need = sizeof(double) * chol_workspace_doubles(n) + 256;
+  if (ws_bytes < need) {
+    set_error("cholesky workspace too small: need %zu bytes", need);
+    return VGG_EWORKSPACE;
+  }
+  int* info = reinterpret_cast<int*>(workspace);
+  double* diag = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 256);
+  int rc = chol_lower_inplace(n, lda, A, diag, info, st);
+  if (rc) return rc;
+  if (info_host) {
+    VGG_CUDA_CHECK(cudaMemcpyAsync(info_host, info, sizeof(int), cudaMemcpyDeviceToHost, st));
+    VGG_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  return VGG_OK;
+}
+
 int vgg_ba_solve(const vgg_ba_problem* prob, const vgg_ba_options* opt_in, void* workspace, size_t ws_bytes,
                  vgg_allreduce_fn allreduce, void* ar_user, vgg_ba_summary* summary, double* trace, void* stream) {
   VGG_REQUIRE(prob && workspace && summary, "null pointer");
@@ -367,18 +392,14 @@ int vgg_ba_solve(const vgg_ba_problem* prob, const vgg_ba_options* opt_in, void*
     if ((rc = launch_scale_damp(D, L.Dpad, Sraw, rhs, hdiag, L.sc_c, prob->param_const, radius, opt.min_lm_diagonal,
                                 opt.max_lm_diagonal, L.bvec, st)))
       return rc;
-    // row-major lower == column-major upper
-    if (cusolverDnDpotrf(cs, CUBLAS_FILL_MODE_UPPER, D, Sraw, L.Dpad, L.potrf_work, (int)L.potrf_lwork, L.dev_info) !=
-        CUSOLVER_STATUS_SUCCESS) {
-      set_error("cusolverDnDpotrf failed to launch");
-      return VGG_ESOLVER;
-    }
+    // own blocked Cholesky (chol.cu); the factor is row-major lower == column-major upper for potrs
+    if ((rc = chol_lower_inplace(D, L.Dpad, Sraw, L.chol_diag, L.dev_info, st))) return rc;
     if (cusolverDnDpotrs(cs, CUBLAS_FILL_MODE_UPPER, D, 1, Sraw, L.Dpad, L.bvec, L.Dpad, L.dev_info + 1) !=
         CUSOLVER_STATUS_SUCCESS) {
       set_error("cusolverDnDpotrs failed to launch");
       return VGG_ESOLVER;
     }
-    g_launch_count += 2;
+    g_launch_count += 1;
     if ((rc = launch_cam_step(D, L.bvec, L.sc_c, hdiag, gvec, prob->param_const, radius, opt.min_lm_diagonal,
                               opt.max_lm_diagonal, L.d_c, L.scal, st)))
       return rc;
