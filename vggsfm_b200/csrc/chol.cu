@@ -21,9 +21,10 @@ constexpr int CH_NB = 64;
 __global__ void __launch_bounds__(256) chol_panel_kernel(int n, int lda, int k0, double* __restrict__ A,
                                                          double* __restrict__ Ldiag /*[nblk][64*64]*/,
                                                          int* __restrict__ info) {
-  __shared__ double L[CH_NB][CH_NB + 1];
-  __shared__ double Li[CH_NB][CH_NB + 1];
-  __shared__ double T[CH_NB][CH_NB + 1];
+  extern __shared__ __align__(16) double panel_smem[];
+  double (*L)[CH_NB + 1] = reinterpret_cast<double (*)[CH_NB + 1]>(panel_smem);
+  double (*Li)[CH_NB + 1] = reinterpret_cast<double (*)[CH_NB + 1]>(panel_smem + CH_NB * (CH_NB + 1));
+  double (*T)[CH_NB + 1] = reinterpret_cast<double (*)[CH_NB + 1]>(panel_smem + 2 * CH_NB * (CH_NB + 1));
   __shared__ int fail;
   const int tid = threadIdx.x;
   const int nb = min(CH_NB, n - k0);
@@ -190,16 +191,18 @@ int chol_lower_inplace(int n, int lda, double* A, double* Ldiag, int* info, cuda
   VGG_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int), st));
   const int nblk = (n + CH_NB - 1) / CH_NB;
   const size_t smem = sizeof(double) * 2 * CH_NB * 128;
+  const size_t psmem = sizeof(double) * 3 * CH_NB * (CH_NB + 1);
   static bool attr_set = false;
   if (!attr_set) {
     VGG_CUDA_CHECK(cudaFuncSetAttribute(chol_trailing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VGG_CUDA_CHECK(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
     attr_set = true;
   }
   for (int b = 0; b < nblk; ++b) {
     const int k0 = b * CH_NB;
     const int below = n - (k0 + CH_NB);
     const int chunks = below > 0 ? (below + CH_NB - 1) / CH_NB : 0;
-    chol_panel_kernel<<<1 + chunks, 256, 0, st>>>(n, lda, k0, A, Ldiag, info);
+    chol_panel_kernel<<<1 + chunks, 256, psmem, st>>>(n, lda, k0, A, Ldiag, info);
     VGG_LAUNCH_CHECK();
     if (below > 0) {
       const int t0 = k0 + CH_NB;
