@@ -11,19 +11,21 @@
 //     copies (cp.async.bulk -> UBLKCP) into a two-stage shared-memory ring with mbarriers; poses and
 //     intrinsics ride the same barrier.
 //   * HBM writes: the camera-point coupling block W = J_c^T J_p (dc x 3 doubles per observation),
-//     assembled per frame in shared memory as dc rows of [TN x 3] and written back with TMA bulk
-//     stores (fully coalesced 3 KB rows), double buffered against the next frame's math.
+//     assembled per frame and per warp in shared memory as dc rows of [32 x 3] and written back with TMA
+//     bulk stores (768 B rows), double buffered against the next frame's math; warps never wait for each
+//     other inside a TS-frame sub-tile (no CTA barrier in the frame loop).
 //   * per-point blocks (H_pp 3x3 sym, g_p) accumulate in registers over the frame chunk;
 //   * per-camera blocks (g_c, H_cc upper-packed, H_cs) are reduced across the 32 tracks of a warp with
-//     a reduce-scatter shuffle network (K-1 shuffles for K values), across warps through shared
-//     memory, then one f64 RED per value per CTA.
+//     a reduce-scatter shuffle network (16 values at a time, 15+1 shuffles), then one f64 RED per value
+//     per warp.
 // Algorithmic HBM bytes per observation: 9 + 24*dc (+ amortised per-frame/per-point terms), see DESIGN.md.
+#include <utility>
 #include "common.cuh"
 
 namespace vgg {
 
 constexpr int TN = 128;   // tracks per CTA (threads)
-constexpr int TS = 8;     // frames per TMA sub-tile
+constexpr int TS = 4;     // frames per TMA sub-tile (keeps smem <= 56 KB -> 4 CTAs/SM)
 constexpr int NWARP = TN / 32;
 
 template <int MODEL, int MODE>
@@ -46,6 +48,39 @@ struct BlkSmem {
   uint64_t bar[2];
 };
 
+// ---- compile-time layout of the per-frame camera record: g_c[DC] | H_cc upper-packed | H_cs[6][NS] ----
+__host__ __device__ constexpr int pack_row(int dc, int p) {
+  int i = 0;
+  while (p >= dc - i) { p -= dc - i; ++i; }
+  return i;
+}
+__host__ __device__ constexpr int pack_col(int dc, int p) {
+  int i = 0;
+  while (p >= dc - i) { p -= dc - i; ++i; }
+  return i + p;
+}
+
+template <int DC, int NS, int K>
+__device__ __forceinline__ double cam_value(const double* jc0, const double* jc1, double rx, double ry) {
+  constexpr int NPACK = DC * (DC + 1) / 2;
+  if constexpr (K < DC) {
+    return jc0[K] * rx + jc1[K] * ry;
+  } else if constexpr (K < DC + NPACK) {
+    constexpr int i = pack_row(DC, K - DC), j = pack_col(DC, K - DC);
+    return jc0[i] * jc0[j] + jc1[i] * jc1[j];
+  } else {
+    constexpr int q = K - DC - NPACK;
+    constexpr int i = q / (NS > 0 ? NS : 1), j = q % (NS > 0 ? NS : 1);
+    return jc0[i] * jc0[6 + j] + jc1[i] * jc1[6 + j];
+  }
+}
+
+template <int DC, int NS, int KR, int BASE, int... G>
+__device__ __forceinline__ void cam_batch(double (&a)[16], const double* jc0, const double* jc1, double rx, double ry,
+                                          std::integer_sequence<int, G...>) {
+  ((a[G] = (BASE + G < KR) ? cam_value<DC, NS, (BASE + G < KR ? BASE + G : 0)>(jc0, jc1, rx, ry) : 0.0), ...);
+}
+
 template <int MODEL, int MODE, bool USE_TMA>
 __global__ void __launch_bounds__(TN) ba_blocks_kernel(
     int S, int N, int frames_per_cta, const float2* __restrict__ uv, const uint8_t* __restrict__ mask,
@@ -54,20 +89,24 @@ __global__ void __launch_bounds__(TN) ba_blocks_kernel(
     double* __restrict__ g_p, double* __restrict__ H_pp, double* __restrict__ W, double* __restrict__ shared_out) {
   using C = BlkCfg<MODEL, MODE>;
   constexpr int DC = C::DC, NS = C::NS, KR = C::KR;
+  constexpr int NB16 = (KR + 15) / 16;          // reduce batches of 16 camera values
   extern __shared__ __align__(128) unsigned char smem_raw[];
   BlkSmem& sm = *reinterpret_cast<BlkSmem*>(smem_raw);
-  // W tile: [2][DC][TN*3] doubles, then red[NWARP][KR]
+  // per-warp W tiles: [NWARP][2][DC][32*3] doubles, then red[NWARP][8]
   double* wsm = reinterpret_cast<double*>(smem_raw + align_up(sizeof(BlkSmem), 128));
-  double* red = wsm + 2 * DC * TN * 3;
+  double* red = wsm + NWARP * 2 * DC * 96;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int n0 = blockIdx.x * TN;
   const int n = n0 + tid;
   const int nvalid = min(TN, N - n0);
+  const int nw0 = n0 + warp * 32;                       // first track of this warp
+  const int nvalid_w = max(0, min(32, N - nw0));
   const int s_begin = blockIdx.y * frames_per_cta;
   const int s_end = min(S, s_begin + frames_per_cta);
   const int ntiles = (s_end - s_begin + TS - 1) / TS;
   const bool active = n < N;
+  double* wwarp = wsm + (size_t)warp * 2 * DC * 96;
 
   if (USE_TMA && tid == 0) {
     mbar_init(&sm.bar[0], 1);
@@ -123,17 +162,17 @@ __global__ void __launch_bounds__(TN) ba_blocks_kernel(
     const int st = tile & 1;
     const int s0 = s_begin + tile * TS;
     const int nf = min(TS, s_end - s0);
-    if (tile + 1 < ntiles) issue_tile(tile + 1);   // other stage was released by the syncs of tile-1
+    // every warp is done with the other stage (tile-1) once it gets here: one CTA sync per TS frames
+    if (tile > 0) __syncthreads();
+    if (tile + 1 < ntiles) issue_tile(tile + 1);
     if (USE_TMA) mbar_wait(&sm.bar[st], (tile >> 1) & 1);
     else __syncthreads();
 
     for (int f = 0; f < nf; ++f, ++fcount) {
       const int s = s0 + f;
-      const int buf = fcount & 1;
-      double* wt = wsm + buf * DC * TN * 3;
-      double v[KR];
-#pragma unroll
-      for (int i = 0; i < KR; ++i) v[i] = 0;
+      double* wt = wwarp + (fcount & 1) * DC * 96;      // this warp's tile: DC rows of [32][3] doubles
+      double jc0[8], jc1[8];
+      double rx = 0.0, ry = 0.0;
       const bool valid = active && sm.mask[st][f][tid] != 0;
       if (valid) {
         const double* P = sm.pose[st][f];
@@ -152,8 +191,8 @@ __global__ void __launch_bounds__(TN) ba_blocks_kernel(
         const double u = px * iz, w_ = py * iz;
         const double r2 = u * u + w_ * w_;
         const double d = 1.0 + kk * r2;
-        const double rx = fo * d * u + cx - (double)ob.x;
-        const double ry = fo * d * w_ + cy - (double)ob.y;
+        rx = fo * d * u + cx - (double)ob.x;
+        ry = fo * d * w_ + cy - (double)ob.y;
         cost_acc += 0.5 * (rx * rx + ry * ry);
         // f*A, A = d(distorted)/d(u,v)
         double a00, a01, a11;
@@ -168,7 +207,6 @@ __global__ void __launch_bounds__(TN) ba_blocks_kernel(
         const double j00 = a00 * iz, j01 = a01 * iz, j02 = -(a00 * u + a01 * w_) * iz;
         const double j10 = a01 * iz, j11 = a11 * iz, j12 = -(a01 * u + a11 * w_) * iz;
         // camera columns: delta(3) = Jproj * (-2[RX]x), t(3) = Jproj, f, k
-        double jc0[8], jc1[8];
         jc0[0] = 2.0 * (-a3 * j01 + a2 * j02);  jc1[0] = 2.0 * (-a3 * j11 + a2 * j12);
         jc0[1] = 2.0 * (a3 * j00 - a1 * j02);   jc1[1] = 2.0 * (a3 * j10 - a1 * j12);
         jc0[2] = 2.0 * (-a2 * j00 + a1 * j01);  jc1[2] = 2.0 * (-a2 * j10 + a1 * j11);
@@ -195,22 +233,10 @@ __global__ void __launch_bounds__(TN) ba_blocks_kernel(
         hpp[3] += jx0[1] * jx0[1] + jx1[1] * jx1[1];
         hpp[4] += jx0[1] * jx0[2] + jx1[1] * jx1[2];
         hpp[5] += jx0[2] * jx0[2] + jx1[2] * jx1[2];
-        // camera values: g_c | H_cc packed upper | H_cs
-        int idx = 0;
-#pragma unroll
-        for (int i = 0; i < DC; ++i) v[idx++] = jc0[i] * rx + jc1[i] * ry;
-#pragma unroll
-        for (int i = 0; i < DC; ++i)
-#pragma unroll
-          for (int j = i; j < DC; ++j) v[idx++] = jc0[i] * jc0[j] + jc1[i] * jc1[j];
-#pragma unroll
-        for (int i = 0; i < 6; ++i)
-#pragma unroll
-          for (int j = 0; j < NS; ++j) v[idx++] = jc0[i] * jc0[6 + j] + jc1[i] * jc1[6 + j];
-        // coupling blocks: row i of the W tile holds [TN][3] doubles
+        // coupling blocks: row i of the warp tile holds [32][3] doubles
 #pragma unroll
         for (int i = 0; i < DC; ++i) {
-          double* row = wt + i * TN * 3 + tid * 3;
+          double* row = wt + i * 96 + lane * 3;
 #pragma unroll
           for (int c = 0; c < 3; ++c) row[c] = jc0[i] * jx0[c] + jc1[i] * jx1[c];
         }
@@ -227,56 +253,46 @@ __global__ void __launch_bounds__(TN) ba_blocks_kernel(
             hss[2] += jc0[7] * jc0[7] + jc1[7] * jc1[7];
           }
         }
-      }
-      else {
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { jc0[i] = 0.0; jc1[i] = 0.0; }
 #pragma unroll
         for (int i = 0; i < DC; ++i) {
-          double* row = wt + i * TN * 3 + tid * 3;
+          double* row = wt + i * 96 + lane * 3;
           row[0] = 0.0; row[1] = 0.0; row[2] = 0.0;
         }
       }
-      // reduce camera values across the warp
-      {
-        constexpr int K1 = C::K1, K2 = C::K2;
-        constexpr int KP1 = K1 <= 1 ? 1 : (K1 <= 2 ? 2 : (K1 <= 4 ? 4 : (K1 <= 8 ? 8 : (K1 <= 16 ? 16 : 32))));
-        double a[KP1];
-#pragma unroll
-        for (int i = 0; i < KP1; ++i) a[i] = (i < K1) ? v[i] : 0.0;
-        const double r1 = warp_reduce_scatter<KP1>(a, lane);
-        if (lane < K1) red[warp * KR + lane] = r1;
-        if constexpr (K2 > 0) {
-          constexpr int KP2 = K2 <= 1 ? 1 : (K2 <= 2 ? 2 : (K2 <= 4 ? 4 : (K2 <= 8 ? 8 : 16)));
-          double b[KP2];
-#pragma unroll
-          for (int i = 0; i < KP2; ++i) b[i] = (i < K2) ? v[K1 + (i < K2 ? i : 0)] : 0.0;
-          const double r2v = warp_reduce_scatter<KP2>(b, lane);
-          if (lane < K2) red[warp * KR + K1 + lane] = r2v;
-        }
-      }
-      if (USE_TMA) fence_proxy_async();
-      __syncthreads();                                            // (A) tile + partials complete
+      // hand the warp tile to the TMA engine; nobody else touches it
       if (USE_TMA) {
-        if (tid == 0) {
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0 && nvalid_w > 0) {
 #pragma unroll
           for (int i = 0; i < DC; ++i)
-            tma_store_1d(W + ((size_t)(s * DC + i) * N + n0) * 3, wt + i * TN * 3, nvalid * 24);
+            tma_store_1d(W + ((size_t)(s * DC + i) * N + nw0) * 3, wt + i * 96, nvalid_w * 24);
           tma_store_commit();
-          tma_store_wait_read<1>();     // the other buffer's store has finished reading shared memory
+          tma_store_wait_read<1>();     // the other buffer (frame-1) has been read out
         }
       } else {
+        __syncwarp();
         for (int i = 0; i < DC; ++i)
-          for (int e = tid; e < nvalid * 3; e += TN) W[((size_t)(s * DC + i) * N + n0) * 3 + e] = wt[i * TN * 3 + e];
+          for (int e = lane; e < nvalid_w * 3; e += 32) W[((size_t)(s * DC + i) * N + nw0) * 3 + e] = wt[i * 96 + e];
       }
-      if (tid < KR) {
-        double acc = 0;
+      // camera record: reduce 16 values at a time across the warp, one f64 RED per value per warp
 #pragma unroll
-        for (int wq = 0; wq < NWARP; ++wq) acc += red[wq * KR + tid];
-        if (acc != 0.0) atomicAdd(&camrec[(size_t)s * KR + tid], acc);
+      for (int b = 0; b < NB16; ++b) {
+        double a[16];
+        if (b == 0) cam_batch<DC, NS, KR, 0>(a, jc0, jc1, rx, ry, std::make_integer_sequence<int, 16>{});
+        if (b == 1) cam_batch<DC, NS, KR, 16>(a, jc0, jc1, rx, ry, std::make_integer_sequence<int, 16>{});
+        if (b == 2) cam_batch<DC, NS, KR, 32>(a, jc0, jc1, rx, ry, std::make_integer_sequence<int, 16>{});
+        const double r = warp_reduce_scatter<16>(a, lane);
+        const int k = b * 16 + lane;
+        if (lane < 16 && k < KR && r != 0.0) atomicAdd(&camrec[(size_t)s * KR + k], r);
       }
-      __syncthreads();                                            // (B) red[] and the other W buffer reusable
+      __syncwarp();      // lanes may not overwrite the other buffer before lane 0 returned from wait_group
     }
   }
-  if (USE_TMA && tid == 0) tma_store_wait_all<0>();
+  if (USE_TMA && lane == 0) tma_store_wait_all<0>();
 
   // flush per-point accumulators
   if (active) {
@@ -315,17 +331,19 @@ static int launch_blocks(const vgg_ba_problem* p, double* cost, double* camrec, 
                          double* W, double* shared_out, int frames_per_cta, cudaStream_t stream) {
   using C = BlkCfg<MODEL, MODE>;
   const int S = p->S, N = p->N;
-  const size_t smem = align_up(sizeof(BlkSmem), 128) + sizeof(double) * (2 * C::DC * TN * 3 + NWARP * (C::KR > 8 ? C::KR : 8));
+  const size_t smem = align_up(sizeof(BlkSmem), 128) + sizeof(double) * (NWARP * 2 * C::DC * 96 + NWARP * 8);
   const bool tma_ok = (N % 16 == 0) && ((reinterpret_cast<uintptr_t>(p->uv) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(p->mask) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(W) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(p->poses) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(p->intr) & 15) == 0);
   if (frames_per_cta <= 0) {
-    // enough CTAs to fill 148 SMs x 2 resident CTAs a few times over, chunks a multiple of TS
+    // small problems: one full wave of 148 SMs x 4 resident CTAs (no tail); large ones: whole frame range
+    // per CTA so the per-point accumulators are flushed once.  Chunks are a multiple of TS frames.
     const int nb = (N + TN - 1) / TN;
-    int chunks = (148 * 4 + nb - 1) / nb;
+    int chunks = (148 * 4) / nb;
     if (chunks < 1) chunks = 1;
+    if (chunks > (S + TS - 1) / TS) chunks = (S + TS - 1) / TS;
     frames_per_cta = (S + chunks - 1) / chunks;
     frames_per_cta = ((frames_per_cta + TS - 1) / TS) * TS;
   }
