@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(TN) ba_blocks_kernel(
 
 template <int MODEL, int MODE>
 static int launch_blocks(const vgg_ba_problem* p, double* cost, double* camrec, double* g_p, double* H_pp,
-                         double* W, double* shared_out, int frames_per_cta, cudaStream_t stream) {
+                         double* W, double* shared_out, int frames_per_cta, cudaStream_t stream, bool outputs_zeroed) {
   using C = BlkCfg<MODEL, MODE>;
   const int S = p->S, N = p->N;
   const size_t smem = align_up(sizeof(BlkSmem), 128) + sizeof(double) * (NWARP * 2 * C::DC * 96 + NWARP * 8);
@@ -350,13 +350,15 @@ static int launch_blocks(const vgg_ba_problem* p, double* cost, double* camrec, 
   dim3 grid((N + TN - 1) / TN, (S + frames_per_cta - 1) / frames_per_cta);
   // zero the accumulated outputs (cost | camrec | g_p | H_pp are contiguous in the solver workspace,
   // but this entry point does not assume it)
-  VGG_CUDA_CHECK(cudaMemsetAsync(cost, 0, sizeof(double), stream));
-  VGG_CUDA_CHECK(cudaMemsetAsync(camrec, 0, sizeof(double) * (size_t)S * C::KR, stream));
-  VGG_CUDA_CHECK(cudaMemsetAsync(g_p, 0, sizeof(double) * (size_t)N * 3, stream));
-  VGG_CUDA_CHECK(cudaMemsetAsync(H_pp, 0, sizeof(double) * (size_t)N * 6, stream));
-  VGG_CUDA_CHECK(cudaMemsetAsync(shared_out, 0, sizeof(double) * 8, stream));
-  if (C::NS > 0)
-    VGG_CUDA_CHECK(cudaMemsetAsync(W + (size_t)S * C::DC * N * 3, 0, sizeof(double) * (size_t)C::NS * N * 3, stream));
+  if (!outputs_zeroed) {
+    VGG_CUDA_CHECK(cudaMemsetAsync(cost, 0, sizeof(double), stream));
+    VGG_CUDA_CHECK(cudaMemsetAsync(camrec, 0, sizeof(double) * (size_t)S * C::KR, stream));
+    VGG_CUDA_CHECK(cudaMemsetAsync(g_p, 0, sizeof(double) * (size_t)N * 3, stream));
+    VGG_CUDA_CHECK(cudaMemsetAsync(H_pp, 0, sizeof(double) * (size_t)N * 6, stream));
+    VGG_CUDA_CHECK(cudaMemsetAsync(shared_out, 0, sizeof(double) * 8, stream));
+    if (C::NS > 0)
+      VGG_CUDA_CHECK(cudaMemsetAsync(W + (size_t)S * C::DC * N * 3, 0, sizeof(double) * (size_t)C::NS * N * 3, stream));
+  }
   if (tma_ok) {
     auto kern = ba_blocks_kernel<MODEL, MODE, true>;
     VGG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -373,15 +375,15 @@ static int launch_blocks(const vgg_ba_problem* p, double* cost, double* camrec, 
 }
 
 int ba_build_blocks(const vgg_ba_problem* p, double* cost, double* camrec, double* g_p, double* H_pp, double* W,
-                    double* shared_out, int frames_per_cta, cudaStream_t stream) {
+                    double* shared_out, int frames_per_cta, cudaStream_t stream, bool outputs_zeroed) {
   const int key = p->camera_model * 3 + p->intr_mode;
   switch (key) {
-    case 0: return launch_blocks<0, 0>(p, cost, camrec, g_p, H_pp, W, shared_out, frames_per_cta, stream);
-    case 1: return launch_blocks<0, 1>(p, cost, camrec, g_p, H_pp, W, shared_out, frames_per_cta, stream);
-    case 2: return launch_blocks<0, 2>(p, cost, camrec, g_p, H_pp, W, shared_out, frames_per_cta, stream);
-    case 3: return launch_blocks<1, 0>(p, cost, camrec, g_p, H_pp, W, shared_out, frames_per_cta, stream);
-    case 4: return launch_blocks<1, 1>(p, cost, camrec, g_p, H_pp, W, shared_out, frames_per_cta, stream);
-    case 5: return launch_blocks<1, 2>(p, cost, camrec, g_p, H_pp, W, shared_out, frames_per_cta, stream);
+    case 0: return launch_blocks<0, 0>(p, cost, camrec, g_p, H_pp, W, shared_out, frames_per_cta, stream, outputs_zeroed);
+    case 1: return launch_blocks<0, 1>(p, cost, camrec, g_p, H_pp, W, shared_out, frames_per_cta, stream, outputs_zeroed);
+    case 2: return launch_blocks<0, 2>(p, cost, camrec, g_p, H_pp, W, shared_out, frames_per_cta, stream, outputs_zeroed);
+    case 3: return launch_blocks<1, 0>(p, cost, camrec, g_p, H_pp, W, shared_out, frames_per_cta, stream, outputs_zeroed);
+    case 4: return launch_blocks<1, 1>(p, cost, camrec, g_p, H_pp, W, shared_out, frames_per_cta, stream, outputs_zeroed);
+    case 5: return launch_blocks<1, 2>(p, cost, camrec, g_p, H_pp, W, shared_out, frames_per_cta, stream, outputs_zeroed);
   }
   set_error("bad camera_model/intr_mode %d/%d", p->camera_model, p->intr_mode);
   return VGG_EINVAL;

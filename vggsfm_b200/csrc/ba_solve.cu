@@ -21,7 +21,7 @@ void set_error(const char* fmt, ...) {
 
 // kernels (ba_blocks.cu / ba_schur.cu)
 int ba_build_blocks(const vgg_ba_problem* p, double* cost, double* camrec, double* g_p, double* H_pp, double* W,
-                    double* shared_out, int frames_per_cta, cudaStream_t stream);
+                    double* shared_out, int frames_per_cta, cudaStream_t stream, bool outputs_zeroed = false);
 int launch_jacobi_scale_points(int N, const double* H_pp, double* sc_p, int enable, cudaStream_t st);
 int launch_jacobi_scale_cams(int D, const double* hdiag, double* sc_c, int enable, cudaStream_t st);
 int launch_point_prep(int N, const double* H_pp, const double* g_p, const double* sc_p, const uint8_t* point_const,
@@ -51,6 +51,24 @@ int launch_gradmax(int D, int N, const double* gvec, const uint8_t* pconst, cons
 size_t chol_workspace_doubles(int n);
 int chol_lower_inplace(int n, int lda, double* A, double* Ldiag, int* info, cudaStream_t st);
 
+// gathers the accept/reject scalars into one 24-double record so the host reads them with ONE copy:
+// [0..7] = scal[0..7], [8..15] = small[0..7], [16] = potrf info, [17] = potrs info
+__global__ void pack_scalars_kernel(const double* __restrict__ scal, const double* __restrict__ small,
+                                    const int* __restrict__ info, double* __restrict__ out) {
+  const int i = threadIdx.x;
+  if (i < 8) out[i] = scal[i];
+  else if (i < 16) out[i] = small[i - 8];
+  else if (i < 18) out[i] = (double)info[i - 16];
+}
+
+static double* pinned_scalars() {
+  static thread_local double* h = nullptr;
+  if (!h) {
+    if (cudaHostAlloc(reinterpret_cast<void**>(&h), sizeof(double) * 32, cudaHostAllocDefault) != cudaSuccess) h = nullptr;
+  }
+  return h;
+}
+
 static int dims_of(int model, int mode, int* dc, int* ns, int* KR) {
   if (model != VGG_SIMPLE_PINHOLE && model != VGG_SIMPLE_RADIAL) return VGG_EINVAL;
   const int ni = model == VGG_SIMPLE_PINHOLE ? 1 : 2;
@@ -79,6 +97,7 @@ struct Layout {
   double *AR;        // [D*Dpad | rhs Dpad | hdiag Dpad | gvec Dpad]  (one all-reduce)
   double *small;     // [8 scalars | gvec_candidate Dpad]           (one small all-reduce)
   double *scal;      // [16]
+  double *packed;    // [24] scalars gathered for the host
   double *potrf_work;
   double *chol_diag;
   int *dev_info;
@@ -120,6 +139,7 @@ static int make_layout(int S, int N, int model, int mode, void* base, size_t cap
   L->AR = c.take<double>((size_t)L->D * L->Dpad + 3 * (size_t)L->Dpad);
   L->small = c.take<double>(8 + (size_t)L->Dpad);
   L->scal = c.take<double>(16);
+  L->packed = c.take<double>(32);
   L->potrf_lwork = potrf_lwork;
   L->potrf_work = c.take<double>(potrf_lwork);
   L->chol_diag = c.take<double>(chol_workspace_doubles(L->D));
@@ -337,10 +357,26 @@ int vgg_ba_solve(const vgg_ba_problem* prob, const vgg_ba_options* opt_in, void*
     p.intr = L.intr[which];
     p.points = L.points[which];
     const BlockSet& b = L.blk[which];
-    return ba_build_blocks(&p, b.cost, b.camrec, b.g_p, b.H_pp, b.W, b.shared, 0, st);
+    // cost | shared | camrec | g_p | H_pp are carved back to back: one memset covers all accumulators
+    const size_t acc_bytes = reinterpret_cast<char*>(b.H_pp + (size_t)N * 6) - reinterpret_cast<char*>(b.cost);
+    VGG_CUDA_CHECK(cudaMemsetAsync(b.cost, 0, acc_bytes, st));
+    if (ns > 0) VGG_CUDA_CHECK(cudaMemsetAsync(b.W + (size_t)S * dc * N * 3, 0, sizeof(double) * (size_t)ns * N * 3, st));
+    return ba_build_blocks(&p, b.cost, b.camrec, b.g_p, b.H_pp, b.W, b.shared, 0, st, true);
   };
   // global cost + gradient max-norm of block set `which`; result lands in host h[0..2] = cost, gmax_c, gmax_p
-  double h_scal[16];
+  double* h_scal = pinned_scalars();
+  if (!h_scal) {
+    set_error("cudaHostAlloc for the scalar read-back failed");
+    return VGG_ECUDA;
+  }
+  VGG_CUDA_CHECK(cudaMemsetAsync(L.dev_info, 0, sizeof(int) * 4, st));
+  auto read_scalars = [&]() -> int {
+    pack_scalars_kernel<<<1, 32, 0, st>>>(L.scal, L.small, L.dev_info, L.packed);
+    VGG_LAUNCH_CHECK();
+    VGG_CUDA_CHECK(cudaMemcpyAsync(h_scal, L.packed, sizeof(double) * 24, cudaMemcpyDeviceToHost, st));
+    VGG_CUDA_CHECK(cudaStreamSynchronize(st));
+    return VGG_OK;
+  };
   auto cost_and_gradient = [&](int which, double* cost_out, double* gmax_out) -> int {
     const BlockSet& b = L.blk[which];
     int r;
@@ -351,9 +387,7 @@ int vgg_ba_solve(const vgg_ba_problem* prob, const vgg_ba_options* opt_in, void*
     VGG_CUDA_CHECK(cudaMemsetAsync(L.scal + 4, 0, sizeof(double) * 2, st));
     if ((r = launch_gradmax(D, N, L.small + 8, prob->param_const, b.g_p, prob->point_const, L.scal, st))) return r;
     if (allreduce && (r = allreduce(ar_user, L.scal + 5, 1, 1, st))) return r;
-    VGG_CUDA_CHECK(cudaMemcpyAsync(h_scal, L.scal, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
-    VGG_CUDA_CHECK(cudaMemcpyAsync(h_scal + 8, L.small, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
-    VGG_CUDA_CHECK(cudaStreamSynchronize(st));
+    if ((r = read_scalars())) return r;
     *cost_out = h_scal[8];
     *gmax_out = fmax(h_scal[4], h_scal[5]);
     return VGG_OK;
@@ -420,11 +454,8 @@ int vgg_ba_solve(const vgg_ba_problem* prob, const vgg_ba_options* opt_in, void*
     if (allreduce && (rc = allreduce(ar_user, L.small, 8 + (size_t)L.Dpad, 0, st))) return rc;
     if ((rc = launch_gradmax(D, N, L.small + 8, prob->param_const, L.blk[cand].g_p, prob->point_const, L.scal, st))) return rc;
     if (allreduce && (rc = allreduce(ar_user, L.scal + 5, 1, 1, st))) return rc;
-    int h_info[2] = {0, 0};
-    VGG_CUDA_CHECK(cudaMemcpyAsync(h_scal, L.scal, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
-    VGG_CUDA_CHECK(cudaMemcpyAsync(h_scal + 8, L.small, sizeof(double) * 8, cudaMemcpyDeviceToHost, st));
-    VGG_CUDA_CHECK(cudaMemcpyAsync(h_info, L.dev_info, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
-    VGG_CUDA_CHECK(cudaStreamSynchronize(st));
+    if ((rc = read_scalars())) return rc;
+    const int h_info[2] = {(int)h_scal[16], (int)h_scal[17]};
 
     const double c_cost = h_scal[8];
     const double quad = h_scal[0] + h_scal[9];
