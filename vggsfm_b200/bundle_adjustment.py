@@ -319,3 +319,107 @@ def bundle_adjustment(points3d, extrinsics, intrinsics, extra_params, tracks, ma
 
 
 run_ba = bundle_adjustment   # the name BASELINE.json's north_star uses for this call
+
+
+# --------------------------------------------------------------------------------------------------
+# mirrors of the reference's BA drivers (vggsfm/utils/triangulation.py:1020-1242)
+# --------------------------------------------------------------------------------------------------
+
+class Reconstruction:
+    """Tensor-backed stand-in for the ``pycolmap.Reconstruction`` the reference returns as the last tuple
+    element (triangulation.py:1073,1208).  Holds what downstream code reads back through
+    pycolmap_to_batch_matrix (tensor_to_pycolmap.py:163-214); the COLMAP binary writer is listed as next
+    in DESIGN.md section 8."""
+
+    def __init__(self, points3D, extrinsics, intrinsics, extra_params, tracks, masks, image_size, camera_type,
+                 shared_camera, summary=None):
+        self.points3D_xyz, self.extrinsics, self.intrinsics, self.extra_params = points3D, extrinsics, intrinsics, extra_params
+        self.tracks, self.masks, self.image_size = tracks, masks, image_size
+        self.camera_type, self.shared_camera, self.summary = camera_type, shared_camera, summary
+
+    def num_points3D(self):
+        return int(self.points3D_xyz.shape[0])
+
+    def num_images(self):
+        return int(self.extrinsics.shape[0])
+
+
+def _revert_negative_focal(extr_new, K_new, extra_new, extr_old, K_old, extra_old):
+    """triangulation.py:1066-1071 / 1158-1165: cameras whose optimised focal is negative keep their old values."""
+    bad = K_new[:, 0, 0] < 0
+    if bad.any():
+        extr_new[bad] = extr_old[bad].to(extr_new.dtype)
+        K_new[bad] = K_old[bad].to(K_new.dtype)
+        if extra_new is not None:
+            extra_new[bad] = extra_old[bad].to(extra_new.dtype)
+    return extr_new, K_new, extra_new
+
+
+def global_BA(triangulated_points, valid_tracks, pred_tracks, inlier_mask, extrinsics, intrinsics, extra_params,
+              image_size, shared_camera=False, camera_type="SIMPLE_PINHOLE", allreduce=None):
+    """vggsfm/utils/triangulation.py:1020-1073 with the same arguments and return tuple
+    (points3D_opt, extrinsics, intrinsics, extra_params, reconstruction)."""
+    BA_points = triangulated_points[valid_tracks]
+    BA_tracks = pred_tracks[:, valid_tracks]
+    BA_inlier_masks = inlier_mask[valid_tracks].transpose(0, 1)
+    pts, extr, K, extra, valid_idx, summary = bundle_adjustment(
+        BA_points, extrinsics, intrinsics, extra_params, BA_tracks, BA_inlier_masks, shared_camera=shared_camera,
+        camera_type=camera_type, options=prepare_ba_options(), allreduce=allreduce)
+    extr, K, extra = _revert_negative_focal(extr, K, extra, extrinsics, intrinsics, extra_params)
+    rec = Reconstruction(pts, extr, K, extra, BA_tracks[:, valid_idx], BA_inlier_masks[:, valid_idx], image_size,
+                         camera_type, shared_camera, summary)
+    return pts, extr, K, extra, rec
+
+
+def get_valid_frame_mask(intrinsics, extrinsics, extra_params, scale):
+    """vggsfm/utils/triangulation.py:1222-1242."""
+    valid = (intrinsics[:, 0, 0] >= 0.1 * scale) & (intrinsics[:, 0, 0] <= 30 * scale)
+    if extra_params is not None:
+        if extra_params.dim() == 1:
+            extra_params = extra_params[:, None]
+        valid = valid & (extra_params.abs() <= 1.0).all(dim=-1)
+    return valid & (extrinsics[:, :, 3].abs() <= 30).all(-1)
+
+
+def iterative_global_BA(pred_tracks, intrinsics, extrinsics, pred_vis, pred_score, valid_tracks, points3D_opt,
+                        image_size, shared_camera=False, min_valid_track_length=2, max_reproj_error=1,
+                        ba_options=None, lastBA=False, camera_type="SIMPLE_PINHOLE", extra_params=None,
+                        allreduce=None):
+    """vggsfm/utils/triangulation.py:1076-1209: re-triangulate (128 hypotheses) -> keep the last BA's points for
+    already-valid tracks -> reprojection/triangle filter -> BA (default options) -> filter again -> compaction.
+    Same arguments; returns (points3D_opt, extrinsics, intrinsics, extra_params, valid_tracks, BA_inlier_masks,
+    reconstruction)."""
+    from . import triangulation as tri
+    tn = tri.cam_from_img(pred_tracks, intrinsics, extra_params)
+    best_points, best_num, best_mask = tri.triangulate_tracks(extrinsics, tn, track_vis=pred_vis, track_score=pred_score,
+                                                             max_ransac_iters=128)
+    best_points[valid_tracks] = points3D_opt.to(best_points.dtype)                      # :1110
+    _, filtered = tri.filter_all_points3D(best_points, pred_tracks, extrinsics, intrinsics, extra_params=extra_params,
+                                          max_reproj_error=max_reproj_error, return_detail=True)
+    valid_tracks = filtered.sum(dim=0) >= min_valid_track_length
+    BA_points = best_points[valid_tracks]
+    BA_tracks = pred_tracks[:, valid_tracks]
+    BA_inlier_masks = filtered[:, valid_tracks]
+    pts, extr, K, extra, valid_idx, summary = bundle_adjustment(
+        BA_points, extrinsics, intrinsics, extra_params, BA_tracks, BA_inlier_masks, shared_camera=shared_camera,
+        camera_type=camera_type, options=ba_options or default_options(), allreduce=allreduce)
+    if valid_idx.numel() != BA_points.shape[0]:
+        # tracks with < 2 inliers never reach this point (min_valid_track_length >= 2), kept for safety
+        full = torch.zeros(BA_points.shape[0], 3, dtype=pts.dtype, device=pts.device)
+        full[valid_idx] = pts
+        pts = full
+    extr, K, extra = _revert_negative_focal(extr, K, extra, extrinsics, intrinsics, extra_params)
+    _, filtered = tri.filter_all_points3D(pts, pred_tracks[:, valid_tracks], extr, K, extra_params=extra,
+                                          max_reproj_error=max_reproj_error, return_detail=True)
+    valid_after = filtered.sum(dim=0) >= min_valid_track_length
+    valid_tmp = valid_tracks.clone()
+    valid_tmp[valid_tracks] = valid_after
+    valid_tracks = valid_tmp
+    pts = pts[valid_after]
+    BA_inlier_masks = filtered[:, valid_after]
+    rec = None
+    if lastBA:
+        p2, e2 = normalize(extr, pts, 5.0, 0.1, 0.9)                                    # filter_reconstruction (:1199)
+        rec = Reconstruction(p2, e2, K, extra, pred_tracks[:, valid_tracks], BA_inlier_masks, image_size, camera_type,
+                             shared_camera, summary)
+    return pts, extr, K, extra, valid_tracks, BA_inlier_masks, rec
