@@ -27,6 +27,10 @@ poses, intr_t, X = t(extr), t(intr), t(pts)
 model, mode = ba.SIMPLE_RADIAL, ba.INTR_SHARED
 for _ in range(2):
     ba.build_blocks(uv, mask, poses, intr_t, X, model, mode)
+torch.cuda.synchronize()
+if os.environ.get("PROF_MODE", "all") == "blocks":
+    print("blocks only")
+    sys.exit(0)
 opt = ba.default_options()
 opt.max_num_iterations = 2
 opt.gradient_tolerance = 0.0

@@ -3,12 +3,11 @@
 // The reduced system of configuration C3 is 2402 x 2402 float64: cuSOLVER's potrf spends ~3.4 ms in ~250
 // tiny launches on it, more than the Schur build once the tracks are sharded over GPUs.  This
 // factorisation uses two launches per 64-column panel:
-//   chol_panel_kernel     every CTA re-factors the 64x64 diagonal block in shared memory (cheap, removes a
-//                         launch and a dependency), inverts it, and multiplies its 64 rows of the panel by
-//                         L_kk^-T (dense 64^3 product instead of per-row substitution chains);
-//                         CTA 0 parks the factored diagonal block in a side buffer.
-//   chol_trailing_kernel  A22 -= P P^T on 128x128 tiles with the whole K=64 panel resident in shared memory
-//                         (8x8 register tiles on the FP64 FMA pipe).
+//   chol_panel_kernel     every CTA re-factors the 64x64 diagonal block (one warp, rows in registers,
+//                         shuffles for the pivot column -- no barrier per column) while its other warps stage
+//                         the CTA's 64 panel rows; then a right-looking triangular solve, 4 threads per row,
+//                         turns the rows into L_ik.  CTA 0 parks the factored diagonal block in a side buffer.
+//   chol_trailing_kernel  A22 -= P P^T on 64x64 tiles with the whole K=64 panel resident in shared memory.
 // and one copy-back of the diagonal blocks at the end.  Ceres' counterpart: DENSE_SCHUR's LLT / LAPACK potrf
 // inside SchurComplementSolver (reached from pycolmap.bundle_adjustment).
 #include "common.cuh"
@@ -16,97 +15,140 @@
 namespace vgg {
 
 constexpr int CH_NB = 64;
+constexpr int CH_LD = 66;     // shared-memory row stride (even: 16-byte aligned pairs; 66*2 mod 32 = 4: conflict-free)
+
+// Cholesky of a 32x32 block held one row per lane (a[c] = row `lane`, col c; only c <= lane is meaningful).
+// Returns 0 or 1 + index of the first non-positive pivot.
+__device__ __forceinline__ int warp_chol32(double (&a)[32], int lane) {
+  int fail = 0;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const double pj = __shfl_sync(0xffffffffu, a[j], j);
+    if (!(pj > 0.0) && fail == 0) fail = j + 1;
+    const double d = sqrt(pj > 0.0 ? pj : 1.0);
+    a[j] = (lane == j) ? d : a[j] / d;
+#pragma unroll
+    for (int c = j + 1; c < 32; ++c) {
+      const double lc = __shfl_sync(0xffffffffu, a[j], c);
+      if (lane >= c) a[c] = fma(-a[j], lc, a[c]);
+    }
+  }
+  return fail;
+}
+
+// In-place Cholesky of the 64x64 block in shared memory Ls (stride CH_LD), by ONE warp.
+__device__ __forceinline__ int warp_chol64(double* Ls, int lane) {
+  double a[32];
+  // A11
+#pragma unroll
+  for (int c = 0; c < 32; ++c) a[c] = Ls[lane * CH_LD + c];
+  int fail = warp_chol32(a, lane);
+#pragma unroll
+  for (int c = 0; c < 32; ++c) Ls[lane * CH_LD + c] = (c <= lane) ? a[c] : 0.0;
+  __syncwarp();
+  // A21 <- A21 L11^-T (row 32+lane), right-looking substitution
+  double b[32];
+#pragma unroll
+  for (int c = 0; c < 32; ++c) b[c] = Ls[(32 + lane) * CH_LD + c];
+#pragma unroll
+  for (int m = 0; m < 32; ++m) {
+    const double x = b[m] / Ls[m * CH_LD + m];
+    b[m] = x;
+#pragma unroll
+    for (int j = m + 1; j < 32; ++j) b[j] = fma(-x, Ls[j * CH_LD + m], b[j]);
+  }
+#pragma unroll
+  for (int c = 0; c < 32; ++c) Ls[(32 + lane) * CH_LD + c] = b[c];
+  __syncwarp();
+  // A22 <- A22 - L21 L21^T (row 32+lane, cols 32..63), then its Cholesky
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    double s = Ls[(32 + lane) * CH_LD + 32 + c];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) s = fma(-b[k], Ls[(32 + c) * CH_LD + k], s);
+    a[c] = s;
+  }
+  const int f2 = warp_chol32(a, lane);
+  if (fail == 0 && f2 != 0) fail = 32 + f2;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) Ls[(32 + lane) * CH_LD + 32 + c] = (c <= lane) ? a[c] : 0.0;
+  // zero the upper-right block so the factor is a clean lower triangle
+#pragma unroll
+  for (int c = 0; c < 32; ++c) Ls[lane * CH_LD + 32 + c] = 0.0;
+  __syncwarp();
+  return fail;
+}
 
 // grid.x = 1 + number of 64-row chunks below the diagonal block; block 256
 __global__ void __launch_bounds__(256) chol_panel_kernel(int n, int lda, int k0, double* __restrict__ A,
                                                          double* __restrict__ Ldiag /*[nblk][64*64]*/,
                                                          int* __restrict__ info) {
   extern __shared__ __align__(16) double panel_smem[];
-  double (*L)[CH_NB + 1] = reinterpret_cast<double (*)[CH_NB + 1]>(panel_smem);
-  double (*Li)[CH_NB + 1] = reinterpret_cast<double (*)[CH_NB + 1]>(panel_smem + CH_NB * (CH_NB + 1));
-  double (*T)[CH_NB + 1] = reinterpret_cast<double (*)[CH_NB + 1]>(panel_smem + 2 * CH_NB * (CH_NB + 1));
-  __shared__ int fail;
-  const int tid = threadIdx.x;
+  double* Ls = panel_smem;
+  double* Ts = panel_smem + CH_NB * CH_LD;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = min(CH_NB, n - k0);
-  if (tid == 0) fail = 0;
-  // load the (unfactored) diagonal block, lower part; pad with identity
+  const int r0 = k0 + CH_NB + ((int)blockIdx.x - 1) * CH_NB;
+  // diagonal block (lower part, identity padding): a warp reads one 512 B row
   for (int e = tid; e < CH_NB * CH_NB; e += 256) {
-    const int i = e / CH_NB, j = e % CH_NB;
+    const int i = e >> 6, j = e & 63;
     double v = (i == j) ? 1.0 : 0.0;
     if (i < nb && j < nb && j <= i) v = A[(size_t)(k0 + i) * lda + k0 + j];
-    L[i][j] = v;
-    Li[i][j] = 0.0;
+    Ls[i * CH_LD + j] = v;
   }
   __syncthreads();
-  // unblocked Cholesky in shared memory
-  for (int j = 0; j < CH_NB; ++j) {
-    if (tid == 0) {
-      const double d = L[j][j];
-      if (!(d > 0.0)) { fail = j + 1; L[j][j] = 1.0; }
-      else L[j][j] = sqrt(d);
-    }
-    __syncthreads();
-    const double dj = L[j][j];
-    if (tid > j && tid < CH_NB) L[tid][j] /= dj;
-    __syncthreads();
-    // trailing update of the lower triangle: rows i > j, cols j < c <= i
-    const int m = CH_NB - 1 - j;
-    for (int e = tid; e < m * m; e += 256) {
-      const int i = j + 1 + e / m, c = j + 1 + e % m;
-      if (c <= i) L[i][c] -= L[i][j] * L[c][j];
-    }
-    __syncthreads();
-  }
-  if (fail && blockIdx.x == 0 && tid == 0) atomicCAS(info, 0, k0 + fail);
-  // inverse of the lower-triangular factor: column j by thread j (forward substitution)
-  if (tid < CH_NB) {
-    const int j = tid;
-    Li[j][j] = 1.0 / L[j][j];
-    for (int i = j + 1; i < CH_NB; ++i) {
-      double s = 0.0;
-      for (int m2 = j; m2 < i; ++m2) s += L[i][m2] * Li[m2][j];
-      Li[i][j] = -s / L[i][i];
+  if (warp == 0) {
+    const int fail = warp_chol64(Ls, lane);
+    if (fail && blockIdx.x == 0 && lane == 0) atomicCAS(info, 0, k0 + fail);
+  } else if (blockIdx.x > 0) {
+    // meanwhile: stage this CTA's 64 panel rows
+    for (int e = tid - 32; e < CH_NB * CH_NB; e += 224) {
+      const int r = e >> 6, c = e & 63;
+      Ts[r * CH_LD + c] = (r0 + r < n && c < nb) ? A[(size_t)(r0 + r) * lda + k0 + c] : 0.0;
     }
   }
   __syncthreads();
   if (blockIdx.x == 0) {
     double* dst = Ldiag + (size_t)(k0 / CH_NB) * CH_NB * CH_NB;
-    for (int e = tid; e < CH_NB * CH_NB; e += 256) dst[e] = L[e / CH_NB][e % CH_NB];
+    for (int e = tid; e < CH_NB * CH_NB; e += 256) dst[e] = Ls[(e >> 6) * CH_LD + (e & 63)];
     return;
   }
-  // panel rows: X = A_ik L^-T  ->  X[r][j] = sum_{m<=j} A[r][m] Li[j][m]
-  const int r0 = k0 + CH_NB + (blockIdx.x - 1) * CH_NB;
-  for (int e = tid; e < CH_NB * CH_NB; e += 256) {
-    const int r = e / CH_NB, c = e % CH_NB;
-    T[r][c] = (r0 + r < n && c < nb) ? A[(size_t)(r0 + r) * lda + k0 + c] : 0.0;
-  }
-  __syncthreads();
-  // 256 threads: thread -> (row r = tid/4, 16 columns j = (tid%4) + 4*jj)
+  // X L^T = A_ik, right-looking: 4 threads per row, thread q owns columns j = q + 4*jj
   {
     const int r = tid >> 2, q = tid & 3;
-    double acc[16];
+    double a[16];
 #pragma unroll
-    for (int jj = 0; jj < 16; ++jj) acc[jj] = 0.0;
-    for (int m2 = 0; m2 < CH_NB; ++m2) {
-      const double a = T[r][m2];
+    for (int jj = 0; jj < 16; ++jj) a[jj] = Ts[r * CH_LD + q + 4 * jj];
 #pragma unroll
-      for (int jj = 0; jj < 16; ++jj) acc[jj] = fma(a, Li[q + 4 * jj][m2], acc[jj]);   // Li[j][m] = 0 for m > j
-    }
-    if (r0 + r < n) {
+    for (int m = 0; m < CH_NB; ++m) {
+      const int qm = m & 3, jm = m >> 2;
+      double x = a[jm] / Ls[m * CH_LD + m];
+      x = __shfl_sync(0xffffffffu, x, (lane & ~3) | qm);
+      if (q == qm) a[jm] = x;
 #pragma unroll
       for (int jj = 0; jj < 16; ++jj) {
-        const int j = q + 4 * jj;
-        if (j < nb) A[(size_t)(r0 + r) * lda + k0 + j] = acc[jj];
+        // column j = q + 4*jj is still open when j > m
+        if (4 * jj + 3 > m) {                       // compile-time prune; exact test below
+          const int j = q + 4 * jj;
+          if (j > m) a[jj] = fma(-x, Ls[j * CH_LD + m], a[jj]);
+        }
       }
     }
+#pragma unroll
+    for (int jj = 0; jj < 16; ++jj) Ts[r * CH_LD + q + 4 * jj] = a[jj];
+  }
+  __syncthreads();
+  for (int e = tid; e < CH_NB * CH_NB; e += 256) {
+    const int r = e >> 6, c = e & 63;
+    if (r0 + r < n && c < nb) A[(size_t)(r0 + r) * lda + k0 + c] = Ts[r * CH_LD + c];
   }
 }
 
-// A[t0.., t0..] -= P P^T, P = A[t0.., k0..k0+63]; 128x128 tiles (lower), 256 threads, 8x8 per thread
+// A[t0.., t0..] -= P P^T, P = A[t0.., k0..k0+63]; 64x64 tiles (lower), 256 threads, 4x4 outputs per thread
 __global__ void __launch_bounds__(256) chol_trailing_kernel(int n, int lda, int k0, int t0, double* __restrict__ A) {
   extern __shared__ __align__(16) double ch_smem[];
-  double* As = ch_smem;                       // [64][128]
-  double* Bs = ch_smem + CH_NB * 128;         // [64][128]
+  double* As = ch_smem;                         // [64 rows][CH_LD]
+  double* Bs = ch_smem + CH_NB * CH_LD;
   int t = blockIdx.x;
   int bi = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
   while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
@@ -114,58 +156,52 @@ __global__ void __launch_bounds__(256) chol_trailing_kernel(int n, int lda, int 
   const int bj = t - bi * (bi + 1) / 2;
   const bool diag = bi == bj;
   const int tid = threadIdx.x;
-  const int ri = t0 + bi * 128, rj = t0 + bj * 128;
-  // load panel rows (row-major, k contiguous) transposed into [k][row]: lane <-> row, 16 B per load
-  {
-    const int row = tid & 127, half = tid >> 7;
-    for (int kp = half; kp < CH_NB / 2; kp += 2) {
-      double2 va = make_double2(0.0, 0.0), vb = make_double2(0.0, 0.0);
-      if (ri + row < n) va = *reinterpret_cast<const double2*>(A + (size_t)(ri + row) * lda + k0 + 2 * kp);
-      As[(2 * kp) * 128 + row] = va.x;
-      As[(2 * kp + 1) * 128 + row] = va.y;
-      if (!diag) {
-        if (rj + row < n) vb = *reinterpret_cast<const double2*>(A + (size_t)(rj + row) * lda + k0 + 2 * kp);
-        Bs[(2 * kp) * 128 + row] = vb.x;
-        Bs[(2 * kp + 1) * 128 + row] = vb.y;
-      }
+  const int ri = t0 + bi * 64, rj = t0 + bj * 64;
+  // panel rows, row-major (k contiguous): a warp loads one 512 B row per step as 32 double2
+  for (int e = tid; e < 64 * 32; e += 256) {
+    const int row = e >> 5, kp = e & 31;
+    double2 va = make_double2(0.0, 0.0);
+    if (ri + row < n) va = *reinterpret_cast<const double2*>(A + (size_t)(ri + row) * lda + k0 + 2 * kp);
+    *reinterpret_cast<double2*>(As + row * CH_LD + 2 * kp) = va;
+    if (!diag) {
+      double2 vb = make_double2(0.0, 0.0);
+      if (rj + row < n) vb = *reinterpret_cast<const double2*>(A + (size_t)(rj + row) * lda + k0 + 2 * kp);
+      *reinterpret_cast<double2*>(Bs + row * CH_LD + 2 * kp) = vb;
     }
   }
   __syncthreads();
   const double* bs = diag ? As : Bs;
-  const int ty = tid >> 4, tx = tid & 15;
-  double acc[8][8];
+  const int ty = tid >> 4, tx = tid & 15;         // rows ty + 16 i, cols tx + 16 j
+  double acc[4][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0;
-#pragma unroll 4
-  for (int kk = 0; kk < CH_NB; ++kk) {
-    double a[8], b[8];
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+#pragma unroll 8
+  for (int kk = 0; kk < CH_NB; kk += 2) {
+    double2 a[4], b[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const double2 av = *reinterpret_cast<const double2*>(As + kk * 128 + ty * 2 + 32 * i);
-      a[2 * i] = av.x; a[2 * i + 1] = av.y;
-      const double2 bv = *reinterpret_cast<const double2*>(bs + kk * 128 + tx * 2 + 32 * i);
-      b[2 * i] = bv.x; b[2 * i + 1] = bv.y;
+      a[i] = *reinterpret_cast<const double2*>(As + (ty + 16 * i) * CH_LD + kk);
+      b[i] = *reinterpret_cast<const double2*>(bs + (tx + 16 * i) * CH_LD + kk);
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+      for (int j = 0; j < 4; ++j) {
+        acc[i][j] = fma(a[i].x, b[j].x, acc[i][j]);
+        acc[i][j] = fma(a[i].y, b[j].y, acc[i][j]);
+      }
   }
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int r = ri + ty * 2 + (i & 1) + 32 * (i >> 1);
+  for (int i = 0; i < 4; ++i) {
+    const int r = ri + ty + 16 * i;
     if (r >= n) continue;
 #pragma unroll
-    for (int jp = 0; jp < 4; ++jp) {
-      const int c = rj + tx * 2 + 32 * jp;
-      if (c > r || c >= n) continue;           // lower triangle only (c even: pair c, c+1)
-      double* p = A + (size_t)r * lda + c;
-      double2 v = *reinterpret_cast<double2*>(p);
-      v.x -= acc[i][2 * jp];
-      v.y -= acc[i][2 * jp + 1];               // element (r, c+1) may sit above the diagonal: harmless
-      *reinterpret_cast<double2*>(p) = v;
+    for (int j = 0; j < 4; ++j) {
+      const int c = rj + tx + 16 * j;
+      if (c > r || c >= n) continue;              // lower triangle only
+      A[(size_t)r * lda + c] -= acc[i][j];
     }
   }
 }
@@ -190,23 +226,22 @@ int chol_lower_inplace(int n, int lda, double* A, double* Ldiag, int* info, cuda
   VGG_REQUIRE((lda % 2) == 0, "lda must be even");
   VGG_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int), st));
   const int nblk = (n + CH_NB - 1) / CH_NB;
-  const size_t smem = sizeof(double) * 2 * CH_NB * 128;
-  const size_t psmem = sizeof(double) * 3 * CH_NB * (CH_NB + 1);
+  const size_t smem = sizeof(double) * 2 * CH_NB * CH_LD;
   static bool attr_set = false;
   if (!attr_set) {
     VGG_CUDA_CHECK(cudaFuncSetAttribute(chol_trailing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VGG_CUDA_CHECK(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+    VGG_CUDA_CHECK(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
   for (int b = 0; b < nblk; ++b) {
     const int k0 = b * CH_NB;
     const int below = n - (k0 + CH_NB);
     const int chunks = below > 0 ? (below + CH_NB - 1) / CH_NB : 0;
-    chol_panel_kernel<<<1 + chunks, 256, psmem, st>>>(n, lda, k0, A, Ldiag, info);
+    chol_panel_kernel<<<1 + chunks, 256, smem, st>>>(n, lda, k0, A, Ldiag, info);
     VGG_LAUNCH_CHECK();
     if (below > 0) {
       const int t0 = k0 + CH_NB;
-      const int nt = (n - t0 + 127) / 128;
+      const int nt = (n - t0 + 63) / 64;
       chol_trailing_kernel<<<nt * (nt + 1) / 2, 256, smem, st>>>(n, lda, k0, t0, A);
       VGG_LAUNCH_CHECK();
     }
