@@ -12,6 +12,7 @@
 //                   tiles, cp.async double-buffered k-slabs, split-K with f64 RED epilogue
 //   scale_damp      A = Dc Sraw Dc + diag(clamp(diag(Dc Hcc Dc)))/radius, constant parameters pinned
 //   cam_step / backsub_partial / point_step / cam_update   back-substitution and the candidate state
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace vgg {
@@ -276,6 +277,102 @@ __global__ void __launch_bounds__(SY_THREADS) syrk_kernel(int Kpad, int Dpad, in
 }
 
 // ------------------------------------------------------------------------------------------------
+// Same SYRK on the FP64 tensor path: mma.sync.m8n8k4.f64 (SASS DMMA).  CTA tile 128x128, 8 warps as 4x2,
+// warp tile 32x64 = 4x8 MMA tiles (64 accumulator doubles per lane); operands k-major in shared memory with a
+// 136-double row stride so the four k-rows of a fragment load fall into disjoint bank halves.
+constexpr int SD_LDS = 136;
+
+__device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(SY_THREADS) syrk_dmma_kernel(int Kpad, int Dpad, int k_per_split,
+                                                               const double* __restrict__ Zt,
+                                                               double* __restrict__ Cmat) {
+  extern __shared__ __align__(16) double sd_smem[];
+  int t = blockIdx.x;
+  int bi = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+  while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+  while (bi * (bi + 1) / 2 > t) --bi;
+  const int bj = t - bi * (bi + 1) / 2;
+  const bool diag = (bi == bj);
+  const int kbeg = blockIdx.y * k_per_split;
+  const int kend = min(Kpad, kbeg + k_per_split);
+  const int nslab = (kend - kbeg + SY_BK - 1) / SY_BK;
+  if (nslab <= 0) return;
+  double* As = sd_smem;                                      // [STAGES][BK][SD_LDS]
+  double* Bs = sd_smem + SY_STAGES * SY_BK * SD_LDS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = warp >> 1, wn = warp & 1;                   // 4 x 2 warps
+  const int g = lane >> 2, q = lane & 3;
+
+  auto load_slab = [&](int slab, int stage) {
+    const int k0 = kbeg + slab * SY_BK;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int chunk = tid + i * SY_THREADS;
+      const int kk = chunk >> 6;
+      const int cc = (chunk & 63) * 2;
+      const size_t grow = (size_t)(k0 + kk) * Dpad;
+      cp_async16(As + (stage * SY_BK + kk) * SD_LDS + cc, Zt + grow + bi * SY_BM + cc);
+      if (!diag) cp_async16(Bs + (stage * SY_BK + kk) * SD_LDS + cc, Zt + grow + bj * SY_BM + cc);
+    }
+    cp_async_commit();
+  };
+
+  double c[4][8][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+
+#pragma unroll
+  for (int s = 0; s < SY_STAGES - 1; ++s) {
+    if (s < nslab) load_slab(s, s);
+    else cp_async_commit();
+  }
+  for (int slab = 0; slab < nslab; ++slab) {
+    cp_async_wait<SY_STAGES - 2>();
+    __syncthreads();
+    {
+      const int nxt = slab + SY_STAGES - 1;
+      if (nxt < nslab) load_slab(nxt, nxt % SY_STAGES);
+      else cp_async_commit();
+    }
+    const int stage = slab % SY_STAGES;
+    const double* as = As + stage * SY_BK * SD_LDS;
+    const double* bs = diag ? as : (Bs + stage * SY_BK * SD_LDS);
+#pragma unroll
+    for (int k4 = 0; k4 < SY_BK / 4; ++k4) {
+      double a[4], b[8];
+      const double* arow = as + (k4 * 4 + q) * SD_LDS + wm * 32 + g;
+      const double* brow = bs + (k4 * 4 + q) * SD_LDS + wn * 64 + g;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = arow[i * 8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b[j] = brow[j * 8];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dmma_m8n8k4(c[i][j][0], c[i][j][1], a[i], b[j]);
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = bi * SY_BM + wm * 32 + i * 8 + g;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int cc = bj * SY_BM + wn * 64 + j * 8 + 2 * q;
+      if (c[i][j][0] != 0.0 && (!diag || cc <= r)) atomicAdd(&Cmat[(size_t)r * Dpad + cc], -c[i][j][0]);
+      if (c[i][j][1] != 0.0 && (!diag || cc + 1 <= r)) atomicAdd(&Cmat[(size_t)r * Dpad + cc + 1], -c[i][j][1]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // A (lower, in place) = sc_i sc_j Sraw + diag; constant parameters pinned; b = sc * rhs
 __global__ void scale_damp_kernel(int D, int Dpad, double* __restrict__ A, const double* __restrict__ rhs,
                                   const double* __restrict__ hdiag, const double* __restrict__ sc,
@@ -498,13 +595,19 @@ int launch_syrk(int Kpad, int Dpad, const double* Zt, double* Cmat, cudaStream_t
   int slabs_per = (nslab + splits - 1) / splits;
   splits = (nslab + slabs_per - 1) / slabs_per;
   const size_t smem = sizeof(double) * 2 * SY_STAGES * SY_BK * SY_BM;
+  const size_t smem_d = sizeof(double) * 2 * SY_STAGES * SY_BK * SD_LDS;
   static bool attr_set = false;
+  static int use_dmma = 0;
   if (!attr_set) {
     VGG_CUDA_CHECK(cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VGG_CUDA_CHECK(cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
+    const char* e = getenv("VGG_SYRK_DMMA");
+    use_dmma = (e && e[0] == '1') ? 1 : 0;
     attr_set = true;
   }
   dim3 grid(ntiles, splits);
-  syrk_kernel<<<grid, SY_THREADS, smem, st>>>(Kpad, Dpad, slabs_per * SY_BK, Zt, Cmat);
+  if (use_dmma) syrk_dmma_kernel<<<grid, SY_THREADS, smem_d, st>>>(Kpad, Dpad, slabs_per * SY_BK, Zt, Cmat);
+  else syrk_kernel<<<grid, SY_THREADS, smem, st>>>(Kpad, Dpad, slabs_per * SY_BK, Zt, Cmat);
   VGG_LAUNCH_CHECK();
   return VGG_OK;
 }

@@ -4,6 +4,7 @@
 // other GPUs join through the caller's all-reduce hook (NCCL over NVLink, see vggsfm_b200/dist.py).
 #include <cusolverDn.h>
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 #include "common.cuh"
@@ -426,8 +427,18 @@ int vgg_ba_solve(const vgg_ba_problem* prob, const vgg_ba_options* opt_in, void*
     if ((rc = launch_scale_damp(D, L.Dpad, Sraw, rhs, hdiag, L.sc_c, prob->param_const, radius, opt.min_lm_diagonal,
                                 opt.max_lm_diagonal, L.bvec, st)))
       return rc;
-    // own blocked Cholesky (chol.cu); the factor is row-major lower == column-major upper for potrs
-    if ((rc = chol_lower_inplace(D, L.Dpad, Sraw, L.chol_diag, L.dev_info, st))) return rc;
+    // own blocked Cholesky (chol.cu); the factor is row-major lower == column-major upper for potrs.
+    // VGG_CHOL=cusolver switches back to cusolverDnDpotrf for A/B measurements.
+    static const bool use_cusolver_potrf = [] { const char* e = getenv("VGG_CHOL"); return e && e[0] == 'c'; }();
+    if (use_cusolver_potrf) {
+      if (cusolverDnDpotrf(cs, CUBLAS_FILL_MODE_UPPER, D, Sraw, L.Dpad, L.potrf_work, (int)L.potrf_lwork, L.dev_info) !=
+          CUSOLVER_STATUS_SUCCESS) {
+        set_error("cusolverDnDpotrf failed to launch");
+        return VGG_ESOLVER;
+      }
+    } else if ((rc = chol_lower_inplace(D, L.Dpad, Sraw, L.chol_diag, L.dev_info, st))) {
+      return rc;
+    }
     if (cusolverDnDpotrs(cs, CUBLAS_FILL_MODE_UPPER, D, 1, Sraw, L.Dpad, L.bvec, L.Dpad, L.dev_info + 1) !=
         CUSOLVER_STATUS_SUCCESS) {
       set_error("cusolverDnDpotrs failed to launch");

@@ -3,10 +3,10 @@
 // The reduced system of configuration C3 is 2402 x 2402 float64: cuSOLVER's potrf spends ~3.4 ms in ~250
 // tiny launches on it, more than the Schur build once the tracks are sharded over GPUs.  This
 // factorisation uses two launches per 64-column panel:
-//   chol_panel_kernel     every CTA re-factors the 64x64 diagonal block (one warp, rows in registers,
-//                         shuffles for the pivot column -- no barrier per column) while its other warps stage
-//                         the CTA's 64 panel rows; then a right-looking triangular solve, 4 threads per row,
-//                         turns the rows into L_ik.  CTA 0 parks the factored diagonal block in a side buffer.
+//   chol_panel_kernel     every CTA re-factors the 64x64 diagonal block in shared memory in 8-column
+//                         micro-panels (8x8 leaf in registers with shuffles + rsqrt, 3 CTA barriers per
+//                         micro-panel), then a right-looking triangular solve, 4 threads per row, turns its 64
+//                         panel rows into L_ik.  CTA 0 parks the factored diagonal block in a side buffer.
 //   chol_trailing_kernel  A22 -= P P^T on 64x64 tiles with the whole K=64 panel resident in shared memory.
 // and one copy-back of the diagonal blocks at the end.  Ceres' counterpart: DENSE_SCHUR's LLT / LAPACK potrf
 // inside SchurComplementSolver (reached from pycolmap.bundle_adjustment).
@@ -17,66 +17,79 @@ namespace vgg {
 constexpr int CH_NB = 64;
 constexpr int CH_LD = 66;     // shared-memory row stride (even: 16-byte aligned pairs; 66*2 mod 32 = 4: conflict-free)
 
-// Cholesky of a 32x32 block held one row per lane (a[c] = row `lane`, col c; only c <= lane is meaningful).
-// Returns 0 or 1 + index of the first non-positive pivot.
-__device__ __forceinline__ int warp_chol32(double (&a)[32], int lane) {
-  int fail = 0;
+// Cholesky of the 64x64 block in shared memory Ls (row stride CH_LD) by the whole CTA (256 threads), in
+// 8-column micro-panels: (a) warp 0 factors the 8x8 diagonal micro-block in registers (one row per lane,
+// shuffles for the pivot column, rsqrt instead of sqrt+divide), (b) one thread per row below solves its 8
+// entries against it, (c) all threads apply the rank-8 update to the rest of the block.  Three CTA barriers per
+// micro-panel instead of three per column.  dinv[j] = 1 / L[j][j].  Returns 0 or 1 + first bad pivot (all threads).
+__device__ __forceinline__ int cta_chol64(double* Ls, double* dinv, int* fail_sm, int tid) {
+  const int lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) *fail_sm = 0;
+  __syncthreads();
+  for (int p = 0; p < 8; ++p) {
+    const int c0 = p * 8;
+    if (warp == 0) {
+      double a[8];
+      const int r = c0 + (lane & 7);
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    const double pj = __shfl_sync(0xffffffffu, a[j], j);
-    if (!(pj > 0.0) && fail == 0) fail = j + 1;
-    const double d = sqrt(pj > 0.0 ? pj : 1.0);
-    a[j] = (lane == j) ? d : a[j] / d;
+      for (int c = 0; c < 8; ++c) a[c] = Ls[r * CH_LD + c0 + c];
+      int fail = 0;
 #pragma unroll
-    for (int c = j + 1; c < 32; ++c) {
-      const double lc = __shfl_sync(0xffffffffu, a[j], c);
-      if (lane >= c) a[c] = fma(-a[j], lc, a[c]);
+      for (int j = 0; j < 8; ++j) {
+        const double pj = __shfl_sync(0xffffffffu, a[j], j);
+        if (!(pj > 0.0) && fail == 0) fail = c0 + j + 1;
+        const double inv = rsqrt(pj > 0.0 ? pj : 1.0);
+        a[j] = (lane == j) ? pj * inv : a[j] * inv;
+        if (lane == j) dinv[c0 + j] = inv;
+#pragma unroll
+        for (int c = j + 1; c < 8; ++c) {
+          const double lc = __shfl_sync(0xffffffffu, a[j], c);
+          if (lane >= c) a[c] = fma(-a[j], lc, a[c]);
+        }
+      }
+      if (lane < 8) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) Ls[r * CH_LD + c0 + c] = (c <= lane) ? a[c] : 0.0;
+      }
+      if (lane == 0 && fail && *fail_sm == 0) *fail_sm = fail;
     }
+    __syncthreads();
+    // (b) rows below the micro-block: x L^T = a  (one thread per row)
+    {
+      const int r = c0 + 8 + tid;
+      if (r < CH_NB) {
+        double x[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) x[c] = Ls[r * CH_LD + c0 + c];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          x[m] *= dinv[c0 + m];
+#pragma unroll
+          for (int j = m + 1; j < 8; ++j) x[j] = fma(-x[m], Ls[(c0 + j) * CH_LD + c0 + m], x[j]);
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) Ls[r * CH_LD + c0 + c] = x[c];
+      }
+    }
+    __syncthreads();
+    // (c) rank-8 update of the remaining lower triangle: rows/cols >= c0+8
+    {
+      const int m = CH_NB - (c0 + 8);           // remaining dimension
+      for (int e = tid; e < m * m; e += 256) {
+        const int i = e / m, c = e - i * m;
+        if (c <= i) {
+          const double* li = Ls + (c0 + 8 + i) * CH_LD + c0;
+          const double* lc = Ls + (c0 + 8 + c) * CH_LD + c0;
+          double s = Ls[(c0 + 8 + i) * CH_LD + c0 + 8 + c];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) s = fma(-li[k], lc[k], s);
+          Ls[(c0 + 8 + i) * CH_LD + c0 + 8 + c] = s;
+        }
+      }
+    }
+    __syncthreads();
   }
-  return fail;
-}
-
-// In-place Cholesky of the 64x64 block in shared memory Ls (stride CH_LD), by ONE warp.
-__device__ __forceinline__ int warp_chol64(double* Ls, int lane) {
-  double a[32];
-  // A11
-#pragma unroll
-  for (int c = 0; c < 32; ++c) a[c] = Ls[lane * CH_LD + c];
-  int fail = warp_chol32(a, lane);
-#pragma unroll
-  for (int c = 0; c < 32; ++c) Ls[lane * CH_LD + c] = (c <= lane) ? a[c] : 0.0;
-  __syncwarp();
-  // A21 <- A21 L11^-T (row 32+lane), right-looking substitution
-  double b[32];
-#pragma unroll
-  for (int c = 0; c < 32; ++c) b[c] = Ls[(32 + lane) * CH_LD + c];
-#pragma unroll
-  for (int m = 0; m < 32; ++m) {
-    const double x = b[m] / Ls[m * CH_LD + m];
-    b[m] = x;
-#pragma unroll
-    for (int j = m + 1; j < 32; ++j) b[j] = fma(-x, Ls[j * CH_LD + m], b[j]);
-  }
-#pragma unroll
-  for (int c = 0; c < 32; ++c) Ls[(32 + lane) * CH_LD + c] = b[c];
-  __syncwarp();
-  // A22 <- A22 - L21 L21^T (row 32+lane, cols 32..63), then its Cholesky
-#pragma unroll
-  for (int c = 0; c < 32; ++c) {
-    double s = Ls[(32 + lane) * CH_LD + 32 + c];
-#pragma unroll
-    for (int k = 0; k < 32; ++k) s = fma(-b[k], Ls[(32 + c) * CH_LD + k], s);
-    a[c] = s;
-  }
-  const int f2 = warp_chol32(a, lane);
-  if (fail == 0 && f2 != 0) fail = 32 + f2;
-#pragma unroll
-  for (int c = 0; c < 32; ++c) Ls[(32 + lane) * CH_LD + 32 + c] = (c <= lane) ? a[c] : 0.0;
-  // zero the upper-right block so the factor is a clean lower triangle
-#pragma unroll
-  for (int c = 0; c < 32; ++c) Ls[lane * CH_LD + 32 + c] = 0.0;
-  __syncwarp();
-  return fail;
+  return *fail_sm;
 }
 
 // grid.x = 1 + number of 64-row chunks below the diagonal block; block 256
@@ -86,28 +99,21 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(int n, int lda, int k0,
   extern __shared__ __align__(16) double panel_smem[];
   double* Ls = panel_smem;
   double* Ts = panel_smem + CH_NB * CH_LD;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ double dinv[CH_NB];
+  __shared__ int fail_sm;
+  const int tid = threadIdx.x, lane = tid & 31;
   const int nb = min(CH_NB, n - k0);
   const int r0 = k0 + CH_NB + ((int)blockIdx.x - 1) * CH_NB;
-  // diagonal block (lower part, identity padding): a warp reads one 512 B row
+  // diagonal block (lower part, identity padding) and this CTA's 64 panel rows: a warp reads one 512 B row
   for (int e = tid; e < CH_NB * CH_NB; e += 256) {
     const int i = e >> 6, j = e & 63;
     double v = (i == j) ? 1.0 : 0.0;
     if (i < nb && j < nb && j <= i) v = A[(size_t)(k0 + i) * lda + k0 + j];
     Ls[i * CH_LD + j] = v;
+    if (blockIdx.x > 0) Ts[i * CH_LD + j] = (r0 + i < n && j < nb) ? A[(size_t)(r0 + i) * lda + k0 + j] : 0.0;
   }
-  __syncthreads();
-  if (warp == 0) {
-    const int fail = warp_chol64(Ls, lane);
-    if (fail && blockIdx.x == 0 && lane == 0) atomicCAS(info, 0, k0 + fail);
-  } else if (blockIdx.x > 0) {
-    // meanwhile: stage this CTA's 64 panel rows
-    for (int e = tid - 32; e < CH_NB * CH_NB; e += 224) {
-      const int r = e >> 6, c = e & 63;
-      Ts[r * CH_LD + c] = (r0 + r < n && c < nb) ? A[(size_t)(r0 + r) * lda + k0 + c] : 0.0;
-    }
-  }
-  __syncthreads();
+  const int fail = cta_chol64(Ls, dinv, &fail_sm, tid);
+  if (fail && blockIdx.x == 0 && tid == 0) atomicCAS(info, 0, k0 + fail);
   if (blockIdx.x == 0) {
     double* dst = Ldiag + (size_t)(k0 / CH_NB) * CH_NB * CH_NB;
     for (int e = tid; e < CH_NB * CH_NB; e += 256) dst[e] = Ls[(e >> 6) * CH_LD + (e & 63)];
@@ -122,12 +128,11 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(int n, int lda, int k0,
 #pragma unroll
     for (int m = 0; m < CH_NB; ++m) {
       const int qm = m & 3, jm = m >> 2;
-      double x = a[jm] / Ls[m * CH_LD + m];
+      double x = a[jm] * dinv[m];
       x = __shfl_sync(0xffffffffu, x, (lane & ~3) | qm);
       if (q == qm) a[jm] = x;
 #pragma unroll
       for (int jj = 0; jj < 16; ++jj) {
-        // column j = q + 4*jj is still open when j > m
         if (4 * jj + 3 > m) {                       // compile-time prune; exact test below
           const int j = q + 4 * jj;
           if (j > m) a[jj] = fma(-x, Ls[j * CH_LD + m], a[jj]);
