@@ -96,11 +96,13 @@ int vgg_ba_workspace_bytes(int S, int N, int camera_model, int intr_mode, size_t
 
 /* Fused residual + analytic 2x(dc+3) Jacobian + normal-equation block kernel (one launch).
  * Outputs (all double): cost[1]; camrec[S,KR] = per frame (g_c[dc] | H_cc upper-packed | H_cs[6,ns]);
- * g_p[N,3]; H_pp[N,6] (xx,xy,xz,yy,yz,zz); W[(S*dc+ns),N,3] coupling blocks J_c^T J_p (shared
- * intrinsics rows last); shared[8] = (g_s[2], H_ss xx,xy,yy).  KR = vgg_ba_camrec_len(). */
+ * g_p[N,3]; H_pp[N,6] (xx,xy,xz,yy,yz,zz); W[N, pitch, 3] track-major coupling blocks J_c^T J_p with
+ * row = s*dc+i (shared-intrinsics rows at S*dc..) and pitch = D rounded up to even, D = S*dc+ns;
+ * shared[8] = (g_s[2], H_ss xx,xy,yy).  KR = vgg_ba_camrec_len().  The last int argument is the number of
+ * tracks each warp walks (0 = choose). */
 int vgg_ba_camrec_len(int camera_model, int intr_mode);
 int vgg_ba_build_blocks(const vgg_ba_problem* prob, double* cost, double* camrec, double* g_p,
-                        double* H_pp, double* W, double* shared, int frames_per_cta, void* stream);
+                        double* H_pp, double* W, double* shared, int tracks_per_warp, void* stream);
 
 /* Schur complement of the point blocks onto the camera system (second kernel of the path):
  * given the blocks above, the Jacobi scales and the trust-region radius, writes

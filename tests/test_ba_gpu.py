@@ -47,10 +47,10 @@ def test_blocks_match_oracle(cuda_dev, S, N, cam, mode):
     Hpp = out["H_pp"].cpu().numpy()
     Hfull = np.stack([Hpp[:, [0, 1, 2]], Hpp[:, [1, 3, 4]], Hpp[:, [2, 4, 5]]], axis=1)
     assert relerr(Hfull, ref["H_pp"]) < tol
-    W = out["W"].cpu().numpy()
-    assert relerr(W[:S * dc].reshape(S, dc, N, 3), ref["W"]) < tol
+    W = out["W"].cpu().numpy()                       # track-major [N, pitch, 3]
+    assert relerr(W[:, :S * dc].reshape(N, S, dc, 3).transpose(1, 2, 0, 3), ref["W"]) < tol
     if ns:
-        assert relerr(W[S * dc:], ref["W_s"]) < tol
+        assert relerr(W[:, S * dc:S * dc + ns].transpose(1, 0, 2), ref["W_s"]) < tol
         assert relerr(H_cs, ref["H_cs"]) < tol
         assert relerr(g_s, ref["g_s"]) < tol
         assert relerr(H_ss, ref["H_ss"]) < tol

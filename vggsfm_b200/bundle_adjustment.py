@@ -118,9 +118,10 @@ def _problem(uv, mask, poses, intr, points, model, mode, param_const, point_cons
     return p
 
 
-def build_blocks(uv, mask, poses, intr, points, model, mode, point_const=None, frames_per_cta=0):
+def build_blocks(uv, mask, poses, intr, points, model, mode, point_const=None, tracks_per_warp=0):
     """One launch of the fused residual+Jacobian+block kernel (vgg_ba_build_blocks).  Returns a dict of
-    device tensors: cost[1], camrec[S,KR], g_p[N,3], H_pp[N,6], W[D,N,3], shared[8]."""
+    device tensors: cost[1], camrec[S,KR], g_p[N,3], H_pp[N,6], W[N,pitch,3] (track-major, pitch = D rounded
+    up to even), shared[8]."""
     L = _lib.lib()
     S, N = mask.shape
     dc, ns = dims(model, mode)
@@ -131,7 +132,7 @@ def build_blocks(uv, mask, poses, intr, points, model, mode, point_const=None, f
         "camrec": torch.empty(S, KR, dtype=torch.float64, device=dev),
         "g_p": torch.empty(N, 3, dtype=torch.float64, device=dev),
         "H_pp": torch.empty(N, 6, dtype=torch.float64, device=dev),
-        "W": torch.empty(S * dc + ns, N, 3, dtype=torch.float64, device=dev),
+        "W": torch.empty(N, (S * dc + ns + 1) // 2 * 2, 3, dtype=torch.float64, device=dev),
         "shared": torch.empty(8, dtype=torch.float64, device=dev),
     }
     p = _problem(uv, mask, poses, intr, points, model, mode, None, point_const)
@@ -139,7 +140,7 @@ def build_blocks(uv, mask, poses, intr, points, model, mode, point_const=None, f
         st = torch.cuda.current_stream().cuda_stream
         _lib.check(L.vgg_ba_build_blocks(ctypes.byref(p), out["cost"].data_ptr(), out["camrec"].data_ptr(),
                                          out["g_p"].data_ptr(), out["H_pp"].data_ptr(), out["W"].data_ptr(),
-                                         out["shared"].data_ptr(), frames_per_cta, st), "vgg_ba_build_blocks")
+                                         out["shared"].data_ptr(), tracks_per_warp, st), "vgg_ba_build_blocks")
     return out
 
 

@@ -6,8 +6,8 @@
 //   point_prep      per point: V = Dp H_pp Dp + diag(clamp(diag))/radius, 3x3 Cholesky,
 //                   M = Dp L^-T, q = M^T g_p
 //   assemble_hc     camera Hessian/gradient from the per-frame records into the dense reduced system
-//   z_transpose     Zt[3n+c][row] = (W[row][n][:] M_n)[c]   (k-major operand for the SYRK),
-//                   rhs[row] += Z[row] . q
+//   z_build         Zt[3n+c][row] = (W[n][row][:] M_n)[c]   (k-major operand for the SYRK; W is track-major,
+//                   so this is a straight streaming pass), rhs[row] += Z[row] . q
 //   syrk            Sraw -= Zt^T Zt on the lower-triangular 128x128 tiles: FP64 FMA pipe, 8x8 register
 //                   tiles, cp.async double-buffered k-slabs, split-K with f64 RED epilogue
 //   scale_damp      A = Dc Sraw Dc + diag(clamp(diag(Dc Hcc Dc)))/radius, constant parameters pinned
@@ -140,49 +140,40 @@ __global__ void assemble_hc_kernel(int S, int dc, int ns, int KR, int Dpad, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// Zt[(3n+c)*Dpad + row] = sum_c' W[row][n][c'] M[n][c'][c];  rhs[row] += sum_{n,c} Z q
-// tile: 32 rows x 32 points; block (32, 8)
-__global__ void __launch_bounds__(256) z_transpose_kernel(int D, int N, int Dpad, const double* __restrict__ W,
-                                                          const double* __restrict__ M, const double* __restrict__ q,
-                                                          double* __restrict__ Zt, double* __restrict__ rhs) {
-  __shared__ double T[96][33];
-  const int nx = threadIdx.x, ry = threadIdx.y;
-  const int n = blockIdx.y * 32 + nx;
-  const int row0 = blockIdx.x * 32;
-  double m[9], qq[3];
-  if (n < N) {
-#pragma unroll
-    for (int i = 0; i < 9; ++i) m[i] = M[(size_t)n * 9 + i];
-    qq[0] = q[n * 3]; qq[1] = q[n * 3 + 1]; qq[2] = q[n * 3 + 2];
-  } else {
-#pragma unroll
-    for (int i = 0; i < 9; ++i) m[i] = 0.0;
-    qq[0] = qq[1] = qq[2] = 0.0;
-  }
-#pragma unroll
-  for (int it = 0; it < 4; ++it) {
-    const int rl = ry + it * 8;
-    const int row = row0 + rl;
-    double z0 = 0, z1 = 0, z2 = 0;
-    if (row < D && n < N) {
-      const double* w = W + ((size_t)row * N + n) * 3;
-      const double w0 = w[0], w1 = w[1], w2 = w[2];
-      z0 = w0 * m[0];                            // M upper triangular (row-major)
-      z1 = w0 * m[1] + w1 * m[4];
-      z2 = w0 * m[2] + w1 * m[5] + w2 * m[8];
-    }
-    T[3 * nx + 0][rl] = z0;
-    T[3 * nx + 1][rl] = z1;
-    T[3 * nx + 2][rl] = z2;
-    const double zq = warp_sum(z0 * qq[0] + z1 * qq[1] + z2 * qq[2]);
-    if (nx == 0 && row < D && zq != 0.0) atomicAdd(&rhs[row], zq);
+// Schur operand: Zt[(3n+c)*Dpad + row] = sum_c' W[n][row][c'] M[n][c'][c];  rhs[row] += sum_{n,c} Z q.
+// W is track-major ([N][pitch][3]), so for a fixed track both the read (24 B per row) and the three writes
+// (8 B per row into three k-rows of Zt) are contiguous across threads: no transpose, no shared-memory tile.
+// block = 128 rows x ZB_NT tracks.
+constexpr int ZB_NT = 32;
+__global__ void __launch_bounds__(128) z_build_kernel(int D, int N, int Dpad, size_t pitch, const double* __restrict__ W,
+                                                      const double* __restrict__ M, const double* __restrict__ q,
+                                                      double* __restrict__ Zt, double* __restrict__ rhs) {
+  __shared__ double sm[ZB_NT][12];
+  const int row = blockIdx.x * 128 + threadIdx.x;
+  const int n0 = blockIdx.y * ZB_NT;
+  const int nt = min(ZB_NT, N - n0);
+  for (int e = threadIdx.x; e < nt * 12; e += 128) {
+    const int t = e / 12, k = e % 12;
+    sm[t][k] = k < 9 ? M[(size_t)(n0 + t) * 9 + k] : q[(size_t)(n0 + t) * 3 + (k - 9)];
   }
   __syncthreads();
-  const int k0 = blockIdx.y * 96;
-  for (int kk = ry; kk < 96; kk += 8) {
-    const int k = k0 + kk;
-    if (k < 3 * N && row0 + nx < Dpad) Zt[(size_t)k * Dpad + row0 + nx] = T[kk][nx];
+  if (row >= D) return;
+  double zq = 0.0;
+  const double* wp = W + ((size_t)n0 * pitch + row) * 3;
+#pragma unroll 4
+  for (int t = 0; t < nt; ++t, wp += pitch * 3) {
+    const double w0 = wp[0], w1 = wp[1], w2 = wp[2];
+    const double* m = sm[t];
+    const double z0 = w0 * m[0];                              // M upper triangular (row-major)
+    const double z1 = w0 * m[1] + w1 * m[4];
+    const double z2 = w0 * m[2] + w1 * m[5] + w2 * m[8];
+    double* zo = Zt + (size_t)(3 * (n0 + t)) * Dpad + row;
+    zo[0] = z0;
+    zo[Dpad] = z1;
+    zo[2 * (size_t)Dpad] = z2;
+    zq += z0 * m[9] + z1 * m[10] + z2 * m[11];
   }
+  if (zq != 0.0) atomicAdd(&rhs[row], zq);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -417,30 +408,27 @@ __global__ void cam_step_kernel(int D, const double* __restrict__ dcs, const dou
   }
 }
 
-// wacc[n][c] += sum_{row in chunk} W[row][n][c] d_c[row]
-__global__ void __launch_bounds__(128) backsub_partial_kernel(int D, int N, int rows_per_cta,
-                                                              const double* __restrict__ W,
-                                                              const double* __restrict__ d_c,
-                                                              double* __restrict__ wacc) {
-  extern __shared__ double dsm[];
-  const int r0 = blockIdx.y * rows_per_cta;
-  const int r1 = min(D, r0 + rows_per_cta);
-  for (int i = threadIdx.x; i < r1 - r0; i += blockDim.x) dsm[i] = d_c[r0 + i];
-  __syncthreads();
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+// wacc[n][c] = sum_row W[n][row][c] d_c[row]: one warp per track, lanes stride over the contiguous rows
+__global__ void __launch_bounds__(256) backsub_kernel(int D, int N, size_t pitch, const double* __restrict__ W,
+                                                      const double* __restrict__ d_c, double* __restrict__ wacc) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (n >= N) return;
+  const double* wp = W + (size_t)n * pitch * 3;
   double w0 = 0, w1 = 0, w2 = 0;
-  const double* wp = W + ((size_t)r0 * N + n) * 3;
 #pragma unroll 4
-  for (int r = r0; r < r1; ++r, wp += (size_t)N * 3) {
-    const double d = dsm[r - r0];
-    w0 = fma(wp[0], d, w0);
-    w1 = fma(wp[1], d, w1);
-    w2 = fma(wp[2], d, w2);
+  for (int r = lane; r < D; r += 32) {
+    const double d = __ldg(d_c + r);
+    w0 = fma(wp[(size_t)r * 3], d, w0);
+    w1 = fma(wp[(size_t)r * 3 + 1], d, w1);
+    w2 = fma(wp[(size_t)r * 3 + 2], d, w2);
   }
-  atomicAdd(&wacc[(size_t)n * 3 + 0], w0);
-  atomicAdd(&wacc[(size_t)n * 3 + 1], w1);
-  atomicAdd(&wacc[(size_t)n * 3 + 2], w2);
+  w0 = warp_sum(w0); w1 = warp_sum(w1); w2 = warp_sum(w2);
+  if (lane == 0) {
+    wacc[(size_t)n * 3] = w0;
+    wacc[(size_t)n * 3 + 1] = w1;
+    wacc[(size_t)n * 3 + 2] = w2;
+  }
 }
 
 // d_p = M M^T (-(g_p + w)); candidate = X + d_p; scal[2] += sum dps^2 dpp/r - d_p.g_p; scal[3] += |d_p|^2
@@ -579,8 +567,9 @@ int launch_assemble_hc(int S, int dc, int ns, int KR, int Dpad, const double* ca
 }
 int launch_z_transpose(int D, int N, int Dpad, const double* W, const double* M, const double* q, double* Zt,
                        double* rhs, cudaStream_t st) {
-  dim3 grid((D + 31) / 32, (N + 31) / 32), block(32, 8);
-  z_transpose_kernel<<<grid, block, 0, st>>>(D, N, Dpad, W, M, q, Zt, rhs);
+  const size_t pitch = (size_t)(D + (D & 1));
+  dim3 grid((D + 127) / 128, (N + ZB_NT - 1) / ZB_NT);
+  z_build_kernel<<<grid, 128, 0, st>>>(D, N, Dpad, pitch, W, M, q, Zt, rhs);
   VGG_LAUNCH_CHECK();
   return VGG_OK;
 }
@@ -602,7 +591,7 @@ int launch_syrk(int Kpad, int Dpad, const double* Zt, double* Cmat, cudaStream_t
     VGG_CUDA_CHECK(cudaFuncSetAttribute(syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     VGG_CUDA_CHECK(cudaFuncSetAttribute(syrk_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_d));
     const char* e = getenv("VGG_SYRK_DMMA");
-    use_dmma = (e && e[0] == '1') ? 1 : 0;
+    use_dmma = (e && e[0] == '0') ? 0 : 1;     // DMMA is the default (r01 A/B: 3.1 ms -> 2.4 ms at C3); VGG_SYRK_DMMA=0 selects the DFMA kernel
     attr_set = true;
   }
   dim3 grid(ntiles, splits);
@@ -627,15 +616,8 @@ int launch_cam_step(int D, const double* dcs, const double* sc, const double* hd
   return VGG_OK;
 }
 int launch_backsub(int D, int N, const double* W, const double* d_c, double* wacc, cudaStream_t st) {
-  VGG_CUDA_CHECK(cudaMemsetAsync(wacc, 0, sizeof(double) * (size_t)N * 3, st));
-  const int nb = (N + 127) / 128;
-  int chunks = (148 * 4 + nb - 1) / nb;
-  if (chunks > D) chunks = D;
-  if (chunks < 1) chunks = 1;
-  int rows_per = (D + chunks - 1) / chunks;
-  chunks = (D + rows_per - 1) / rows_per;
-  dim3 grid(nb, chunks);
-  backsub_partial_kernel<<<grid, 128, sizeof(double) * rows_per, st>>>(D, N, rows_per, W, d_c, wacc);
+  const size_t pitch = (size_t)(D + (D & 1));
+  backsub_kernel<<<(N + 7) / 8, 256, 0, st>>>(D, N, pitch, W, d_c, wacc);
   VGG_LAUNCH_CHECK();
   return VGG_OK;
 }

@@ -123,7 +123,7 @@ static int make_layout(int S, int N, int model, int mode, void* base, size_t cap
     L->blk[b].camrec = c.take<double>((size_t)S * KR);
     L->blk[b].g_p = c.take<double>((size_t)N * 3);
     L->blk[b].H_pp = c.take<double>((size_t)N * 6);
-    L->blk[b].W = c.take<double>((size_t)L->D * N * 3);
+    L->blk[b].W = c.take<double>((size_t)(L->D + (L->D & 1)) * N * 3);   // track-major [N][pitch][3]
     L->poses[b] = c.take<double>((size_t)S * 12);
     L->intr[b] = c.take<double>((size_t)S * 4);
     L->points[b] = c.take<double>((size_t)N * 3);
@@ -361,7 +361,6 @@ int vgg_ba_solve(const vgg_ba_problem* prob, const vgg_ba_options* opt_in, void*
     // cost | shared | camrec | g_p | H_pp are carved back to back: one memset covers all accumulators
     const size_t acc_bytes = reinterpret_cast<char*>(b.H_pp + (size_t)N * 6) - reinterpret_cast<char*>(b.cost);
     VGG_CUDA_CHECK(cudaMemsetAsync(b.cost, 0, acc_bytes, st));
-    if (ns > 0) VGG_CUDA_CHECK(cudaMemsetAsync(b.W + (size_t)S * dc * N * 3, 0, sizeof(double) * (size_t)ns * N * 3, st));
     return ba_build_blocks(&p, b.cost, b.camrec, b.g_p, b.H_pp, b.W, b.shared, 0, st, true);
   };
   // global cost + gradient max-norm of block set `which`; result lands in host h[0..2] = cost, gmax_c, gmax_p
