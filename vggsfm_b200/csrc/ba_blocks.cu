@@ -30,6 +30,7 @@ namespace vgg {
 constexpr int BW = 4;            // warps per CTA
 constexpr int BT = BW * 32;      // threads per CTA
 constexpr int TB = 4;            // tracks per prefetch batch (32 B of uv per lane)
+constexpr int XT = 32;           // tracks per shared-memory point tile (one per lane)
 
 template <int MODEL, int MODE>
 struct BlkCfg {
@@ -89,7 +90,8 @@ __global__ void __launch_bounds__(BT, 3) ba_blocks_kernel(
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // per warp: pose/intrinsics transposed [16][32], two W staging buffers [32][WB]
   double* sm_pose = reinterpret_cast<double*>(smem_raw);                // [BW][16][32]
-  double* sm_w = sm_pose + BW * 16 * 32;                                 // [BW][2][32*WB]
+  double* sm_x = sm_pose + BW * 16 * 32;                                 // [BW][XT][4]: X,Y,Z,const flag per track
+  double* sm_w = sm_x + BW * XT * 4;                                     // [BW][2][32*WB]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int D = S * DC + NS;
   const size_t pitch = w_pitch(D);
@@ -104,6 +106,7 @@ __global__ void __launch_bounds__(BT, 3) ba_blocks_kernel(
   const bool frame_ok = s < S;
   const int nf = min(32, S - g * 32);              // frames of this group that exist
   double* pw = sm_pose + warp * 16 * 32;
+  double* xw = sm_x + warp * XT * 4;
   double* wbuf = sm_w + (size_t)warp * 2 * 32 * WB;
 
   // camera of this lane -> shared, transposed (conflict-free one-frame-per-lane reads)
@@ -145,6 +148,19 @@ __global__ void __launch_bounds__(BT, 3) ba_blocks_kernel(
   fetch(t_begin, ua, ub, mk);
   int tcount = 0;
   for (int t0 = t_begin; t0 < t_end; t0 += TB) {
+    if (((t0 - t_begin) & (XT - 1)) == 0) {
+      // next 32 tracks' points -> shared (one track per lane, coalesced), read back as broadcasts
+      __syncwarp();
+      const int nn = t0 + lane;
+      double x0 = 0.0, x1 = 0.0, x2 = 1.0, cf = 1.0;
+      if (nn < t_end) {
+        x0 = points[(size_t)nn * 3]; x1 = points[(size_t)nn * 3 + 1]; x2 = points[(size_t)nn * 3 + 2];
+        cf = (point_const && point_const[nn] != 0) ? 1.0 : 0.0;
+      }
+      *reinterpret_cast<double2*>(xw + lane * 4) = make_double2(x0, x1);
+      *reinterpret_cast<double2*>(xw + lane * 4 + 2) = make_double2(x2, cf);
+      __syncwarp();
+    }
     const float4 ca = ua, cb = ub;
     const uint32_t cm = mk;
     fetch(t0 + TB, ua, ub, mk);                                  // next batch in flight during this one
@@ -152,9 +168,10 @@ __global__ void __launch_bounds__(BT, 3) ba_blocks_kernel(
     for (int k = 0; k < TB; ++k) {
       const int n = t0 + k;
       if (n >= t_end) break;                                     // warp-uniform
-      const double X0 = __ldg(points + (size_t)n * 3), X1 = __ldg(points + (size_t)n * 3 + 1),
-                   X2 = __ldg(points + (size_t)n * 3 + 2);
-      const bool pconst = point_const ? (__ldg(point_const + n) != 0) : false;
+      const double2 xa = *reinterpret_cast<const double2*>(xw + ((n - t_begin) & (XT - 1)) * 4);
+      const double2 xb = *reinterpret_cast<const double2*>(xw + ((n - t_begin) & (XT - 1)) * 4 + 2);
+      const double X0 = xa.x, X1 = xa.y, X2 = xb.x;
+      const bool pconst = xb.y != 0.0;
       const float ox = k == 0 ? ca.x : (k == 1 ? ca.z : (k == 2 ? cb.x : cb.z));
       const float oy = k == 0 ? ca.y : (k == 1 ? ca.w : (k == 2 ? cb.y : cb.w));
       const bool valid = frame_ok && ((cm >> (8 * k)) & 0xffu) != 0;
@@ -242,9 +259,7 @@ __global__ void __launch_bounds__(BT, 3) ba_blocks_kernel(
         if ((WB & 1) == 0) {
 #pragma unroll
           for (int e = 0; e < WB; e += 2) *reinterpret_cast<double2*>(wt + e) = make_double2(wb[e], wb[e + 1]);
-          // camera record of this lane's frame: straight into registers
-        cam_accumulate<DC, NS, KR>(acc, jc0, jc1, rx, ry, std::make_integer_sequence<int, KR>{});
-      } else {
+        } else {
 #pragma unroll
           for (int e = 0; e < WB; ++e) wt[e] = wb[e];
         }
@@ -312,7 +327,7 @@ static int launch_blocks(const vgg_ba_problem* p, double* cost, double* camrec, 
   const int S = p->S, N = p->N;
   const int D = S * C::DC + C::NS;
   const size_t pitch = w_pitch(D);
-  const size_t smem = sizeof(double) * (BW * 16 * 32 + (size_t)BW * 2 * 32 * C::DC * 3);
+  const size_t smem = sizeof(double) * (BW * 16 * 32 + BW * XT * 4 + (size_t)BW * 2 * 32 * C::DC * 3);
   const bool tma_ok = ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
   const int ngroups = (S + 31) / 32;
   if (tracks_per_warp <= 0) {

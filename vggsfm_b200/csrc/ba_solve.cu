@@ -428,8 +428,31 @@ int vgg_ba_solve(const vgg_ba_problem* prob, const vgg_ba_options* opt_in, void*
       return rc;
     // own blocked Cholesky (chol.cu); the factor is row-major lower == column-major upper for potrs.
     // VGG_CHOL=cusolver switches back to cusolverDnDpotrf for A/B measurements.
-    static const bool use_cusolver_potrf = [] { const char* e = getenv("VGG_CHOL"); return e && e[0] == 'c'; }();
-    if (use_cusolver_potrf) {
+    static const int chol_mode = [] {
+      const char* e = getenv("VGG_CHOL");
+      return !e ? 0 : (e[0] == 'c' ? 1 : (e[0] == 'x' ? 2 : 0));
+    }();
+    if (chol_mode == 2) {
+      // 64-bit cuSOLVER API (what torch.linalg.cholesky uses)
+      static thread_local cusolverDnParams_t xp = nullptr;
+      static thread_local void* xdev = nullptr;
+      static thread_local void* xhost = nullptr;
+      static thread_local size_t xdev_b = 0, xhost_b = 0;
+      if (!xp) cusolverDnCreateParams(&xp);
+      size_t db = 0, hb = 0;
+      if (cusolverDnXpotrf_bufferSize(cs, xp, CUBLAS_FILL_MODE_UPPER, D, CUDA_R_64F, Sraw, L.Dpad, CUDA_R_64F, &db, &hb) !=
+          CUSOLVER_STATUS_SUCCESS) {
+        set_error("cusolverDnXpotrf_bufferSize failed");
+        return VGG_ESOLVER;
+      }
+      if (db > xdev_b) { if (xdev) cudaFree(xdev); VGG_CUDA_CHECK(cudaMalloc(&xdev, db)); xdev_b = db; }
+      if (hb > xhost_b) { free(xhost); xhost = malloc(hb); xhost_b = hb; }
+      if (cusolverDnXpotrf(cs, xp, CUBLAS_FILL_MODE_UPPER, D, CUDA_R_64F, Sraw, L.Dpad, CUDA_R_64F, xdev, db, xhost, hb,
+                           L.dev_info) != CUSOLVER_STATUS_SUCCESS) {
+        set_error("cusolverDnXpotrf failed to launch");
+        return VGG_ESOLVER;
+      }
+    } else if (chol_mode == 1) {
       if (cusolverDnDpotrf(cs, CUBLAS_FILL_MODE_UPPER, D, Sraw, L.Dpad, L.potrf_work, (int)L.potrf_lwork, L.dev_info) !=
           CUSOLVER_STATUS_SUCCESS) {
         set_error("cusolverDnDpotrf failed to launch");
