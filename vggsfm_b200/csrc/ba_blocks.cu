@@ -22,6 +22,7 @@
 //   * observations (uv 8 B + mask 1 B) are read with 32-byte vector loads, 4 tracks per lane at a time,
 //     prefetched one batch ahead; poses/intrinsics sit transposed in shared memory (one frame per lane).
 // Algorithmic HBM bytes per observation: 9 + 24*dc (+ amortised per-frame/per-point terms), see DESIGN.md.
+#include <stdlib.h>
 #include <utility>
 #include "common.cuh"
 
@@ -78,8 +79,8 @@ __device__ __forceinline__ void cam_accumulate(double (&acc)[KR], const double* 
 // W row pitch (rows of 3 doubles) of one track: D rounded up to even so every track starts 16-B aligned
 __host__ __device__ inline size_t w_pitch(int D) { return (size_t)(D + (D & 1)); }
 
-template <int MODEL, int MODE, bool USE_TMA>
-__global__ void __launch_bounds__(BT, 3) ba_blocks_kernel(
+template <int MODEL, int MODE, bool USE_TMA, int MINB>
+__global__ void __launch_bounds__(BT, MINB) ba_blocks_kernel(
     int S, int N, int tracks_per_warp, const float* __restrict__ uv, const uint8_t* __restrict__ mask,
     const double* __restrict__ poses, const double* __restrict__ intr, const double* __restrict__ points,
     const uint8_t* __restrict__ point_const, double* __restrict__ cost, double* __restrict__ camrec,
@@ -164,8 +165,8 @@ __global__ void __launch_bounds__(BT, 3) ba_blocks_kernel(
     const float4 ca = ua, cb = ub;
     const uint32_t cm = mk;
     fetch(t0 + TB, ua, ub, mk);                                  // next batch in flight during this one
-#pragma unroll
-    for (int k = 0; k < TB; ++k) {
+#pragma unroll 1
+    for (int k = 0; k < TB; ++k) {                               // not unrolled: keeps the body inside the I-cache
       const int n = t0 + k;
       if (n >= t_end) break;                                     // warp-uniform
       const double2 xa = *reinterpret_cast<const double2*>(xw + ((n - t_begin) & (XT - 1)) * 4);
@@ -355,13 +356,21 @@ static int launch_blocks(const vgg_ba_problem* p, double* cost, double* camrec, 
     const size_t tail = pitch - (size_t)S * C::DC;
     VGG_CUDA_CHECK(cudaMemset2DAsync(W + (size_t)S * C::DC * 3, pitch * 24, 0, tail * 24, (size_t)N, stream));
   }
-  if (tma_ok) {
-    auto kern = ba_blocks_kernel<MODEL, MODE, true>;
+  // MINB = 3 caps registers at 168 (12 resident warps/SM, a few spills); MINB = 2 lets ptxas use ~210 (no spills,
+  // 8 warps/SM).  VGG_K1_MINB=2|3 selects for A/B runs.
+  static const int minb = [] { const char* e = getenv("VGG_K1_MINB"); return (e && e[0] == '2') ? 2 : 3; }();
+  if (tma_ok && minb == 2) {
+    auto kern = ba_blocks_kernel<MODEL, MODE, true, 2>;
+    VGG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, BT, smem, stream>>>(S, N, tracks_per_warp, p->uv, p->mask, p->poses, p->intr, p->points,
+                                     p->point_const, cost, camrec, g_p, H_pp, W, shared_out);
+  } else if (tma_ok) {
+    auto kern = ba_blocks_kernel<MODEL, MODE, true, 3>;
     VGG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, BT, smem, stream>>>(S, N, tracks_per_warp, p->uv, p->mask, p->poses, p->intr, p->points,
                                      p->point_const, cost, camrec, g_p, H_pp, W, shared_out);
   } else {
-    auto kern = ba_blocks_kernel<MODEL, MODE, false>;
+    auto kern = ba_blocks_kernel<MODEL, MODE, false, 3>;
     VGG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, BT, smem, stream>>>(S, N, tracks_per_warp, p->uv, p->mask, p->poses, p->intr, p->points,
                                      p->point_const, cost, camrec, g_p, H_pp, W, shared_out);
