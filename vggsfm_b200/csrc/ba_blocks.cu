@@ -11,8 +11,9 @@
 //   * the per-camera blocks (g_c, H_cc upper-packed, H_cs: 27..44 doubles) accumulate in the lane's
 //     REGISTERS over the warp's whole track range and are flushed once with f64 REDs -- no per-observation
 //     cross-lane traffic for them at all;
-//   * the per-point blocks (g_p, H_pp, shared-intrinsics coupling: 9..15 doubles) are reduced across the 32
-//     frames of the warp by one 16-wide reduce-scatter (16 shuffles) and committed with one RED instruction;
+//   * the per-point blocks (g_p, H_pp, shared-intrinsics coupling: 9..15 doubles) go through a small per-warp
+//     shared-memory scratch (one column per lane): 9..15 lanes each sum one row of 32 and commit it with one
+//     RED instruction -- this keeps them out of the register file, which the camera accumulators fill;
 //   * the coupling block W = J_c^T J_p lives in a TRACK-MAJOR layout W[n][row][3] (row = s*dc+i), so the 32
 //     lanes' blocks of one track are 32*dc*24 B CONTIGUOUS bytes: each warp stages them in shared memory
 //     (16-byte stores) and ships them with ONE TMA bulk store per track (cp.async.bulk.global.shared::cta ->
@@ -32,6 +33,7 @@ constexpr int BW = 4;            // warps per CTA
 constexpr int BT = BW * 32;      // threads per CTA
 constexpr int TB = 4;            // tracks per prefetch batch (32 B of uv per lane)
 constexpr int XT = 32;           // tracks per shared-memory point tile (one per lane)
+constexpr int PVS = 33;          // row stride of the per-point scratch (odd: conflict-free column sums)
 
 template <int MODEL, int MODE>
 struct BlkCfg {
@@ -92,7 +94,8 @@ __global__ void __launch_bounds__(BT, MINB) ba_blocks_kernel(
   // per warp: pose/intrinsics transposed [16][32], two W staging buffers [32][WB]
   double* sm_pose = reinterpret_cast<double*>(smem_raw);                // [BW][16][32]
   double* sm_x = sm_pose + BW * 16 * 32;                                 // [BW][XT][4]: X,Y,Z,const flag per track
-  double* sm_w = sm_x + BW * XT * 4;                                     // [BW][2][32*WB]
+  double* sm_pv = sm_x + BW * XT * 4;                                    // [BW][16][PVS]: per-point values, one column per lane
+  double* sm_w = sm_pv + BW * 16 * PVS;                                  // [BW][2][32*WB]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int D = S * DC + NS;
   const size_t pitch = w_pitch(D);
@@ -108,6 +111,7 @@ __global__ void __launch_bounds__(BT, MINB) ba_blocks_kernel(
   const int nf = min(32, S - g * 32);              // frames of this group that exist
   double* pw = sm_pose + warp * 16 * 32;
   double* xw = sm_x + warp * XT * 4;
+  double* pvw = sm_pv + warp * 16 * PVS;
   double* wbuf = sm_w + (size_t)warp * 2 * 32 * WB;
 
   // camera of this lane -> shared, transposed (conflict-free one-frame-per-lane reads)
@@ -178,9 +182,6 @@ __global__ void __launch_bounds__(BT, MINB) ba_blocks_kernel(
       const bool valid = frame_ok && ((cm >> (8 * k)) & 0xffu) != 0;
       double* wstage = wbuf + (size_t)(tcount & 1) * 32 * WB;
       double* wt = wstage + lane * WB;             // this lane's block in the staging buffer
-      double pv[16];
-#pragma unroll
-      for (int i = 0; i < 16; ++i) pv[i] = 0.0;
       if (valid) {
         const double R00 = pw[0 * 32 + lane], R01 = pw[1 * 32 + lane], R02 = pw[2 * 32 + lane], t0_ = pw[3 * 32 + lane];
         const double R10 = pw[4 * 32 + lane], R11 = pw[5 * 32 + lane], R12 = pw[6 * 32 + lane], t1_ = pw[7 * 32 + lane];
@@ -229,20 +230,20 @@ __global__ void __launch_bounds__(BT, MINB) ba_blocks_kernel(
         jx1[2] = j10 * R02 + j11 * R12 + j12 * R22;
         if (pconst) { jx0[0] = jx0[1] = jx0[2] = jx1[0] = jx1[1] = jx1[2] = 0.0; }
         // per-point values (reduced across the warp's frames below)
-        pv[0] = jx0[0] * rx + jx1[0] * ry;
-        pv[1] = jx0[1] * rx + jx1[1] * ry;
-        pv[2] = jx0[2] * rx + jx1[2] * ry;
-        pv[3] = jx0[0] * jx0[0] + jx1[0] * jx1[0];
-        pv[4] = jx0[0] * jx0[1] + jx1[0] * jx1[1];
-        pv[5] = jx0[0] * jx0[2] + jx1[0] * jx1[2];
-        pv[6] = jx0[1] * jx0[1] + jx1[1] * jx1[1];
-        pv[7] = jx0[1] * jx0[2] + jx1[1] * jx1[2];
-        pv[8] = jx0[2] * jx0[2] + jx1[2] * jx1[2];
+        pvw[0 * PVS + lane] = jx0[0] * rx + jx1[0] * ry;
+        pvw[1 * PVS + lane] = jx0[1] * rx + jx1[1] * ry;
+        pvw[2 * PVS + lane] = jx0[2] * rx + jx1[2] * ry;
+        pvw[3 * PVS + lane] = jx0[0] * jx0[0] + jx1[0] * jx1[0];
+        pvw[4 * PVS + lane] = jx0[0] * jx0[1] + jx1[0] * jx1[1];
+        pvw[5 * PVS + lane] = jx0[0] * jx0[2] + jx1[0] * jx1[2];
+        pvw[6 * PVS + lane] = jx0[1] * jx0[1] + jx1[1] * jx1[1];
+        pvw[7 * PVS + lane] = jx0[1] * jx0[2] + jx1[1] * jx1[2];
+        pvw[8 * PVS + lane] = jx0[2] * jx0[2] + jx1[2] * jx1[2];
         if (NS > 0) {
 #pragma unroll
           for (int j = 0; j < NS; ++j)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) pv[9 + j * 3 + c] = jc0[6 + j] * jx0[c] + jc1[6 + j] * jx1[c];
+            for (int c = 0; c < 3; ++c) pvw[(9 + j * 3 + c) * PVS + lane] = jc0[6 + j] * jx0[c] + jc1[6 + j] * jx1[c];
           gs0 += jc0[6] * rx + jc1[6] * ry;
           hss0 += jc0[6] * jc0[6] + jc1[6] * jc1[6];
           if (NS > 1) {
@@ -267,6 +268,8 @@ __global__ void __launch_bounds__(BT, MINB) ba_blocks_kernel(
         // camera record of this lane's frame: straight into registers
         cam_accumulate<DC, NS, KR>(acc, jc0, jc1, rx, ry, std::make_integer_sequence<int, KR>{});
       } else {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) pvw[i * PVS + lane] = 0.0;
         if ((WB & 1) == 0) {
 #pragma unroll
           for (int e = 0; e < WB; e += 2) *reinterpret_cast<double2*>(wt + e) = make_double2(0.0, 0.0);
@@ -292,7 +295,13 @@ __global__ void __launch_bounds__(BT, MINB) ba_blocks_kernel(
       }
       // per-point sums over the warp's frames: one 16-wide reduce-scatter, one RED instruction
       {
-        const double r = warp_reduce_scatter<16>(pv, lane);
+        // (the __syncwarp of the W hand-off above also published the per-point scratch)
+        double r = 0.0;
+        if (lane < NP) {
+          const double* row = pvw + lane * PVS;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r += row[j];
+        }
         if (lane < 16 && r != 0.0) {
           if (lane < 3) atomicAdd(&g_p[(size_t)n * 3 + lane], r);
           else if (lane < 9) atomicAdd(&H_pp[(size_t)n * 6 + (lane - 3)], r);
@@ -328,7 +337,7 @@ static int launch_blocks(const vgg_ba_problem* p, double* cost, double* camrec, 
   const int S = p->S, N = p->N;
   const int D = S * C::DC + C::NS;
   const size_t pitch = w_pitch(D);
-  const size_t smem = sizeof(double) * (BW * 16 * 32 + BW * XT * 4 + (size_t)BW * 2 * 32 * C::DC * 3);
+  const size_t smem = sizeof(double) * (BW * 16 * 32 + BW * XT * 4 + BW * 16 * PVS + (size_t)BW * 2 * 32 * C::DC * 3);
   const bool tma_ok = ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
   const int ngroups = (S + 31) / 32;
   if (tracks_per_warp <= 0) {
