@@ -78,6 +78,93 @@ __device__ __forceinline__ void cam_accumulate(double (&acc)[KR], const double* 
   (cam_accumulate_one<DC, NS, K, KR>(acc, jc0, jc1, rx, ry), ...);
 }
 
+// One observation, branch-free: residual and Jacobian columns, all scaled by the validity mask (an invalid
+// observation computes on a safe depth and contributes exact zeros).  jc: delta(3), t(3), f, k; jx: point(3).
+template <int MODEL>
+__device__ __forceinline__ void obs_math(const double* pw, int lane, const double* xt, float ox, float oy, bool valid,
+                                         double* jc0, double* jc1, double* jx0, double* jx1, double& rx, double& ry) {
+  const double2 xa = *reinterpret_cast<const double2*>(xt);
+  const double2 xb = *reinterpret_cast<const double2*>(xt + 2);
+  const double X0 = xa.x, X1 = xa.y, X2 = xb.x;
+  const double m = valid ? 1.0 : 0.0;
+  const double mp = (xb.y != 0.0) ? 0.0 : m;                    // constant point: no point columns
+  const double R00 = pw[0 * 32 + lane], R01 = pw[1 * 32 + lane], R02 = pw[2 * 32 + lane], t0_ = pw[3 * 32 + lane];
+  const double R10 = pw[4 * 32 + lane], R11 = pw[5 * 32 + lane], R12 = pw[6 * 32 + lane], t1_ = pw[7 * 32 + lane];
+  const double R20 = pw[8 * 32 + lane], R21 = pw[9 * 32 + lane], R22 = pw[10 * 32 + lane], t2_ = pw[11 * 32 + lane];
+  const double fo = pw[12 * 32 + lane], cx = pw[13 * 32 + lane], cy = pw[14 * 32 + lane];
+  const double kk = (MODEL == VGG_SIMPLE_RADIAL) ? pw[15 * 32 + lane] : 0.0;
+  const double a1 = R00 * X0 + R01 * X1 + R02 * X2;
+  const double a2 = R10 * X0 + R11 * X1 + R12 * X2;
+  const double a3 = R20 * X0 + R21 * X1 + R22 * X2;
+  const double px = a1 + t0_, py = a2 + t1_;
+  const double pz = valid ? (a3 + t2_) : 1.0;
+  const double iz = 1.0 / pz;
+  const double u = px * iz, w_ = py * iz;
+  const double r2 = u * u + w_ * w_;
+  const double d = 1.0 + kk * r2;
+  rx = m * (fo * d * u + cx - (double)ox);
+  ry = m * (fo * d * w_ + cy - (double)oy);
+  double a00, a01, a11;
+  if (MODEL == VGG_SIMPLE_RADIAL) {
+    a00 = fo * (d + 2.0 * kk * u * u);
+    a01 = fo * (2.0 * kk * u * w_);
+    a11 = fo * (d + 2.0 * kk * w_ * w_);
+  } else {
+    a00 = fo; a01 = 0.0; a11 = fo;
+  }
+  // Jproj (2x3) = f*A * iz*[[1,0,-u],[0,1,-v]], masked
+  const double izm = iz * m;
+  const double j00 = a00 * izm, j01 = a01 * izm, j02 = -(a00 * u + a01 * w_) * izm;
+  const double j10 = a01 * izm, j11 = a11 * izm, j12 = -(a01 * u + a11 * w_) * izm;
+  const double b1 = 2.0 * a1, b2 = 2.0 * a2, b3 = 2.0 * a3;
+  jc0[0] = b2 * j02 - b3 * j01;  jc1[0] = b2 * j12 - b3 * j11;
+  jc0[1] = b3 * j00 - b1 * j02;  jc1[1] = b3 * j10 - b1 * j12;
+  jc0[2] = b1 * j01 - b2 * j00;  jc1[2] = b1 * j11 - b2 * j10;
+  jc0[3] = j00; jc0[4] = j01; jc0[5] = j02;
+  jc1[3] = j10; jc1[4] = j11; jc1[5] = j12;
+  jc0[6] = m * d * u;            jc1[6] = m * d * w_;
+  jc0[7] = m * fo * u * r2;      jc1[7] = m * fo * w_ * r2;
+  const double mq = (xb.y != 0.0) ? 0.0 : 1.0;
+  jx0[0] = mq * (j00 * R00 + j01 * R10 + j02 * R20);
+  jx0[1] = mq * (j00 * R01 + j01 * R11 + j02 * R21);
+  jx0[2] = mq * (j00 * R02 + j01 * R12 + j02 * R22);
+  jx1[0] = mq * (j10 * R00 + j11 * R10 + j12 * R20);
+  jx1[1] = mq * (j10 * R01 + j11 * R11 + j12 * R21);
+  jx1[2] = mq * (j10 * R02 + j11 * R12 + j12 * R22);
+  (void)mp;
+}
+
+// coupling block (DC rows x 3, 16-byte stores into the staging buffer) and per-point values (scratch column)
+template <int DC, int NS, int WB>
+__device__ __forceinline__ void emit_blocks(double* wt, double* pvw, int lane, const double* jc0, const double* jc1,
+                                            const double* jx0, const double* jx1, double rx, double ry) {
+  double wb[WB];
+#pragma unroll
+  for (int i = 0; i < DC; ++i)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) wb[i * 3 + c] = jc0[i] * jx0[c] + jc1[i] * jx1[c];
+  if ((WB & 1) == 0) {
+#pragma unroll
+    for (int e = 0; e < WB; e += 2) *reinterpret_cast<double2*>(wt + e) = make_double2(wb[e], wb[e + 1]);
+  } else {
+#pragma unroll
+    for (int e = 0; e < WB; ++e) wt[e] = wb[e];
+  }
+  pvw[0 * PVS + lane] = jx0[0] * rx + jx1[0] * ry;
+  pvw[1 * PVS + lane] = jx0[1] * rx + jx1[1] * ry;
+  pvw[2 * PVS + lane] = jx0[2] * rx + jx1[2] * ry;
+  pvw[3 * PVS + lane] = jx0[0] * jx0[0] + jx1[0] * jx1[0];
+  pvw[4 * PVS + lane] = jx0[0] * jx0[1] + jx1[0] * jx1[1];
+  pvw[5 * PVS + lane] = jx0[0] * jx0[2] + jx1[0] * jx1[2];
+  pvw[6 * PVS + lane] = jx0[1] * jx0[1] + jx1[1] * jx1[1];
+  pvw[7 * PVS + lane] = jx0[1] * jx0[2] + jx1[1] * jx1[2];
+  pvw[8 * PVS + lane] = jx0[2] * jx0[2] + jx1[2] * jx1[2];
+#pragma unroll
+  for (int j = 0; j < NS; ++j)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) pvw[(9 + j * 3 + c) * PVS + lane] = jc0[6 + j] * jx0[c] + jc1[6 + j] * jx1[c];
+}
+
 // W row pitch (rows of 3 doubles) of one track: D rounded up to even so every track starts 16-B aligned
 __host__ __device__ inline size_t w_pitch(int D) { return (size_t)(D + (D & 1)); }
 
@@ -94,8 +181,8 @@ __global__ void __launch_bounds__(BT, MINB) ba_blocks_kernel(
   // per warp: pose/intrinsics transposed [16][32], two W staging buffers [32][WB]
   double* sm_pose = reinterpret_cast<double*>(smem_raw);                // [BW][16][32]
   double* sm_x = sm_pose + BW * 16 * 32;                                 // [BW][XT][4]: X,Y,Z,const flag per track
-  double* sm_pv = sm_x + BW * XT * 4;                                    // [BW][16][PVS]: per-point values, one column per lane
-  double* sm_w = sm_pv + BW * 16 * PVS;                                  // [BW][2][32*WB]
+  double* sm_pv = sm_x + BW * XT * 4;                                    // [BW][2 tracks x 16][PVS]: per-point values, one column per lane
+  double* sm_w = sm_pv + BW * 32 * PVS;                                  // [BW][2][32*WB]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int D = S * DC + NS;
   const size_t pitch = w_pitch(D);
@@ -111,7 +198,7 @@ __global__ void __launch_bounds__(BT, MINB) ba_blocks_kernel(
   const int nf = min(32, S - g * 32);              // frames of this group that exist
   double* pw = sm_pose + warp * 16 * 32;
   double* xw = sm_x + warp * XT * 4;
-  double* pvw = sm_pv + warp * 16 * PVS;
+  double* pvw = sm_pv + warp * 32 * PVS;
   double* wbuf = sm_w + (size_t)warp * 2 * 32 * WB;
 
   // camera of this lane -> shared, transposed (conflict-free one-frame-per-lane reads)
@@ -151,7 +238,6 @@ __global__ void __launch_bounds__(BT, MINB) ba_blocks_kernel(
     }
   };
   fetch(t_begin, ua, ub, mk);
-  int tcount = 0;
   for (int t0 = t_begin; t0 < t_end; t0 += TB) {
     if (((t0 - t_begin) & (XT - 1)) == 0) {
       // next 32 tracks' points -> shared (one track per lane, coalesced), read back as broadcasts
@@ -170,147 +256,83 @@ __global__ void __launch_bounds__(BT, MINB) ba_blocks_kernel(
     const uint32_t cm = mk;
     fetch(t0 + TB, ua, ub, mk);                                  // next batch in flight during this one
 #pragma unroll 1
-    for (int k = 0; k < TB; ++k) {                               // not unrolled: keeps the body inside the I-cache
-      const int n = t0 + k;
-      if (n >= t_end) break;                                     // warp-uniform
-      const double2 xa = *reinterpret_cast<const double2*>(xw + ((n - t_begin) & (XT - 1)) * 4);
-      const double2 xb = *reinterpret_cast<const double2*>(xw + ((n - t_begin) & (XT - 1)) * 4 + 2);
-      const double X0 = xa.x, X1 = xa.y, X2 = xb.x;
-      const bool pconst = xb.y != 0.0;
-      const float ox = k == 0 ? ca.x : (k == 1 ? ca.z : (k == 2 ? cb.x : cb.z));
-      const float oy = k == 0 ? ca.y : (k == 1 ? ca.w : (k == 2 ? cb.y : cb.w));
-      const bool valid = frame_ok && ((cm >> (8 * k)) & 0xffu) != 0;
-      double* wstage = wbuf + (size_t)(tcount & 1) * 32 * WB;
-      double* wt = wstage + lane * WB;             // this lane's block in the staging buffer
-      if (valid) {
-        const double R00 = pw[0 * 32 + lane], R01 = pw[1 * 32 + lane], R02 = pw[2 * 32 + lane], t0_ = pw[3 * 32 + lane];
-        const double R10 = pw[4 * 32 + lane], R11 = pw[5 * 32 + lane], R12 = pw[6 * 32 + lane], t1_ = pw[7 * 32 + lane];
-        const double R20 = pw[8 * 32 + lane], R21 = pw[9 * 32 + lane], R22 = pw[10 * 32 + lane], t2_ = pw[11 * 32 + lane];
-        const double fo = pw[12 * 32 + lane], cx = pw[13 * 32 + lane], cy = pw[14 * 32 + lane];
-        const double kk = (MODEL == VGG_SIMPLE_RADIAL) ? pw[15 * 32 + lane] : 0.0;
-        const double a1 = R00 * X0 + R01 * X1 + R02 * X2;
-        const double a2 = R10 * X0 + R11 * X1 + R12 * X2;
-        const double a3 = R20 * X0 + R21 * X1 + R22 * X2;
-        const double px = a1 + t0_, py = a2 + t1_, pz = a3 + t2_;
-        const double iz = 1.0 / pz;
-        const double u = px * iz, w_ = py * iz;
-        const double r2 = u * u + w_ * w_;
-        const double d = 1.0 + kk * r2;
-        const double rx = fo * d * u + cx - (double)ox;
-        const double ry = fo * d * w_ + cy - (double)oy;
-        cost_acc += 0.5 * (rx * rx + ry * ry);
-        double a00, a01, a11;
-        if (MODEL == VGG_SIMPLE_RADIAL) {
-          a00 = fo * (d + 2.0 * kk * u * u);
-          a01 = fo * (2.0 * kk * u * w_);
-          a11 = fo * (d + 2.0 * kk * w_ * w_);
-        } else {
-          a00 = fo; a01 = 0.0; a11 = fo;
-        }
-        // Jproj (2x3) = f*A * iz*[[1,0,-u],[0,1,-v]]
-        const double j00 = a00 * iz, j01 = a01 * iz, j02 = -(a00 * u + a01 * w_) * iz;
-        const double j10 = a01 * iz, j11 = a11 * iz, j12 = -(a01 * u + a11 * w_) * iz;
-        // camera columns: delta(3) = Jproj * (-2[RX]x), t(3) = Jproj, f, k
-        const double b1 = 2.0 * a1, b2 = 2.0 * a2, b3 = 2.0 * a3;
-        double jc0[8], jc1[8];
-        jc0[0] = b2 * j02 - b3 * j01;  jc1[0] = b2 * j12 - b3 * j11;
-        jc0[1] = b3 * j00 - b1 * j02;  jc1[1] = b3 * j10 - b1 * j12;
-        jc0[2] = b1 * j01 - b2 * j00;  jc1[2] = b1 * j11 - b2 * j10;
-        jc0[3] = j00; jc0[4] = j01; jc0[5] = j02;
-        jc1[3] = j10; jc1[4] = j11; jc1[5] = j12;
-        jc0[6] = d * u;            jc1[6] = d * w_;
-        jc0[7] = fo * u * r2;      jc1[7] = fo * w_ * r2;
-        // point columns: Jproj * R
-        double jx0[3], jx1[3];
-        jx0[0] = j00 * R00 + j01 * R10 + j02 * R20;
-        jx0[1] = j00 * R01 + j01 * R11 + j02 * R21;
-        jx0[2] = j00 * R02 + j01 * R12 + j02 * R22;
-        jx1[0] = j10 * R00 + j11 * R10 + j12 * R20;
-        jx1[1] = j10 * R01 + j11 * R11 + j12 * R21;
-        jx1[2] = j10 * R02 + j11 * R12 + j12 * R22;
-        if (pconst) { jx0[0] = jx0[1] = jx0[2] = jx1[0] = jx1[1] = jx1[2] = 0.0; }
-        // per-point values (reduced across the warp's frames below)
-        pvw[0 * PVS + lane] = jx0[0] * rx + jx1[0] * ry;
-        pvw[1 * PVS + lane] = jx0[1] * rx + jx1[1] * ry;
-        pvw[2 * PVS + lane] = jx0[2] * rx + jx1[2] * ry;
-        pvw[3 * PVS + lane] = jx0[0] * jx0[0] + jx1[0] * jx1[0];
-        pvw[4 * PVS + lane] = jx0[0] * jx0[1] + jx1[0] * jx1[1];
-        pvw[5 * PVS + lane] = jx0[0] * jx0[2] + jx1[0] * jx1[2];
-        pvw[6 * PVS + lane] = jx0[1] * jx0[1] + jx1[1] * jx1[1];
-        pvw[7 * PVS + lane] = jx0[1] * jx0[2] + jx1[1] * jx1[2];
-        pvw[8 * PVS + lane] = jx0[2] * jx0[2] + jx1[2] * jx1[2];
-        if (NS > 0) {
-#pragma unroll
-          for (int j = 0; j < NS; ++j)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) pvw[(9 + j * 3 + c) * PVS + lane] = jc0[6 + j] * jx0[c] + jc1[6 + j] * jx1[c];
-          gs0 += jc0[6] * rx + jc1[6] * ry;
-          hss0 += jc0[6] * jc0[6] + jc1[6] * jc1[6];
-          if (NS > 1) {
-            gs1 += jc0[7] * rx + jc1[7] * ry;
-            hss1 += jc0[6] * jc0[7] + jc1[6] * jc1[7];
-            hss2 += jc0[7] * jc0[7] + jc1[7] * jc1[7];
-          }
-        }
-        // coupling block of this (frame, track): DC rows x 3 = 24*DC contiguous bytes, 16-byte stores
-        double wb[WB];
-#pragma unroll
-        for (int i = 0; i < DC; ++i)
-#pragma unroll
-          for (int c = 0; c < 3; ++c) wb[i * 3 + c] = jc0[i] * jx0[c] + jc1[i] * jx1[c];
-        if ((WB & 1) == 0) {
-#pragma unroll
-          for (int e = 0; e < WB; e += 2) *reinterpret_cast<double2*>(wt + e) = make_double2(wb[e], wb[e + 1]);
-        } else {
-#pragma unroll
-          for (int e = 0; e < WB; ++e) wt[e] = wb[e];
-        }
-        // camera record of this lane's frame: straight into registers
-        cam_accumulate<DC, NS, KR>(acc, jc0, jc1, rx, ry, std::make_integer_sequence<int, KR>{});
-      } else {
-#pragma unroll
-        for (int i = 0; i < NP; ++i) pvw[i * PVS + lane] = 0.0;
-        if ((WB & 1) == 0) {
-#pragma unroll
-          for (int e = 0; e < WB; e += 2) *reinterpret_cast<double2*>(wt + e) = make_double2(0.0, 0.0);
-        } else {
-#pragma unroll
-          for (int e = 0; e < WB; ++e) wt[e] = 0.0;
-        }
+    for (int k = 0; k < TB; k += 2) {                            // two tracks per step: one branch-free block
+      const int nA = t0 + k;
+      if (nA >= t_end) break;                                    // warp-uniform
+      const bool hasB = nA + 1 < t_end;
+      // ---- math for both tracks, registers only (overlaps the previous step's TMA read-out)
+      double jcA0[8], jcA1[8], jxA0[3], jxA1[3], rxA, ryA;
+      double jcB0[8], jcB1[8], jxB0[3], jxB1[3], rxB, ryB;
+      {
+        const float ox = k == 0 ? ca.x : cb.x, oy = k == 0 ? ca.y : cb.y;
+        const bool valid = frame_ok && ((cm >> (8 * k)) & 0xffu) != 0;
+        obs_math<MODEL>(pw, lane, xw + ((nA - t_begin) & (XT - 1)) * 4, ox, oy, valid, jcA0, jcA1, jxA0, jxA1, rxA, ryA);
       }
-      // ship the 32 frames' blocks of track n: one contiguous run W[n][g*32*DC .. +nf*DC][3]
-      double* dst = W + ((size_t)n * pitch + (size_t)g * 32 * DC) * 3;
+      {
+        const float ox = k == 0 ? ca.z : cb.z, oy = k == 0 ? ca.w : cb.w;
+        const bool valid = hasB && frame_ok && ((cm >> (8 * (k + 1))) & 0xffu) != 0;
+        obs_math<MODEL>(pw, lane, xw + ((nA + 1 - t_begin) & (XT - 1)) * 4, ox, oy, valid, jcB0, jcB1, jxB0, jxB1, rxB, ryB);
+      }
+      cost_acc += 0.5 * (rxA * rxA + ryA * ryA) + 0.5 * (rxB * rxB + ryB * ryB);
+      // ---- both staging buffers must have been read out by the previous step's bulk stores
+      if (USE_TMA) {
+        if (lane == 0) tma_store_wait_read<0>();
+        __syncwarp();
+      }
+      double* wA = wbuf + lane * WB;
+      double* wB = wbuf + 32 * WB + lane * WB;
+      emit_blocks<DC, NS, WB>(wA, pvw, lane, jcA0, jcA1, jxA0, jxA1, rxA, ryA);
+      emit_blocks<DC, NS, WB>(wB, pvw + 16 * PVS, lane, jcB0, jcB1, jxB0, jxB1, rxB, ryB);
+      // ---- ship the 32 frames' blocks of each track: contiguous runs W[n][g*32*DC .. +nf*DC][3]
+      double* dstA = W + ((size_t)nA * pitch + (size_t)g * 32 * DC) * 3;
+      double* dstB = dstA + pitch * 3;
       const uint32_t bytes = (uint32_t)nf * WB * 8u;
       if (USE_TMA && (bytes & 15u) == 0) {
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) {
-          tma_store_1d(dst, wstage, bytes);
+          tma_store_1d(dstA, wbuf, bytes);
+          if (hasB) tma_store_1d(dstB, wbuf + 32 * WB, bytes);
           tma_store_commit();
-          tma_store_wait_read<1>();            // the other staging buffer (previous track) has been read out
         }
       } else {
         __syncwarp();
-        for (int e = lane; e < nf * WB; e += 32) dst[e] = wstage[e];
+        for (int e = lane; e < nf * WB; e += 32) dstA[e] = wbuf[e];
+        if (hasB)
+          for (int e = lane; e < nf * WB; e += 32) dstB[e] = wbuf[32 * WB + e];
+        __syncwarp();
       }
-      // per-point sums over the warp's frames: one 16-wide reduce-scatter, one RED instruction
+      // ---- camera records straight into registers
+      cam_accumulate<DC, NS, KR>(acc, jcA0, jcA1, rxA, ryA, std::make_integer_sequence<int, KR>{});
+      cam_accumulate<DC, NS, KR>(acc, jcB0, jcB1, rxB, ryB, std::make_integer_sequence<int, KR>{});
+      if (NS > 0) {
+        gs0 += jcA0[6] * rxA + jcA1[6] * ryA + jcB0[6] * rxB + jcB1[6] * ryB;
+        hss0 += jcA0[6] * jcA0[6] + jcA1[6] * jcA1[6] + jcB0[6] * jcB0[6] + jcB1[6] * jcB1[6];
+        if (NS > 1) {
+          gs1 += jcA0[7] * rxA + jcA1[7] * ryA + jcB0[7] * rxB + jcB1[7] * ryB;
+          hss1 += jcA0[6] * jcA0[7] + jcA1[6] * jcA1[7] + jcB0[6] * jcB0[7] + jcB1[6] * jcB1[7];
+          hss2 += jcA0[7] * jcA0[7] + jcA1[7] * jcA1[7] + jcB0[7] * jcB0[7] + jcB1[7] * jcB1[7];
+        }
+      }
+      // ---- per-point sums over the warp's frames: lanes 0..NP-1 take track A, lanes 16..16+NP-1 track B
       {
-        // (the __syncwarp of the W hand-off above also published the per-point scratch)
+        const int v = lane & 15;
+        const int nT = nA + (lane >> 4);
         double r = 0.0;
-        if (lane < NP) {
-          const double* row = pvw + lane * PVS;
+        if (v < NP) {
+          const double* row = pvw + ((lane >> 4) * 16 + v) * PVS;
+          double r0 = 0.0, r1 = 0.0, r2s = 0.0, r3 = 0.0;      // four independent chains, not one of 32
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r += row[j];
+          for (int j = 0; j < 32; j += 4) { r0 += row[j]; r1 += row[j + 1]; r2s += row[j + 2]; r3 += row[j + 3]; }
+          r = (r0 + r1) + (r2s + r3);
         }
-        if (lane < 16 && r != 0.0) {
-          if (lane < 3) atomicAdd(&g_p[(size_t)n * 3 + lane], r);
-          else if (lane < 9) atomicAdd(&H_pp[(size_t)n * 6 + (lane - 3)], r);
-          else if (lane < NP)
-            atomicAdd(&W[((size_t)n * pitch + (size_t)S * DC + (lane - 9) / 3) * 3 + (lane - 9) % 3], r);
+        if (r != 0.0 && nT < t_end) {
+          if (v < 3) atomicAdd(&g_p[(size_t)nT * 3 + v], r);
+          else if (v < 9) atomicAdd(&H_pp[(size_t)nT * 6 + (v - 3)], r);
+          else if (v < NP) atomicAdd(&W[((size_t)nT * pitch + (size_t)S * DC + (v - 9) / 3) * 3 + (v - 9) % 3], r);
         }
       }
-      __syncwarp();        // lanes may not overwrite the other buffer before lane 0 returned from wait_group
-      ++tcount;
+      __syncwarp();        // the scratch and the staging buffers are rewritten next step
     }
   }
   if (USE_TMA && lane == 0) tma_store_wait_all<0>();
@@ -337,7 +359,7 @@ static int launch_blocks(const vgg_ba_problem* p, double* cost, double* camrec, 
   const int S = p->S, N = p->N;
   const int D = S * C::DC + C::NS;
   const size_t pitch = w_pitch(D);
-  const size_t smem = sizeof(double) * (BW * 16 * 32 + BW * XT * 4 + BW * 16 * PVS + (size_t)BW * 2 * 32 * C::DC * 3);
+  const size_t smem = sizeof(double) * (BW * 16 * 32 + BW * XT * 4 + BW * 32 * PVS + (size_t)BW * 2 * 32 * C::DC * 3);
   const bool tma_ok = ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
   const int ngroups = (S + 31) / 32;
   if (tracks_per_warp <= 0) {
@@ -367,7 +389,7 @@ static int launch_blocks(const vgg_ba_problem* p, double* cost, double* camrec, 
   }
   // MINB = 3 caps registers at 168 (12 resident warps/SM, a few spills); MINB = 2 lets ptxas use ~210 (no spills,
   // 8 warps/SM).  VGG_K1_MINB=2|3 selects for A/B runs.
-  static const int minb = [] { const char* e = getenv("VGG_K1_MINB"); return (e && e[0] == '2') ? 2 : 3; }();
+  static const int minb = [] { const char* e = getenv("VGG_K1_MINB"); return (e && e[0] == '3') ? 3 : 2; }();
   if (tma_ok && minb == 2) {
     auto kern = ba_blocks_kernel<MODEL, MODE, true, 2>;
     VGG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
