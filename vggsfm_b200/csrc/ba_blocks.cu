@@ -362,15 +362,34 @@ static int launch_blocks(const vgg_ba_problem* p, double* cost, double* camrec, 
   const size_t smem = sizeof(double) * (BW * 16 * 32 + BW * XT * 4 + BW * 32 * PVS + (size_t)BW * 2 * 32 * C::DC * 3);
   const bool tma_ok = ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
   const int ngroups = (S + 31) / 32;
+  static const int minb = [] { const char* e = getenv("VGG_K1_MINB"); return (e && e[0] == '3') ? 3 : 2; }();
   if (tracks_per_warp <= 0) {
-    // enough warps to fill 148 SMs x 12 resident warps about twice, but at least 32 tracks per warp so the
-    // per-warp camera flush (32 x KR REDs) stays amortised; multiples of TB
-    const long want = 148L * 12 * 2;
-    const long chunks = (want + ngroups - 1) / ngroups;
-    long tpw = (N + chunks - 1) / chunks;
-    if (tpw < 32) tpw = 32;
-    tpw = (tpw + TB - 1) / TB * TB;
-    tracks_per_warp = (int)tpw;
+    // Every warp does the same amount of work, so the grid must be a whole number of waves: resident warps =
+    // SMs x CTAs/SM (occupancy query) x BW.  Pick the smallest wave count that keeps >= 32 tracks per warp
+    // amortising the per-warp camera flush (32 x KR REDs), capped at 4 waves; tracks per warp multiple of TB.
+    static int slots_cache[2] = {0, 0};
+    int& slots = slots_cache[minb == 3];
+    if (slots == 0) {
+      int dev = 0, sms = 148, per_sm = minb;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (minb == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_blocks_kernel<MODEL, MODE, true, 3>, BT, smem);
+      else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_blocks_kernel<MODEL, MODE, true, 2>, BT, smem);
+      if (per_sm < 1) per_sm = 1;
+      slots = sms * per_sm;
+    }
+    const long wave_warps = (long)slots * BW;
+    long best_tpw = N;
+    for (int waves = 1; waves <= 4; ++waves) {
+      long chunks = waves * wave_warps / ngroups;
+      if (chunks < 1) chunks = 1;
+      long tpw = (N + chunks - 1) / chunks;
+      tpw = (tpw + TB - 1) / TB * TB;
+      if (tpw < 32 && waves > 1) break;
+      best_tpw = tpw;
+      if (tpw <= 512) break;                    // enough parallel slack; more waves only add flush traffic
+    }
+    tracks_per_warp = (int)best_tpw;
   }
   const int chunks = (N + tracks_per_warp - 1) / tracks_per_warp;
   const long nwarps = (long)chunks * ngroups;
@@ -387,9 +406,8 @@ static int launch_blocks(const vgg_ba_problem* p, double* cost, double* camrec, 
     const size_t tail = pitch - (size_t)S * C::DC;
     VGG_CUDA_CHECK(cudaMemset2DAsync(W + (size_t)S * C::DC * 3, pitch * 24, 0, tail * 24, (size_t)N, stream));
   }
-  // MINB = 3 caps registers at 168 (12 resident warps/SM, a few spills); MINB = 2 lets ptxas use ~210 (no spills,
-  // 8 warps/SM).  VGG_K1_MINB=2|3 selects for A/B runs.
-  static const int minb = [] { const char* e = getenv("VGG_K1_MINB"); return (e && e[0] == '3') ? 3 : 2; }();
+  // MINB = 3 caps registers at 168 (12 resident warps/SM, a few spills); MINB = 2 lets ptxas use ~250 (no spills,
+  // 8 warps/SM) and is the default.  VGG_K1_MINB=2|3 selects for A/B runs.
   if (tma_ok && minb == 2) {
     auto kern = ba_blocks_kernel<MODEL, MODE, true, 2>;
     VGG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
