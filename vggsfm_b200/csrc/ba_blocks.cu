@@ -102,8 +102,8 @@ __device__ __forceinline__ void obs_math(const double* pw, int lane, const doubl
   const double u = px * iz, w_ = py * iz;
   const double r2 = u * u + w_ * w_;
   const double d = 1.0 + kk * r2;
-  rx = m * (fo * d * u + cx - (double)ox);
-  ry = m * (fo * d * w_ + cy - (double)oy);
+  rx = valid ? (fo * d * u + cx - (double)ox) : 0.0;            // select, not multiply: ox/oy of a masked slot may be anything
+  ry = valid ? (fo * d * w_ + cy - (double)oy) : 0.0;
   double a00, a01, a11;
   if (MODEL == VGG_SIMPLE_RADIAL) {
     a00 = fo * (d + 2.0 * kk * u * u);
@@ -238,6 +238,8 @@ __global__ void __launch_bounds__(BT, MINB) ba_blocks_kernel(
         reinterpret_cast<uint32_t*>(slot)[8] = m;
       }
     } else {
+      *reinterpret_cast<float4*>(slot) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(slot + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
       reinterpret_cast<uint32_t*>(slot)[8] = 0u;
     }
     cp_async_commit();
