@@ -10,6 +10,7 @@
 //   chol_trailing_kernel  A22 -= P P^T on 64x64 tiles with the whole K=64 panel resident in shared memory.
 // and one copy-back of the diagonal blocks at the end.  Ceres' counterpart: DENSE_SCHUR's LLT / LAPACK potrf
 // inside SchurComplementSolver (reached from pycolmap.bundle_adjustment).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace vgg {
@@ -150,15 +151,23 @@ __global__ void __launch_bounds__(256) chol_panel_kernel(int n, int lda, int k0,
 }
 
 // A[t0.., t0..] -= P P^T, P = A[t0.., k0..k0+63]; 64x64 tiles (lower), 256 threads, 4x4 outputs per thread
-__global__ void __launch_bounds__(256) chol_trailing_kernel(int n, int lda, int k0, int t0, double* __restrict__ A) {
+// mode 0: all lower tiles; mode 1: first tile column only (the next panel's columns); mode 2: the tiles right of it
+__global__ void __launch_bounds__(256) chol_trailing_kernel(int n, int lda, int k0, int t0, int mode,
+                                                            double* __restrict__ A) {
   extern __shared__ __align__(16) double ch_smem[];
   double* As = ch_smem;                         // [64 rows][CH_LD]
   double* Bs = ch_smem + CH_NB * CH_LD;
-  int t = blockIdx.x;
-  int bi = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-  while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
-  while (bi * (bi + 1) / 2 > t) --bi;
-  const int bj = t - bi * (bi + 1) / 2;
+  int bi, bj;
+  if (mode == 1) {
+    bi = blockIdx.x; bj = 0;
+  } else {
+    const int t = blockIdx.x;
+    bi = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+    while (bi * (bi + 1) / 2 > t) --bi;
+    bj = t - bi * (bi + 1) / 2;
+    if (mode == 2) { ++bi; ++bj; }
+  }
   const bool diag = bi == bj;
   const int tid = threadIdx.x;
   const int ri = t0 + bi * 64, rj = t0 + bj * 64;
@@ -227,6 +236,9 @@ size_t chol_workspace_doubles(int n) {
 
 // In-place Cholesky of the row-major lower triangle of A[n x n] (lda even, A 16-byte aligned).
 // info (device int): 0 on success, else 1-based index of the first non-positive pivot.
+// One-panel lookahead: the trailing update of panel b first refreshes the next panel's 64 columns; panel b+1 is
+// then factored on a side stream while the main stream finishes the rest of the update (the panel kernel is a
+// latency chain on ~40 CTAs, the update is throughput work on the whole chip).
 int chol_lower_inplace(int n, int lda, double* A, double* Ldiag, int* info, cudaStream_t st) {
   VGG_REQUIRE((lda % 2) == 0, "lda must be even");
   VGG_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int), st));
@@ -238,18 +250,44 @@ int chol_lower_inplace(int n, int lda, double* A, double* Ldiag, int* info, cuda
     VGG_CUDA_CHECK(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_set = true;
   }
-  for (int b = 0; b < nblk; ++b) {
+  static thread_local cudaStream_t side = nullptr;
+  static thread_local cudaEvent_t ev_col = nullptr, ev_panel = nullptr;
+  static const bool lookahead = [] { const char* e = getenv("VGG_CHOL_LOOKAHEAD"); return !(e && e[0] == '0'); }();
+  if (lookahead && !side) {
+    VGG_CUDA_CHECK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
+    VGG_CUDA_CHECK(cudaEventCreateWithFlags(&ev_col, cudaEventDisableTiming));
+    VGG_CUDA_CHECK(cudaEventCreateWithFlags(&ev_panel, cudaEventDisableTiming));
+  }
+  auto panel = [&](int b, cudaStream_t s2) -> int {
     const int k0 = b * CH_NB;
     const int below = n - (k0 + CH_NB);
     const int chunks = below > 0 ? (below + CH_NB - 1) / CH_NB : 0;
-    chol_panel_kernel<<<1 + chunks, 256, smem, st>>>(n, lda, k0, A, Ldiag, info);
+    chol_panel_kernel<<<1 + chunks, 256, smem, s2>>>(n, lda, k0, A, Ldiag, info);
     VGG_LAUNCH_CHECK();
-    if (below > 0) {
-      const int t0 = k0 + CH_NB;
-      const int nt = (n - t0 + 63) / 64;
-      chol_trailing_kernel<<<nt * (nt + 1) / 2, 256, smem, st>>>(n, lda, k0, t0, A);
+    return VGG_OK;
+  };
+  int rc;
+  if ((rc = panel(0, st))) return rc;
+  for (int b = 0; b + 1 < nblk; ++b) {
+    const int k0 = b * CH_NB, t0 = k0 + CH_NB;
+    const int nt = (n - t0 + 63) / 64;
+    if (!lookahead) {
+      chol_trailing_kernel<<<nt * (nt + 1) / 2, 256, smem, st>>>(n, lda, k0, t0, 0, A);
+      VGG_LAUNCH_CHECK();
+      if ((rc = panel(b + 1, st))) return rc;
+      continue;
+    }
+    chol_trailing_kernel<<<nt, 256, smem, st>>>(n, lda, k0, t0, 1, A);
+    VGG_LAUNCH_CHECK();
+    VGG_CUDA_CHECK(cudaEventRecord(ev_col, st));
+    VGG_CUDA_CHECK(cudaStreamWaitEvent(side, ev_col, 0));
+    if ((rc = panel(b + 1, side))) return rc;
+    VGG_CUDA_CHECK(cudaEventRecord(ev_panel, side));
+    if (nt > 1) {
+      chol_trailing_kernel<<<(nt - 1) * nt / 2, 256, smem, st>>>(n, lda, k0, t0, 2, A);
       VGG_LAUNCH_CHECK();
     }
+    VGG_CUDA_CHECK(cudaStreamWaitEvent(st, ev_panel, 0));
   }
   chol_copy_diag_kernel<<<nblk, 256, 0, st>>>(n, lda, Ldiag, A);
   VGG_LAUNCH_CHECK();
