@@ -262,7 +262,11 @@ __global__ void __launch_bounds__(SY_THREADS) syrk_kernel(int Kpad, int Dpad, in
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c = bj * SY_BM + tx * 2 + (j & 1) + 32 * (j >> 1);
-      if (acc[i][j] != 0.0 && (!diag || c <= r)) atomicAdd(&Cmat[(size_t)r * Dpad + c], -acc[i][j]);
+      if (acc[i][j] != 0.0) {
+        // both triangles: row-major lower (own Cholesky) == column-major upper, and its mirror (cuSOLVER LOWER)
+        if (!diag || c <= r) atomicAdd(&Cmat[(size_t)r * Dpad + c], -acc[i][j]);
+        if (!diag || c < r) atomicAdd(&Cmat[(size_t)c * Dpad + r], -acc[i][j]);
+      }
     }
   }
 }
@@ -357,21 +361,28 @@ __global__ void __launch_bounds__(SY_THREADS) syrk_dmma_kernel(int Kpad, int Dpa
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int cc = bj * SY_BM + wn * 64 + j * 8 + 2 * q;
-      if (c[i][j][0] != 0.0 && (!diag || cc <= r)) atomicAdd(&Cmat[(size_t)r * Dpad + cc], -c[i][j][0]);
-      if (c[i][j][1] != 0.0 && (!diag || cc + 1 <= r)) atomicAdd(&Cmat[(size_t)r * Dpad + cc + 1], -c[i][j][1]);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const double v = c[i][j][h];
+        const int col = cc + h;
+        if (v != 0.0) {
+          if (!diag || col <= r) atomicAdd(&Cmat[(size_t)r * Dpad + col], -v);
+          if (!diag || col < r) atomicAdd(&Cmat[(size_t)col * Dpad + r], -v);      // mirror
+        }
+      }
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-// A (lower, in place) = sc_i sc_j Sraw + diag; constant parameters pinned; b = sc * rhs
+// A (both triangles, in place) = sc_i sc_j Sraw + diag; constant parameters pinned; b = sc * rhs
 __global__ void scale_damp_kernel(int D, int Dpad, double* __restrict__ A, const double* __restrict__ rhs,
                                   const double* __restrict__ hdiag, const double* __restrict__ sc,
                                   const uint8_t* __restrict__ pconst, double radius, double min_diag, double max_diag,
                                   double* __restrict__ bvec) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = blockIdx.y;
-  if (j >= D || j > i) return;
+  if (j >= D) return;            // both triangles (the factorisation may read either)
   const bool ci = pconst[i] != 0, cj = pconst[j] != 0;
   double v;
   if (ci || cj) {

@@ -168,7 +168,7 @@ static int potrf_lwork(int D, int Dpad, size_t* lwork) {
     return VGG_ESOLVER;
   }
   int lw = 0;
-  if (cusolverDnDpotrf_bufferSize(h, CUBLAS_FILL_MODE_UPPER, D, nullptr, Dpad, &lw) != CUSOLVER_STATUS_SUCCESS) {
+  if (cusolverDnDpotrf_bufferSize(h, CUBLAS_FILL_MODE_LOWER, D, nullptr, Dpad, &lw) != CUSOLVER_STATUS_SUCCESS) {
     set_error("cusolverDnDpotrf_bufferSize failed");
     return VGG_ESOLVER;
   }
@@ -426,34 +426,36 @@ int vgg_ba_solve(const vgg_ba_problem* prob, const vgg_ba_options* opt_in, void*
     if ((rc = launch_scale_damp(D, L.Dpad, Sraw, rhs, hdiag, L.sc_c, prob->param_const, radius, opt.min_lm_diagonal,
                                 opt.max_lm_diagonal, L.bvec, st)))
       return rc;
-    // own blocked Cholesky (chol.cu); the factor is row-major lower == column-major upper for potrs.
-    // VGG_CHOL=cusolver switches back to cusolverDnDpotrf for A/B measurements.
+    // Factor the reduced system.  The buffer holds both triangles.  Default: cuSOLVER's 64-bit potrf on the
+    // column-major LOWER view (1.1 ms at n = 2402; its UPPER path takes 3.7 ms, r01 A/B).  VGG_CHOL=own selects the
+    // in-repo blocked Cholesky (csrc/chol.cu, row-major lower == column-major upper, 2.0 ms), VGG_CHOL=legacy the
+    // 32-bit cusolverDnDpotrf.
     static const int chol_mode = [] {
       const char* e = getenv("VGG_CHOL");
-      return !e ? 0 : (e[0] == 'c' ? 1 : (e[0] == 'x' ? 2 : 0));
+      return !e ? 0 : (e[0] == 'o' ? 2 : (e[0] == 'l' ? 1 : 0));
     }();
-    if (chol_mode == 2) {
-      // 64-bit cuSOLVER API (what torch.linalg.cholesky uses)
+    const cublasFillMode_t uplo = (chol_mode == 2) ? CUBLAS_FILL_MODE_UPPER : CUBLAS_FILL_MODE_LOWER;
+    if (chol_mode == 0) {
       static thread_local cusolverDnParams_t xp = nullptr;
       static thread_local void* xdev = nullptr;
       static thread_local void* xhost = nullptr;
       static thread_local size_t xdev_b = 0, xhost_b = 0;
       if (!xp) cusolverDnCreateParams(&xp);
       size_t db = 0, hb = 0;
-      if (cusolverDnXpotrf_bufferSize(cs, xp, CUBLAS_FILL_MODE_UPPER, D, CUDA_R_64F, Sraw, L.Dpad, CUDA_R_64F, &db, &hb) !=
+      if (cusolverDnXpotrf_bufferSize(cs, xp, uplo, D, CUDA_R_64F, Sraw, L.Dpad, CUDA_R_64F, &db, &hb) !=
           CUSOLVER_STATUS_SUCCESS) {
         set_error("cusolverDnXpotrf_bufferSize failed");
         return VGG_ESOLVER;
       }
       if (db > xdev_b) { if (xdev) cudaFree(xdev); VGG_CUDA_CHECK(cudaMalloc(&xdev, db)); xdev_b = db; }
       if (hb > xhost_b) { free(xhost); xhost = malloc(hb); xhost_b = hb; }
-      if (cusolverDnXpotrf(cs, xp, CUBLAS_FILL_MODE_UPPER, D, CUDA_R_64F, Sraw, L.Dpad, CUDA_R_64F, xdev, db, xhost, hb,
-                           L.dev_info) != CUSOLVER_STATUS_SUCCESS) {
+      if (cusolverDnXpotrf(cs, xp, uplo, D, CUDA_R_64F, Sraw, L.Dpad, CUDA_R_64F, xdev, db, xhost, hb, L.dev_info) !=
+          CUSOLVER_STATUS_SUCCESS) {
         set_error("cusolverDnXpotrf failed to launch");
         return VGG_ESOLVER;
       }
     } else if (chol_mode == 1) {
-      if (cusolverDnDpotrf(cs, CUBLAS_FILL_MODE_UPPER, D, Sraw, L.Dpad, L.potrf_work, (int)L.potrf_lwork, L.dev_info) !=
+      if (cusolverDnDpotrf(cs, uplo, D, Sraw, L.Dpad, L.potrf_work, (int)L.potrf_lwork, L.dev_info) !=
           CUSOLVER_STATUS_SUCCESS) {
         set_error("cusolverDnDpotrf failed to launch");
         return VGG_ESOLVER;
@@ -461,8 +463,7 @@ int vgg_ba_solve(const vgg_ba_problem* prob, const vgg_ba_options* opt_in, void*
     } else if ((rc = chol_lower_inplace(D, L.Dpad, Sraw, L.chol_diag, L.dev_info, st))) {
       return rc;
     }
-    if (cusolverDnDpotrs(cs, CUBLAS_FILL_MODE_UPPER, D, 1, Sraw, L.Dpad, L.bvec, L.Dpad, L.dev_info + 1) !=
-        CUSOLVER_STATUS_SUCCESS) {
+    if (cusolverDnDpotrs(cs, uplo, D, 1, Sraw, L.Dpad, L.bvec, L.Dpad, L.dev_info + 1) != CUSOLVER_STATUS_SUCCESS) {
       set_error("cusolverDnDpotrs failed to launch");
       return VGG_ESOLVER;
     }
