@@ -29,12 +29,11 @@
 
 namespace vgg {
 
-constexpr int BW = 3;            // warps per CTA (3 CTAs x 3 warps at <= 224 registers: 9 resident warps per SM)
+constexpr int BW = 4;            // warps per CTA
 constexpr int BT = BW * 32;      // threads per CTA
 constexpr int TB = 4;            // tracks per prefetch batch (32 B of uv per lane)
 constexpr int XT = 32;           // tracks per shared-memory point tile (one per lane)
 constexpr int PVS = 33;          // row stride of the per-point scratch (odd: conflict-free column sums)
-constexpr int PVR = 15;          // scratch rows per track (max NP)
 
 template <int MODEL, int MODE>
 struct BlkCfg {
@@ -170,7 +169,7 @@ __device__ __forceinline__ void emit_blocks(double* wt, double* pvw, int lane, c
 __host__ __device__ inline size_t w_pitch(int D) { return (size_t)(D + (D & 1)); }
 
 template <int MODEL, int MODE, bool USE_TMA, int MINB>
-__global__ void __maxnreg__(MINB == 3 ? 224 : 255) ba_blocks_kernel(
+__global__ void __launch_bounds__(BT, MINB) ba_blocks_kernel(
     int S, int N, int tracks_per_warp, const float* __restrict__ uv, const uint8_t* __restrict__ mask,
     const double* __restrict__ poses, const double* __restrict__ intr, const double* __restrict__ points,
     const uint8_t* __restrict__ point_const, double* __restrict__ cost, double* __restrict__ camrec,
@@ -183,7 +182,7 @@ __global__ void __maxnreg__(MINB == 3 ? 224 : 255) ba_blocks_kernel(
   double* sm_pose = reinterpret_cast<double*>(smem_raw);                // [BW][16][32]
   double* sm_x = sm_pose + BW * 16 * 32;                                 // [BW][XT][4]: X,Y,Z,const flag per track
   double* sm_pv = sm_x + BW * XT * 4;                                    // [BW][2 tracks x 16][PVS]: per-point values, one column per lane
-  double* sm_w = sm_pv + BW * 2 * PVR * PVS;                                  // [BW][2][32*WB]
+  double* sm_w = sm_pv + BW * 32 * PVS;                                  // [BW][2][32*WB]
   float* sm_obs = reinterpret_cast<float*>(sm_w + (size_t)BW * 2 * 32 * WB);   // [BW][2 stages][32 lanes][12]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int D = S * DC + NS;
@@ -200,7 +199,7 @@ __global__ void __maxnreg__(MINB == 3 ? 224 : 255) ba_blocks_kernel(
   const int nf = min(32, S - g * 32);              // frames of this group that exist
   double* pw = sm_pose + warp * 16 * 32;
   double* xw = sm_x + warp * XT * 4;
-  double* pvw = sm_pv + warp * 2 * PVR * PVS;
+  double* pvw = sm_pv + warp * 32 * PVS;
   float* ow = sm_obs + (size_t)warp * 2 * 32 * 12 + lane * 12;           // this lane's slot, stage stride 32*12
   double* wbuf = sm_w + (size_t)warp * 2 * 32 * WB;
 
@@ -295,7 +294,7 @@ __global__ void __maxnreg__(MINB == 3 ? 224 : 255) ba_blocks_kernel(
       double* wA = wbuf + lane * WB;
       double* wB = wbuf + 32 * WB + lane * WB;
       emit_blocks<DC, NS, WB>(wA, pvw, lane, jcA0, jcA1, jxA0, jxA1, rxA, ryA);
-      emit_blocks<DC, NS, WB>(wB, pvw + PVR * PVS, lane, jcB0, jcB1, jxB0, jxB1, rxB, ryB);
+      emit_blocks<DC, NS, WB>(wB, pvw + 16 * PVS, lane, jcB0, jcB1, jxB0, jxB1, rxB, ryB);
       // ---- ship the 32 frames' blocks of each track: contiguous runs W[n][g*32*DC .. +nf*DC][3]
       double* dstA = W + ((size_t)nA * pitch + (size_t)g * 32 * DC) * 3;
       double* dstB = dstA + pitch * 3;
@@ -333,7 +332,7 @@ __global__ void __maxnreg__(MINB == 3 ? 224 : 255) ba_blocks_kernel(
         const int nT = nA + (lane >> 4);
         double r = 0.0;
         if (v < NP) {
-          const double* row = pvw + ((lane >> 4) * PVR + v) * PVS;
+          const double* row = pvw + ((lane >> 4) * 16 + v) * PVS;
           double r0 = 0.0, r1 = 0.0, r2s = 0.0, r3 = 0.0;      // four independent chains, not one of 32
 #pragma unroll
           for (int j = 0; j < 32; j += 4) { r0 += row[j]; r1 += row[j + 1]; r2s += row[j + 2]; r3 += row[j + 3]; }
@@ -372,11 +371,11 @@ static int launch_blocks(const vgg_ba_problem* p, double* cost, double* camrec, 
   const int S = p->S, N = p->N;
   const int D = S * C::DC + C::NS;
   const size_t pitch = w_pitch(D);
-  const size_t smem = sizeof(double) * (BW * 16 * 32 + BW * XT * 4 + BW * 2 * PVR * PVS + (size_t)BW * 2 * 32 * C::DC * 3) +
+  const size_t smem = sizeof(double) * (BW * 16 * 32 + BW * XT * 4 + BW * 32 * PVS + (size_t)BW * 2 * 32 * C::DC * 3) +
                       sizeof(float) * BW * 2 * 32 * 12;
   const bool tma_ok = ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
   const int ngroups = (S + 31) / 32;
-  static const int minb = [] { const char* e = getenv("VGG_K1_MINB"); return (e && e[0] == '2') ? 2 : 3; }();
+  static const int minb = [] { const char* e = getenv("VGG_K1_MINB"); return (e && e[0] == '3') ? 3 : 2; }();
   if (tracks_per_warp <= 0) {
     // Every warp does the same amount of work, so the grid must be a whole number of waves: resident warps =
     // SMs x CTAs/SM (occupancy query) x BW.  Pick the smallest wave count that keeps >= 32 tracks per warp
