@@ -200,7 +200,21 @@ def run_gpu(args):
     opt = ba.default_options()
     opt.max_num_iterations = ITERS
     opt.gradient_tolerance = 0.0          # run exactly ITERS iterations every step
-    hook = AllReduceHook() if world > 1 else None
+    hook = None
+    reduction = "none (1 GPU)"
+    if world > 1:
+        fabric = None
+        if os.environ.get("VGG_FABRIC", "1") != "0":
+            try:
+                from vggsfm_b200.dist import FabricBuffer
+                fabric = FabricBuffer(S_FRAMES, model, mode, dev)
+            except Exception as e:       # no symmetric memory / multicast on this box: NCCL all-reduce instead
+                if rank == 0:
+                    print(f"[bench] fabric reduction unavailable ({str(e)[:120]}); using NCCL all-reduce", file=sys.stderr)
+                fabric = None
+        hook = AllReduceHook(fabric=fabric)
+        reduction = "multimem.red fused into the Schur kernels (NVSwitch multicast)" if hook.fabric is not None \
+            else "NCCL all-reduce of the reduced system"
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
 
     def barrier():
@@ -362,6 +376,7 @@ def run_gpu(args):
             "ms_per_step": ba_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "lm_iterations_per_step": ITERS, "parallelism": f"track-shard x{world}",
+                       "reduction": reduction,
                        "tracks_per_rank": n_loc, "l2": "256 MB flush write between steps; working set ~0.8 GB > 126 MB L2",
                        "final_cost": final_cost},
             "tracks_per_s": tracks_per_s, "tri_ms_per_pass": tri_ms / args.steps, "tri_median_point_error": tri_median_err,
@@ -371,6 +386,7 @@ def run_gpu(args):
         if hook is not None:
             line["config"]["allreduce_calls"] = hook.calls
             line["config"]["allreduce_bytes"] = hook.bytes
+            line["config"]["fabric_barriers"] = hook.barriers
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

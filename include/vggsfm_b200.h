@@ -87,8 +87,19 @@ typedef struct vgg_ba_summary {
 #define VGG_BA_FAILURE 5
 
 /* Sum/max all-reduce hook over track shards (one process per GPU).  `buf` is a device pointer
- * inside the caller's workspace; op 0 = sum, 1 = max.  NULL = single GPU. */
+ * inside the caller's workspace; op 0 = sum, 1 = max, 2 = barrier across ranks on `stream` (buf NULL).
+ * NULL = single GPU. */
 typedef int (*vgg_allreduce_fn)(void* user, double* buf, size_t count, int op, void* stream);
+
+/* Fused reduction over NVLink/NVSwitch: the reduced camera system lives in symmetric (peer-mapped) memory and
+ * every rank's assemble / Schur kernels add their contributions with multimem.red on the multicast address,
+ * so the per-iteration all-reduce of [D x Dpad | rhs | diag | g] needs no separate collective.  ar_local and
+ * ar_multicast address the same allocation (e.g. torch.distributed._symmetric_memory). */
+typedef struct vgg_ba_fabric {
+  double* ar_local;
+  double* ar_multicast;
+  size_t ar_doubles;     /* >= vgg_ba_reduced_system_doubles() */
+} vgg_ba_fabric;
 
 void vgg_ba_default_options(vgg_ba_options* opt);
 int vgg_ba_dims(int camera_model, int intr_mode, int* dc, int* ns);
@@ -123,6 +134,10 @@ int vgg_cholesky_lower(int n, int lda, double* A, void* workspace, size_t ws_byt
 int vgg_ba_solve(const vgg_ba_problem* prob, const vgg_ba_options* opt, void* workspace,
                  size_t ws_bytes, vgg_allreduce_fn allreduce, void* allreduce_user,
                  vgg_ba_summary* summary, double* trace, void* stream);
+int vgg_ba_reduced_system_doubles(int S, int camera_model, int intr_mode, size_t* doubles);
+int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt, void* workspace,
+                        size_t ws_bytes, vgg_allreduce_fn allreduce, void* allreduce_user,
+                        const vgg_ba_fabric* fabric, vgg_ba_summary* summary, double* trace, void* stream);
 
 /* ------------------------------------------------------------------------------------------- */
 /* Triangulation side (float64, like the reference's real pipeline: models/triangulator.py:91) */

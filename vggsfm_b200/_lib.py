@@ -16,6 +16,7 @@ EXPORTS = [
     "vgg_last_error", "vgg_version",
     "vgg_ba_default_options", "vgg_ba_dims", "vgg_ba_workspace_bytes", "vgg_ba_camrec_len",
     "vgg_ba_build_blocks", "vgg_ba_schur", "vgg_cholesky_lower", "vgg_ba_solve",
+    "vgg_ba_reduced_system_doubles", "vgg_ba_solve_fabric",
     "vgg_tri_workspace_bytes", "vgg_triangulate_tracks", "vgg_triangulate_by_pair", "vgg_filter_points3d",
     "vgg_project_points", "vgg_normalize_tracks", "vgg_undistort_simple_radial",
     "vgg_corr_pyramid_bytes", "vgg_corr_build_pyramid", "vgg_corr_sample",
@@ -60,6 +61,10 @@ class BASummary(ctypes.Structure):
     ]
 
 
+class BAFabric(ctypes.Structure):
+    _fields_ = [("ar_local", ctypes.c_void_p), ("ar_multicast", ctypes.c_void_p), ("ar_doubles", ctypes.c_size_t)]
+
+
 ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                 ctypes.c_int, ctypes.c_void_p)
 
@@ -96,6 +101,9 @@ def lib() -> ctypes.CDLL:
                                ALLREDUCE_FN, ctypes.c_void_p, ctypes.POINTER(BASummary), ctypes.c_void_p,
                                ctypes.c_void_p]
     vp, ci, cd, cs = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_size_t
+    L.vgg_ba_reduced_system_doubles.argtypes = [ci, ci, ci, ctypes.POINTER(cs)]
+    L.vgg_ba_solve_fabric.argtypes = [ctypes.POINTER(BAProblem), ctypes.POINTER(BAOptions), vp, cs, ALLREDUCE_FN, vp,
+                                      ctypes.POINTER(BAFabric), ctypes.POINTER(BASummary), vp, vp]
     L.vgg_cholesky_lower.argtypes = [ci, ci, vp, vp, cs, ctypes.POINTER(ci), vp]
     L.vgg_tri_workspace_bytes.argtypes = [ci, ci, ci, ci, ctypes.POINTER(cs)]
     L.vgg_triangulate_tracks.argtypes = [ci, ci, vp, vp, vp, vp, vp, ci, ci, cd, cd, vp, vp, vp, vp, cs, vp]

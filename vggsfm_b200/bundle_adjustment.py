@@ -196,10 +196,17 @@ def lm_solve(uv, mask, poses, intr, points, model, mode, param_const=None, point
     summ = BASummary()
     trace = torch.zeros(max(1, opt.max_num_iterations), 8, dtype=torch.float64) if want_trace else None
     cb = allreduce.bind(ws) if allreduce is not None else _lib.ALLREDUCE_FN()
+    fabric = getattr(allreduce, "fabric", None)
     with torch.cuda.device(dev):
         st = torch.cuda.current_stream().cuda_stream
-        rc = L.vgg_ba_solve(ctypes.byref(p), ctypes.byref(opt), ws.data_ptr(), ws.numel(), cb, None,
-                            ctypes.byref(summ), trace.data_ptr() if trace is not None else None, st)
+        if fabric is not None:
+            fs = fabric.struct()
+            rc = L.vgg_ba_solve_fabric(ctypes.byref(p), ctypes.byref(opt), ws.data_ptr(), ws.numel(), cb, None,
+                                       ctypes.byref(fs), ctypes.byref(summ),
+                                       trace.data_ptr() if trace is not None else None, st)
+        else:
+            rc = L.vgg_ba_solve(ctypes.byref(p), ctypes.byref(opt), ws.data_ptr(), ws.numel(), cb, None,
+                                ctypes.byref(summ), trace.data_ptr() if trace is not None else None, st)
     _lib.check(rc, "vgg_ba_solve")
     return Summary(summ.iterations, summ.successful, TERMINATION.get(summ.termination, "?"), summ.initial_cost,
                    summ.final_cost, summ.final_radius, summ.device_ms, summ.kernel_launches,

@@ -12,10 +12,24 @@
 //                   tiles, cp.async double-buffered k-slabs, split-K with f64 RED epilogue
 //   scale_damp      A = Dc Sraw Dc + diag(clamp(diag(Dc Hcc Dc)))/radius, constant parameters pinned
 //   cam_step / backsub_partial / point_step / cam_update   back-substitution and the candidate state
+#include <stddef.h>
 #include <stdlib.h>
 #include "common.cuh"
 
 namespace vgg {
+
+// Add v to one element of the reduced-system buffer.  Single GPU: plain f64 RED on the local copy.  Track-sharded
+// multi-GPU ("fabric" mode): ONE multimem reduction on the NVSwitch multicast address, which lands the addend in every
+// rank's copy of the buffer -- the all-reduce of the reduced camera system happens inside the kernels that
+// produce it (assemble, z_build, SYRK epilogue), tile by tile, instead of in a separate NCCL call afterwards.
+__device__ __forceinline__ void ar_add(double* local, double* mc, double v) {
+  if (mc) asm volatile("multimem.red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(mc), "d"(v) : "memory");
+  else atomicAdd(local, v);
+}
+__device__ __forceinline__ void ar_put(double* local, double* mc, double v) {   // buffer is zero beforehand
+  if (mc) asm volatile("multimem.red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(mc), "d"(v) : "memory");
+  else *local = v;
+}
 
 // ------------------------------------------------------------------------------------------------
 __global__ void jacobi_scale_points_kernel(int N, const double* __restrict__ H_pp, double* __restrict__ sc_p, int enable) {
@@ -99,44 +113,47 @@ __global__ void point_prep_kernel(int N, const double* __restrict__ H_pp, const 
 // rhs = -g, hdiag, gvec.  One CTA per frame, plus one for the shared-intrinsics block.
 __global__ void assemble_hc_kernel(int S, int dc, int ns, int KR, int Dpad, const double* __restrict__ camrec,
                                    const double* __restrict__ shared_in, double* __restrict__ Sraw,
-                                   double* __restrict__ rhs, double* __restrict__ hdiag, double* __restrict__ gvec) {
+                                   double* __restrict__ rhs, double* __restrict__ hdiag, double* __restrict__ gvec,
+                                   ptrdiff_t mc_off) {
   const int s = blockIdx.x;
   const int tid = threadIdx.x;
+#define VGG_PUT(ptr, val) ar_put((ptr), mc_off ? (ptr) + mc_off : nullptr, (val))
   if (s < S) {
     const double* rec = camrec + (size_t)s * KR;
     const int base = s * dc;
     if (tid < dc) {
-      gvec[base + tid] = rec[tid];
-      rhs[base + tid] = -rec[tid];
+      VGG_PUT(&gvec[base + tid], rec[tid]);
+      VGG_PUT(&rhs[base + tid], -rec[tid]);
     }
     if (tid < dc * dc) {
       const int i = tid / dc, j = tid % dc;
       const int a = i < j ? i : j, b = i < j ? j : i;
       const int idx = dc + a * dc - a * (a - 1) / 2 + (b - a);
       const double val = rec[idx];
-      Sraw[(size_t)(base + i) * Dpad + base + j] = val;
-      if (i == j) hdiag[base + i] = val;
+      VGG_PUT(&Sraw[(size_t)(base + i) * Dpad + base + j], val);
+      if (i == j) VGG_PUT(&hdiag[base + i], val);
     }
     if (tid < 6 * ns) {
       const int i = tid / ns, j = tid % ns;
       const double val = rec[dc + dc * (dc + 1) / 2 + tid];
-      Sraw[(size_t)(S * dc + j) * Dpad + base + i] = val;
-      Sraw[(size_t)(base + i) * Dpad + S * dc + j] = val;
+      VGG_PUT(&Sraw[(size_t)(S * dc + j) * Dpad + base + i], val);
+      VGG_PUT(&Sraw[(size_t)(base + i) * Dpad + S * dc + j], val);
     }
   } else if (ns > 0) {
     const int base = S * dc;
     if (tid < ns) {
-      gvec[base + tid] = shared_in[tid];
-      rhs[base + tid] = -shared_in[tid];
+      VGG_PUT(&gvec[base + tid], shared_in[tid]);
+      VGG_PUT(&rhs[base + tid], -shared_in[tid]);
     }
     if (tid < ns * ns) {
       const int i = tid / ns, j = tid % ns;
       const int a = i < j ? i : j, b = i < j ? j : i;
       const double val = shared_in[2 + (a == 0 ? b : 2)];
-      Sraw[(size_t)(base + i) * Dpad + base + j] = val;
-      if (i == j) hdiag[base + i] = val;
+      VGG_PUT(&Sraw[(size_t)(base + i) * Dpad + base + j], val);
+      if (i == j) VGG_PUT(&hdiag[base + i], val);
     }
   }
+#undef VGG_PUT
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -147,7 +164,8 @@ __global__ void assemble_hc_kernel(int S, int dc, int ns, int KR, int Dpad, cons
 constexpr int ZB_NT = 32;
 __global__ void __launch_bounds__(128) z_build_kernel(int D, int N, int Dpad, size_t pitch, const double* __restrict__ W,
                                                       const double* __restrict__ M, const double* __restrict__ q,
-                                                      double* __restrict__ Zt, double* __restrict__ rhs) {
+                                                      double* __restrict__ Zt, double* __restrict__ rhs,
+                                                      ptrdiff_t mc_off) {
   __shared__ double sm[ZB_NT][12];
   const int row = blockIdx.x * 128 + threadIdx.x;
   const int n0 = blockIdx.y * ZB_NT;
@@ -173,7 +191,7 @@ __global__ void __launch_bounds__(128) z_build_kernel(int D, int N, int Dpad, si
     zo[2 * (size_t)Dpad] = z2;
     zq += z0 * m[9] + z1 * m[10] + z2 * m[11];
   }
-  if (zq != 0.0) atomicAdd(&rhs[row], zq);
+  if (zq != 0.0) ar_add(&rhs[row], mc_off ? &rhs[row] + mc_off : nullptr, zq);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -181,7 +199,8 @@ __global__ void __launch_bounds__(128) z_build_kernel(int D, int N, int Dpad, si
 constexpr int SY_BM = 128, SY_BK = 16, SY_THREADS = 256, SY_STAGES = 3;
 
 __global__ void __launch_bounds__(SY_THREADS) syrk_kernel(int Kpad, int Dpad, int k_per_split,
-                                                          const double* __restrict__ Zt, double* __restrict__ Cmat) {
+                                                          const double* __restrict__ Zt, double* __restrict__ Cmat,
+                                                          ptrdiff_t mc_off) {
   extern __shared__ __align__(16) double sy_smem[];
   // tile decode: blockIdx.x -> (bi >= bj)
   int t = blockIdx.x;
@@ -264,8 +283,12 @@ __global__ void __launch_bounds__(SY_THREADS) syrk_kernel(int Kpad, int Dpad, in
       const int c = bj * SY_BM + tx * 2 + (j & 1) + 32 * (j >> 1);
       if (acc[i][j] != 0.0) {
         // both triangles: row-major lower (own Cholesky) == column-major upper, and its mirror (cuSOLVER LOWER)
-        if (!diag || c <= r) atomicAdd(&Cmat[(size_t)r * Dpad + c], -acc[i][j]);
-        if (!diag || c < r) atomicAdd(&Cmat[(size_t)c * Dpad + r], -acc[i][j]);
+        // fabric mode: only the triangle the library factorisation reads (column-major lower), one multimem op each
+        if (!mc_off && (!diag || c <= r)) atomicAdd(&Cmat[(size_t)r * Dpad + c], -acc[i][j]);
+        if (!diag || c < r || (mc_off && c == r)) {
+          double* q = &Cmat[(size_t)c * Dpad + r];
+          ar_add(q, mc_off ? q + mc_off : nullptr, -acc[i][j]);
+        }
       }
     }
   }
@@ -285,7 +308,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 
 __global__ void __launch_bounds__(SY_THREADS) syrk_dmma_kernel(int Kpad, int Dpad, int k_per_split,
                                                                const double* __restrict__ Zt,
-                                                               double* __restrict__ Cmat) {
+                                                               double* __restrict__ Cmat, ptrdiff_t mc_off) {
   extern __shared__ __align__(16) double sd_smem[];
   int t = blockIdx.x;
   int bi = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
@@ -366,8 +389,11 @@ __global__ void __launch_bounds__(SY_THREADS) syrk_dmma_kernel(int Kpad, int Dpa
         const double v = c[i][j][h];
         const int col = cc + h;
         if (v != 0.0) {
-          if (!diag || col <= r) atomicAdd(&Cmat[(size_t)r * Dpad + col], -v);
-          if (!diag || col < r) atomicAdd(&Cmat[(size_t)col * Dpad + r], -v);      // mirror
+          if (!mc_off && (!diag || col <= r)) atomicAdd(&Cmat[(size_t)r * Dpad + col], -v);
+          if (!diag || col < r || (mc_off && col == r)) {                         // mirror / fabric triangle
+            double* q = &Cmat[(size_t)col * Dpad + r];
+            ar_add(q, mc_off ? q + mc_off : nullptr, -v);
+          }
         }
       }
     }
@@ -571,20 +597,21 @@ int launch_point_prep(int N, const double* H_pp, const double* g_p, const double
   return VGG_OK;
 }
 int launch_assemble_hc(int S, int dc, int ns, int KR, int Dpad, const double* camrec, const double* shared_in,
-                       double* Sraw, double* rhs, double* hdiag, double* gvec, cudaStream_t st) {
-  assemble_hc_kernel<<<S + (ns > 0 ? 1 : 0), 64, 0, st>>>(S, dc, ns, KR, Dpad, camrec, shared_in, Sraw, rhs, hdiag, gvec);
+                       double* Sraw, double* rhs, double* hdiag, double* gvec, ptrdiff_t mc_off, cudaStream_t st) {
+  assemble_hc_kernel<<<S + (ns > 0 ? 1 : 0), 64, 0, st>>>(S, dc, ns, KR, Dpad, camrec, shared_in, Sraw, rhs, hdiag, gvec,
+                                                          mc_off);
   VGG_LAUNCH_CHECK();
   return VGG_OK;
 }
 int launch_z_transpose(int D, int N, int Dpad, const double* W, const double* M, const double* q, double* Zt,
-                       double* rhs, cudaStream_t st) {
+                       double* rhs, ptrdiff_t mc_off, cudaStream_t st) {
   const size_t pitch = (size_t)(D + (D & 1));
   dim3 grid((D + 127) / 128, (N + ZB_NT - 1) / ZB_NT);
-  z_build_kernel<<<grid, 128, 0, st>>>(D, N, Dpad, pitch, W, M, q, Zt, rhs);
+  z_build_kernel<<<grid, 128, 0, st>>>(D, N, Dpad, pitch, W, M, q, Zt, rhs, mc_off);
   VGG_LAUNCH_CHECK();
   return VGG_OK;
 }
-int launch_syrk(int Kpad, int Dpad, const double* Zt, double* Cmat, cudaStream_t st) {
+int launch_syrk(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t mc_off, cudaStream_t st) {
   const int nb = Dpad / SY_BM;
   const int ntiles = nb * (nb + 1) / 2;
   const int nslab = Kpad / SY_BK;
@@ -606,8 +633,8 @@ int launch_syrk(int Kpad, int Dpad, const double* Zt, double* Cmat, cudaStream_t
     attr_set = true;
   }
   dim3 grid(ntiles, splits);
-  if (use_dmma) syrk_dmma_kernel<<<grid, SY_THREADS, smem_d, st>>>(Kpad, Dpad, slabs_per * SY_BK, Zt, Cmat);
-  else syrk_kernel<<<grid, SY_THREADS, smem, st>>>(Kpad, Dpad, slabs_per * SY_BK, Zt, Cmat);
+  if (use_dmma) syrk_dmma_kernel<<<grid, SY_THREADS, smem_d, st>>>(Kpad, Dpad, slabs_per * SY_BK, Zt, Cmat, mc_off);
+  else syrk_kernel<<<grid, SY_THREADS, smem, st>>>(Kpad, Dpad, slabs_per * SY_BK, Zt, Cmat, mc_off);
   VGG_LAUNCH_CHECK();
   return VGG_OK;
 }

@@ -29,10 +29,10 @@ int launch_point_prep(int N, const double* H_pp, const double* g_p, const double
                       double radius, double min_diag, double max_diag, double* M, double* q, double* dpp,
                       double* scal, cudaStream_t st);
 int launch_assemble_hc(int S, int dc, int ns, int KR, int Dpad, const double* camrec, const double* shared_in,
-                       double* Sraw, double* rhs, double* hdiag, double* gvec, cudaStream_t st);
+                       double* Sraw, double* rhs, double* hdiag, double* gvec, ptrdiff_t mc_off, cudaStream_t st);
 int launch_z_transpose(int D, int N, int Dpad, const double* W, const double* M, const double* q, double* Zt,
-                       double* rhs, cudaStream_t st);
-int launch_syrk(int Kpad, int Dpad, const double* Zt, double* Cmat, cudaStream_t st);
+                       double* rhs, ptrdiff_t mc_off, cudaStream_t st);
+int launch_syrk(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t mc_off, cudaStream_t st);
 int launch_scale_damp(int D, int Dpad, double* A, const double* rhs, const double* hdiag, const double* sc,
                       const uint8_t* pconst, double radius, double min_diag, double max_diag, double* bvec,
                       cudaStream_t st);
@@ -178,7 +178,8 @@ static int potrf_lwork(int D, int Dpad, size_t* lwork) {
 
 // Schur complement of blk onto AR (Sraw, rhs, hdiag, gvec) at the given radius
 static int schur_build(const Layout& L, const BlockSet& b, const uint8_t* point_const, double radius, double min_diag,
-                       double max_diag, cudaStream_t st) {
+                       double max_diag, cudaStream_t st, ptrdiff_t mc_off = 0, vgg_allreduce_fn barrier = nullptr,
+                       void* barrier_user = nullptr) {
   int rc;
   double* Sraw = L.AR;
   double* rhs = L.AR + (size_t)L.D * L.Dpad;
@@ -188,9 +189,13 @@ static int schur_build(const Layout& L, const BlockSet& b, const uint8_t* point_
                               L.scal, st)))
     return rc;
   VGG_CUDA_CHECK(cudaMemsetAsync(L.AR, 0, sizeof(double) * ((size_t)L.D * L.Dpad + 3 * (size_t)L.Dpad), st));
-  if ((rc = launch_assemble_hc(L.S, L.dc, L.ns, L.KR, L.Dpad, b.camrec, b.shared, Sraw, rhs, hdiag, gvec, st))) return rc;
-  if ((rc = launch_z_transpose(L.D, L.N, L.Dpad, b.W, L.M, L.q, L.Zt, rhs, st))) return rc;
-  if ((rc = launch_syrk(L.Kpad, L.Dpad, L.Zt, Sraw, st))) return rc;
+  // fabric mode: every rank's copy must be zero before anyone's multimem reductions land in it
+  if (mc_off && barrier && (rc = barrier(barrier_user, nullptr, 0, 2, st))) return rc;
+  if ((rc = launch_assemble_hc(L.S, L.dc, L.ns, L.KR, L.Dpad, b.camrec, b.shared, Sraw, rhs, hdiag, gvec, mc_off, st))) return rc;
+  if ((rc = launch_z_transpose(L.D, L.N, L.Dpad, b.W, L.M, L.q, L.Zt, rhs, mc_off, st))) return rc;
+  if ((rc = launch_syrk(L.Kpad, L.Dpad, L.Zt, Sraw, mc_off, st))) return rc;
+  // ... and all reductions must have landed before anyone reads its copy
+  if (mc_off && barrier && (rc = barrier(barrier_user, nullptr, 0, 2, st))) return rc;
   return VGG_OK;
 }
 
@@ -307,8 +312,25 @@ int vgg_cholesky_lower(int n, int lda, double* A, void* workspace, size_t ws_byt
   return VGG_OK;
 }
 
+int vgg_ba_reduced_system_doubles(int S, int camera_model, int intr_mode, size_t* doubles) {
+  int dc, ns;
+  if (!doubles || dims_of(camera_model, intr_mode, &dc, &ns, nullptr) != VGG_OK) {
+    set_error("bad camera_model/intr_mode");
+    return VGG_EINVAL;
+  }
+  const size_t D = (size_t)S * dc + ns, Dpad = align_up(D, 128);
+  *doubles = D * Dpad + 3 * Dpad;
+  return VGG_OK;
+}
+
 int vgg_ba_solve(const vgg_ba_problem* prob, const vgg_ba_options* opt_in, void* workspace, size_t ws_bytes,
                  vgg_allreduce_fn allreduce, void* ar_user, vgg_ba_summary* summary, double* trace, void* stream) {
+  return vgg_ba_solve_fabric(prob, opt_in, workspace, ws_bytes, allreduce, ar_user, nullptr, summary, trace, stream);
+}
+
+int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in, void* workspace, size_t ws_bytes,
+                        vgg_allreduce_fn allreduce, void* ar_user, const vgg_ba_fabric* fabric, vgg_ba_summary* summary,
+                        double* trace, void* stream) {
   VGG_REQUIRE(prob && workspace && summary, "null pointer");
   VGG_REQUIRE(prob->uv && prob->mask && prob->param_const && prob->poses && prob->intr && prob->points, "null problem array");
   cudaStream_t st = (cudaStream_t)stream;
@@ -334,11 +356,20 @@ int vgg_ba_solve(const vgg_ba_problem* prob, const vgg_ba_options* opt_in, void*
     set_error("cusolverDnSetStream failed");
     return VGG_ESOLVER;
   }
+  const size_t ar_count = (size_t)D * L.Dpad + 3 * (size_t)L.Dpad;
+  // fabric mode: the reduced system lives in symmetric (peer-mapped) memory and is reduced by multimem operations
+  // issued from the producing kernels; mc_off is the distance from a local address to its multicast twin
+  ptrdiff_t mc_off = 0;
+  if (fabric && fabric->ar_local && fabric->ar_multicast) {
+    VGG_REQUIRE(allreduce, "fabric mode needs the hook for its barrier (op 2)");
+    VGG_REQUIRE(fabric->ar_doubles >= ar_count, "fabric buffer too small (vgg_ba_reduced_system_doubles)");
+    L.AR = fabric->ar_local;
+    mc_off = fabric->ar_multicast - fabric->ar_local;
+  }
   double* Sraw = L.AR;
   double* rhs = L.AR + (size_t)D * L.Dpad;
   double* hdiag = rhs + L.Dpad;
   double* gvec = hdiag + L.Dpad;
-  const size_t ar_count = (size_t)D * L.Dpad + 3 * (size_t)L.Dpad;
 
   cudaEvent_t ev0, ev1;
   VGG_CUDA_CHECK(cudaEventCreate(&ev0));
@@ -417,8 +448,10 @@ int vgg_ba_solve(const vgg_ba_problem* prob, const vgg_ba_options* opt_in, void*
     ++it;
     const int cand = cur ^ 1;
     VGG_CUDA_CHECK(cudaMemsetAsync(L.scal, 0, sizeof(double) * 16, st));
-    if ((rc = schur_build(L, L.blk[cur], prob->point_const, radius, opt.min_lm_diagonal, opt.max_lm_diagonal, st))) return rc;
-    if (allreduce && (rc = allreduce(ar_user, L.AR, ar_count, 0, st))) return rc;
+    if ((rc = schur_build(L, L.blk[cur], prob->point_const, radius, opt.min_lm_diagonal, opt.max_lm_diagonal, st, mc_off,
+                          allreduce, ar_user)))
+      return rc;
+    if (allreduce && !mc_off && (rc = allreduce(ar_user, L.AR, ar_count, 0, st))) return rc;
     if (!have_scale_c) {
       if ((rc = launch_jacobi_scale_cams(D, hdiag, L.sc_c, opt.jacobi_scaling, st))) return rc;
       have_scale_c = true;
@@ -434,8 +467,9 @@ int vgg_ba_solve(const vgg_ba_problem* prob, const vgg_ba_options* opt_in, void*
       const char* e = getenv("VGG_CHOL");
       return !e ? 0 : (e[0] == 'o' ? 2 : (e[0] == 'l' ? 1 : 0));
     }();
-    const cublasFillMode_t uplo = (chol_mode == 2) ? CUBLAS_FILL_MODE_UPPER : CUBLAS_FILL_MODE_LOWER;
-    if (chol_mode == 0) {
+    const int cm = (mc_off && chol_mode == 2) ? 0 : chol_mode;      // fabric mode reduces one triangle only
+    const cublasFillMode_t uplo = (cm == 2) ? CUBLAS_FILL_MODE_UPPER : CUBLAS_FILL_MODE_LOWER;
+    if (cm == 0) {
       static thread_local cusolverDnParams_t xp = nullptr;
       static thread_local void* xdev = nullptr;
       static thread_local void* xhost = nullptr;
@@ -454,7 +488,7 @@ int vgg_ba_solve(const vgg_ba_problem* prob, const vgg_ba_options* opt_in, void*
         set_error("cusolverDnXpotrf failed to launch");
         return VGG_ESOLVER;
       }
-    } else if (chol_mode == 1) {
+    } else if (cm == 1) {
       if (cusolverDnDpotrf(cs, uplo, D, Sraw, L.Dpad, L.potrf_work, (int)L.potrf_lwork, L.dev_info) !=
           CUSOLVER_STATUS_SUCCESS) {
         set_error("cusolverDnDpotrf failed to launch");

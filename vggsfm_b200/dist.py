@@ -28,13 +28,39 @@ def shard_range(N: int, rank: int, world: int, multiple: int = 16):
     return lo, hi
 
 
-class AllReduceHook:
-    """vgg_allreduce_fn implemented with torch.distributed on views of the solver workspace."""
+class FabricBuffer:
+    """Reduced-system buffer in symmetric (peer-mapped, NVSwitch-multicast) memory for the fused reduction:
+    the Schur kernels of every rank add into all copies with multimem.red (csrc/ba_schur.cu: ar_add), so the
+    per-iteration all-reduce of [D x Dpad | rhs | diag | g] needs no separate collective -- only two barriers."""
 
-    def __init__(self, group=None):
+    def __init__(self, S: int, model: int, mode: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        n = ctypes.c_size_t()
+        _lib.check(_lib.lib().vgg_ba_reduced_system_doubles(S, model, mode, ctypes.byref(n)), "vgg_ba_reduced_system_doubles")
+        self.count = n.value
+        self.tensor = symm_mem.empty(self.count, dtype=torch.float64, device=device)
+        self.handle = symm_mem.rendezvous(self.tensor, group if group is not None else dist.group.WORLD)
+        self.multicast_ptr = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        self.ok = self.multicast_ptr != 0
+
+    def barrier(self):
+        self.handle.barrier(channel=0)
+
+    def struct(self):
+        return _lib.BAFabric(self.tensor.data_ptr(), self.multicast_ptr, self.count)
+
+
+class AllReduceHook:
+    """vgg_allreduce_fn implemented with torch.distributed on views of the solver workspace.  With a FabricBuffer
+    attached, the big per-iteration reduction is done by the kernels themselves and this hook only provides the
+    cross-rank barrier (op 2) and the small cost/gradient reductions."""
+
+    def __init__(self, group=None, fabric: "FabricBuffer | None" = None):
         self.group = group
+        self.fabric = fabric if (fabric is not None and fabric.ok) else None
         self.calls = 0
         self.bytes = 0
+        self.barriers = 0
         self._ws = None
         self._cb = None
 
@@ -44,6 +70,10 @@ class AllReduceHook:
 
         def _fn(user, buf, count, op, stream):
             try:
+                if op == 2:
+                    self.fabric.barrier()
+                    self.barriers += 1
+                    return 0
                 off = buf - base
                 view = self._ws[off:off + count * 8].view(torch.float64)
                 dist.all_reduce(view, op=dist.ReduceOp.SUM if op == 0 else dist.ReduceOp.MAX, group=self.group)
