@@ -151,7 +151,7 @@ def schur(uv, mask, poses, intr, points, model, mode, blocks, scale_p, radius, m
     S, N = mask.shape
     dc, ns = dims(model, mode)
     D = S * dc + ns
-    Dpad = (D + 127) // 128 * 128
+    Dpad = (D + 2 + 127) // 128 * 128          # same rule as csrc/ba_solve.cu make_layout
     dev = uv.device
     ws = workspace(S, N, model, mode, dev)
     Sraw = torch.empty(D, Dpad, dtype=torch.float64, device=dev)

@@ -114,7 +114,7 @@ static int make_layout(int S, int N, int model, int mode, void* base, size_t cap
   }
   L->S = S; L->N = N; L->dc = dc; L->ns = ns; L->KR = KR;
   L->D = S * dc + ns;
-  L->Dpad = (int)align_up(L->D, 128);
+  L->Dpad = (int)align_up((size_t)L->D + 2, 128);      // >= 2 spare slots after D (fabric-mode scalar sync)
   L->Kpad = (int)align_up((size_t)3 * N, 16);
   Carver c(base, cap);
   for (int b = 0; b < 2; ++b) {
@@ -243,7 +243,7 @@ int vgg_ba_workspace_bytes(int S, int N, int camera_model, int intr_mode, size_t
   }
   const int D = S * dc + ns;
   size_t lwork = 0;
-  int rc = potrf_lwork(D, (int)align_up(D, 128), &lwork);
+  int rc = potrf_lwork(D, (int)align_up((size_t)D + 2, 128), &lwork);
   if (rc) return rc;
   Layout L;
   rc = make_layout(S, N, camera_model, intr_mode, nullptr, 0, lwork, &L);
@@ -269,7 +269,7 @@ int vgg_ba_schur(const vgg_ba_problem* prob, const double* camrec, const double*
   size_t lwork = 0;
   int dc, ns;
   dims_of(prob->camera_model, prob->intr_mode, &dc, &ns, nullptr);
-  int rc = potrf_lwork(prob->S * dc + ns, (int)align_up(prob->S * dc + ns, 128), &lwork);
+  int rc = potrf_lwork(prob->S * dc + ns, (int)align_up((size_t)(prob->S * dc + ns) + 2, 128), &lwork);
   if (rc) return rc;
   Layout L;
   rc = make_layout(prob->S, prob->N, prob->camera_model, prob->intr_mode, workspace, ws_bytes, lwork, &L);
@@ -318,7 +318,7 @@ int vgg_ba_reduced_system_doubles(int S, int camera_model, int intr_mode, size_t
     set_error("bad camera_model/intr_mode");
     return VGG_EINVAL;
   }
-  const size_t D = (size_t)S * dc + ns, Dpad = align_up(D, 128);
+  const size_t D = (size_t)S * dc + ns, Dpad = align_up(D + 2, 128);
   *doubles = D * Dpad + 3 * Dpad;
   return VGG_OK;
 }
@@ -346,7 +346,7 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
   }
   const int D = S * dc + ns;
   size_t lwork = 0;
-  int rc = potrf_lwork(D, (int)align_up(D, 128), &lwork);
+  int rc = potrf_lwork(D, (int)align_up((size_t)D + 2, 128), &lwork);
   if (rc) return rc;
   Layout L;
   rc = make_layout(S, N, prob->camera_model, prob->intr_mode, workspace, ws_bytes, lwork, &L);
@@ -505,6 +505,15 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
     if ((rc = launch_cam_step(D, L.bvec, L.sc_c, hdiag, gvec, prob->param_const, radius, opt.min_lm_diagonal,
                               opt.max_lm_diagonal, L.d_c, L.scal, st)))
       return rc;
+    if (mc_off) {
+      // Fabric mode: the multimem reductions reach each rank's copy in a different order, so the copies (and with
+      // them the factorisation and the camera step) differ in the last bits.  Keep the replicated camera state
+      // and the accept/reject scalars bit-identical on every rank: element-wise MAX over ranks of
+      // [d_c | quad_c | |d_c|^2] (one 19 KB collective; any rank-consistent choice within rounding would do).
+      VGG_CUDA_CHECK(cudaMemcpyAsync(L.d_c + L.Dpad - 2, L.scal, sizeof(double) * 2, cudaMemcpyDeviceToDevice, st));
+      if ((rc = allreduce(ar_user, L.d_c, (size_t)L.Dpad, 1, st))) return rc;
+      VGG_CUDA_CHECK(cudaMemcpyAsync(L.scal, L.d_c + L.Dpad - 2, sizeof(double) * 2, cudaMemcpyDeviceToDevice, st));
+    }
     if ((rc = launch_backsub(D, N, L.blk[cur].W, L.d_c, L.wacc, st))) return rc;
     if ((rc = launch_point_step(N, L.M, L.blk[cur].g_p, L.wacc, L.sc_p, L.dpp, L.points[cur], radius, L.points[cand],
                                 L.scal, st)))
