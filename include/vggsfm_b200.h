@@ -140,6 +140,42 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt, v
                         const vgg_ba_fabric* fabric, vgg_ba_summary* summary, double* trace, void* stream);
 
 /* ------------------------------------------------------------------------------------------- */
+/* Absolute-pose refinement: replaces the per-frame loop around pycolmap.pose_refinement        */
+/* (vggsfm/utils/triangulation.py:260-479 refine_pose, :482-647 init_refine_pose).               */
+/* ------------------------------------------------------------------------------------------- */
+
+/* COLMAP AbsolutePoseRefinementOptions + the Ceres defaults behind it, plus the two pre-filters the
+ * reference applies around the call: max_reproj_error > 0 ANDs the mask with (depth > 0 and squared
+ * reprojection error <= max^2) at the input camera (triangulation.py:298-315); a frame is refined only
+ * when its effective inlier count is > min_inliers (:386, :585). */
+typedef struct vgg_pose_options {
+  int32_t max_num_iterations;
+  int32_t max_num_consecutive_invalid_steps;
+  int32_t min_inliers;
+  int32_t reserved;
+  double function_tolerance, gradient_tolerance, parameter_tolerance;
+  double initial_trust_region_radius, max_trust_region_radius, min_trust_region_radius;
+  double min_relative_decrease, min_lm_diagonal, max_lm_diagonal;
+  double loss_function_scale;   /* ceres::CauchyLoss scale */
+  double max_reproj_error;      /* pixels; <= 0 disables the pre-filter */
+} vgg_pose_options;
+
+#define VGG_POSE_SKIPPED 6       /* frame_flags bit0 clear */
+#define VGG_POSE_FEW_INLIERS 7   /* effective inliers <= min_inliers: pose left unchanged */
+
+void vgg_pose_default_options(vgg_pose_options* opt);
+
+/* One launch, one CTA per frame.  uv float [S,P,2] pixels; inlier uint8 [S,P]; frame_flags uint8 [S]
+ * (bit0 refine this frame, bit1 refine_focal_length, bit2 refine_extra_params); points double [P,3]
+ * (constant); poses [S,12] / intr [S,4] in/out.  Outputs: inlier_used uint8 [S,P] (the effective mask),
+ * summary_d double [S,4] = (initial_cost, final_cost, final_radius, effective inliers), summary_i int32
+ * [S,4] = (iterations, successful steps, termination VGG_BA_* / VGG_POSE_*, 0). */
+int vgg_pose_refinement(int S, int P, int camera_model, const float* uv, const uint8_t* inlier,
+                        const uint8_t* frame_flags, const double* points, double* poses, double* intr,
+                        const vgg_pose_options* opt, uint8_t* inlier_used, double* summary_d, int32_t* summary_i,
+                        void* stream);
+
+/* ------------------------------------------------------------------------------------------- */
 /* Triangulation side (float64, like the reference's real pipeline: models/triangulator.py:91) */
 /* ------------------------------------------------------------------------------------------- */
 
@@ -204,6 +240,12 @@ int vgg_corr_build_pyramid(int BS, int C, int H, int W, int num_levels, const fl
  * pixels, out float [BS,N,num_levels*(2r+1)^2] with out[a*(2r+1)+b] sampled at (x+a-r, y+b-r). */
 int vgg_corr_sample(int BS, int N, int C, int H, int W, int num_levels, int radius, const void* pyramid, int elem_size,
                     const float* targets, const float* coords, int border_padding, float* out, void* stream);
+
+/* sample_features4d (vggsfm/models/utils.py:415-447; colour read-back at models/triangulator.py:324, query
+ * features in the tracker): bilinear sampling, align_corners=True, border padding.  input float [B,C,H,W],
+ * coords float [B,R,2] (x,y) pixels, out float [B,R,C]. */
+int vgg_sample_features4d(int B, int C, int H, int W, int R, const float* input_nchw, const float* coords, float* out,
+                          void* stream);
 
 #ifdef __cplusplus
 }

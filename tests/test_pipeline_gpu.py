@@ -66,3 +66,58 @@ def test_triangulate_then_ba(cuda_dev, cam, shared):
     # focal close to the ground truth 1000 px
     assert abs(K2[:, 0, 0].mean().item() - 1000.0) < 10.0
     assert rec2 is not None and ba.get_valid_frame_mask(K2, E2, ex2, 1024).all()
+
+
+class _Cameras:
+    """The three attributes get_EFP reads from the camera predictor's output (models/utils.py:46-55)."""
+
+    def __init__(self, focal_ndc, R, T):
+        self.focal_length, self.R, self.T = focal_ndc, R, T
+
+
+@pytest.mark.parametrize("cam,shared", [("SIMPLE_PINHOLE", False), ("SIMPLE_RADIAL", True)])
+def test_triangulator_forward(cuda_dev, cam, shared):
+    """Triangulator.forward (models/triangulator.py:44-363) end to end on the CUDA path: same arguments, same
+    9-tuple; checked by size-independent properties (reprojection RMS at the noise floor, camera centres equal to
+    the ground truth up to a similarity)."""
+    import torch
+    from vggsfm_b200 import triangulation as tri
+    from vggsfm_b200.synthetic import make_scene, perturb
+    from vggsfm_b200.triangulator import Triangulator
+    S, N = 12, 1024
+    sc = make_scene(S, N, cam, seed=11, invisible_frac=0.1, outlier_frac=0.02, k=0.03)
+    extr0, K0, _, _ = perturb(sc, rot_deg=0.4, trans_frac=0.01, focal_frac=0.02, seed=12)
+    dev = cuda_dev
+    W = H = 1024
+    cams = _Cameras(to_dev(np.stack([K0[:, 0, 0], K0[:, 1, 1]], -1) * 2.0 / min(W, H), dev, torch.float32),
+                    to_dev(extr0[:, :, :3], dev, torch.float32), to_dev(extr0[:, :, 3], dev, torch.float32))
+    tracks = to_dev(sc.tracks, dev)[None]
+    vis = to_dev(sc.vis, dev)[None]
+    score = to_dev(sc.score, dev)[None]
+    images = torch.rand(1, S, 3, H, W, device=dev)
+    prelim = {"fmat_inlier_mask": torch.ones(1, S - 1, N, dtype=torch.bool, device=dev)}
+    torch.manual_seed(0)
+    out = Triangulator()(cams, tracks, vis, images, prelim, pred_score=score, BA_iters=2, shared_camera=shared,
+                         robust_refine=2, camera_type=cam)
+    E, K, ex, pts, rgb, rec, vframe, v2d, vtracks = out
+    P = int(vtracks.sum())
+    assert E.shape == (S, 3, 4) and E.dtype == torch.float64 and K.shape == (S, 3, 3)
+    assert pts.shape == (P, 3) and rgb.shape == (P, 3) and v2d.shape == (S, N) and vframe.shape == (S,)
+    assert (ex is None) == (cam == "SIMPLE_PINHOLE")
+    assert P > 0.85 * N and bool(vframe.all())
+    assert not bool(v2d[:, ~vtracks].any())
+    assert bool(((rgb >= 0) & (rgb <= 1)).all())
+    uvh = tri.project_3D_points(pts, E, K, ex)
+    err = ((uvh - tracks[0][:, vtracks].double()) ** 2).sum(-1)
+    rms = torch.sqrt(err[v2d[:, vtracks]].mean()).item()
+    assert rms < 0.6, rms
+    # camera centres vs ground truth up to a similarity
+    En = E.cpu().numpy()
+    C_est = -np.einsum("sji,sj->si", En[:, :, :3], En[:, :, 3])
+    C_gt = -np.einsum("sji,sj->si", sc.extrinsics[:, :, :3], sc.extrinsics[:, :, 3])
+    s, R, t = _umeyama(C_est, C_gt)
+    resid = np.linalg.norm((s * (R @ C_est.T).T + t) - C_gt, axis=1).max()
+    assert resid < 0.02, resid
+    if shared:
+        assert torch.all(K[:, 0, 0] == K[0, 0, 0])
+        assert abs(K[0, 0, 0].item() - 1000.0) < 5.0

@@ -17,9 +17,10 @@ EXPORTS = [
     "vgg_ba_default_options", "vgg_ba_dims", "vgg_ba_workspace_bytes", "vgg_ba_camrec_len",
     "vgg_ba_build_blocks", "vgg_ba_schur", "vgg_cholesky_lower", "vgg_ba_solve",
     "vgg_ba_reduced_system_doubles", "vgg_ba_solve_fabric",
+    "vgg_pose_default_options", "vgg_pose_refinement",
     "vgg_tri_workspace_bytes", "vgg_triangulate_tracks", "vgg_triangulate_by_pair", "vgg_filter_points3d",
     "vgg_project_points", "vgg_normalize_tracks", "vgg_undistort_simple_radial",
-    "vgg_corr_pyramid_bytes", "vgg_corr_build_pyramid", "vgg_corr_sample",
+    "vgg_corr_pyramid_bytes", "vgg_corr_build_pyramid", "vgg_corr_sample", "vgg_sample_features4d",
 ]
 
 
@@ -65,6 +66,26 @@ class BAFabric(ctypes.Structure):
     _fields_ = [("ar_local", ctypes.c_void_p), ("ar_multicast", ctypes.c_void_p), ("ar_doubles", ctypes.c_size_t)]
 
 
+class PoseOptions(ctypes.Structure):
+    _fields_ = [
+        ("max_num_iterations", ctypes.c_int32),
+        ("max_num_consecutive_invalid_steps", ctypes.c_int32),
+        ("min_inliers", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+        ("function_tolerance", ctypes.c_double),
+        ("gradient_tolerance", ctypes.c_double),
+        ("parameter_tolerance", ctypes.c_double),
+        ("initial_trust_region_radius", ctypes.c_double),
+        ("max_trust_region_radius", ctypes.c_double),
+        ("min_trust_region_radius", ctypes.c_double),
+        ("min_relative_decrease", ctypes.c_double),
+        ("min_lm_diagonal", ctypes.c_double),
+        ("max_lm_diagonal", ctypes.c_double),
+        ("loss_function_scale", ctypes.c_double),
+        ("max_reproj_error", ctypes.c_double),
+    ]
+
+
 ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t,
                                 ctypes.c_int, ctypes.c_void_p)
 
@@ -104,6 +125,9 @@ def lib() -> ctypes.CDLL:
     L.vgg_ba_reduced_system_doubles.argtypes = [ci, ci, ci, ctypes.POINTER(cs)]
     L.vgg_ba_solve_fabric.argtypes = [ctypes.POINTER(BAProblem), ctypes.POINTER(BAOptions), vp, cs, ALLREDUCE_FN, vp,
                                       ctypes.POINTER(BAFabric), ctypes.POINTER(BASummary), vp, vp]
+    L.vgg_pose_default_options.argtypes = [ctypes.POINTER(PoseOptions)]
+    L.vgg_pose_default_options.restype = None
+    L.vgg_pose_refinement.argtypes = [ci, ci, ci, vp, vp, vp, vp, vp, vp, ctypes.POINTER(PoseOptions), vp, vp, vp, vp]
     L.vgg_cholesky_lower.argtypes = [ci, ci, vp, vp, cs, ctypes.POINTER(ci), vp]
     L.vgg_tri_workspace_bytes.argtypes = [ci, ci, ci, ci, ctypes.POINTER(cs)]
     L.vgg_triangulate_tracks.argtypes = [ci, ci, vp, vp, vp, vp, vp, ci, ci, cd, cd, vp, vp, vp, vp, cs, vp]
@@ -114,6 +138,7 @@ def lib() -> ctypes.CDLL:
     L.vgg_undistort_simple_radial.argtypes = [ci, ci, vp, vp, ci, cd, cd, vp, ctypes.POINTER(ci), vp, cs, vp]
     L.vgg_corr_pyramid_bytes.argtypes = [ci, ci, ci, ci, ci, ci, ctypes.POINTER(cs), ctypes.POINTER(cs)]
     L.vgg_corr_build_pyramid.argtypes = [ci, ci, ci, ci, ci, vp, ci, vp, vp, vp]
+    L.vgg_sample_features4d.argtypes = [ci, ci, ci, ci, ci, vp, vp, vp, vp]
     L.vgg_corr_sample.argtypes = [ci, ci, ci, ci, ci, ci, ci, vp, ci, vp, vp, ci, vp, vp]
     _lib = L
     return L

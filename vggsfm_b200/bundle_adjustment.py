@@ -262,7 +262,7 @@ def pad_tracks(n: int, multiple: int = 16) -> int:
 def bundle_adjustment(points3d, extrinsics, intrinsics, extra_params, tracks, masks, shared_camera=False,
                       camera_type="SIMPLE_PINHOLE", options: Optional[BAOptions] = None, max_points3D_val=3000.0,
                       allreduce=None, want_trace=False, refine_focal_length=True, refine_extra_params=True,
-                      const_pose=None, const_points=None, gauge=True, do_normalize=True):
+                      const_pose=None, const_points=None, gauge=True, do_normalize=True, filter_reconstruction=True):
     """Tensor-in / tensor-out equivalent of batch_matrix_to_pycolmap + pycolmap.bundle_adjustment +
     filter_reconstruction + pycolmap_to_batch_matrix (triangulation.py:1033-1063).
 
@@ -314,7 +314,8 @@ def bundle_adjustment(points3d, extrinsics, intrinsics, extra_params, tracks, ma
     pts = X[:P]
     if do_normalize:
         poses, pts = normalize(poses, pts, 10.0, 0.1, 0.9, alive)   # BundleAdjustmentController::Run
-        poses, pts = normalize(poses, pts, 5.0, 0.1, 0.9, alive)    # filter_reconstruction (triangulation.py:1217)
+        if filter_reconstruction:
+            poses, pts = normalize(poses, pts, 5.0, 0.1, 0.9, alive)    # filter_reconstruction (triangulation.py:1217)
     pts = torch.where(alive[:, None], pts, torch.zeros_like(pts))
     K = torch.zeros(S, 3, 3, dtype=torch.float64, device=dev)
     K[:, 0, 0] = intr[:, 0]
@@ -377,6 +378,41 @@ def global_BA(triangulated_points, valid_tracks, pred_tracks, inlier_mask, extri
     rec = Reconstruction(pts, extr, K, extra, BA_tracks[:, valid_idx], BA_inlier_masks[:, valid_idx], image_size,
                          camera_type, shared_camera, summary)
     return pts, extr, K, extra, rec
+
+
+def init_BA(extrinsics, intrinsics, extra_params, tracks, points_3d_pair, inlier, image_size, shared_camera=False,
+            init_max_reproj_error=0.5, camera_type="SIMPLE_PINHOLE"):
+    """vggsfm/utils/triangulation.py:138-257 with the same arguments and return tuple
+    (points3D_opt, extrinsics, intrinsics, extra_params, filtered_valid_track_mask, reconstruction, init_idx):
+    two-frame BA of the query frame and the frame with the most triangulation inliers, then the reprojection
+    filter at ``init_max_reproj_error``.  Like the reference it writes the optimised pair back INTO the
+    extrinsics / intrinsics / extra_params it was given (:243-246) and does not call filter_reconstruction."""
+    from . import triangulation as tri
+    init_idx = int(torch.argmax(inlier.sum(dim=-1)).item())
+    init_indices = [0, init_idx + 1]
+    toBA_extrinsics = extrinsics[init_indices]
+    toBA_intrinsics = intrinsics[init_indices]
+    toBA_extra = extra_params[init_indices] if extra_params is not None else None
+    toBA_masks = inlier[init_idx].unsqueeze(0)
+    toBA_masks = torch.cat([torch.ones_like(toBA_masks), toBA_masks], dim=0)
+    valid_track = toBA_masks.sum(dim=0) >= 2
+    toBA_masks = toBA_masks[:, valid_track]
+    toBA_points = points_3d_pair[init_idx][valid_track]
+    toBA_tracks = tracks[init_indices][:, valid_track]
+    pts, extr, K, extra, valid_idx, summary = bundle_adjustment(
+        toBA_points, toBA_extrinsics, toBA_intrinsics, toBA_extra, toBA_tracks, toBA_masks, shared_camera=shared_camera,
+        camera_type=camera_type, options=prepare_ba_options(), filter_reconstruction=False)
+    rec = Reconstruction(pts, extr, K, extra, toBA_tracks, toBA_masks, image_size, camera_type, shared_camera, summary)
+    ok, _ = tri.filter_all_points3D(pts, toBA_tracks, extr, K, extra, check_triangle=False,
+                                    max_reproj_error=init_max_reproj_error)
+    points3D_opt = pts[ok]
+    filtered = valid_track.clone()
+    filtered[valid_track] = ok
+    extrinsics[init_indices] = extr.to(extrinsics.dtype)
+    intrinsics[init_indices] = K.to(intrinsics.dtype)
+    if extra_params is not None:
+        extra_params[init_indices] = extra.to(extra_params.dtype)
+    return points3D_opt, extrinsics, intrinsics, extra_params, filtered, rec, init_idx
 
 
 def get_valid_frame_mask(intrinsics, extrinsics, extra_params, scale):

@@ -94,3 +94,18 @@ class EfficientCorrBlock:
 
     def sample(self, coords, target):
         return self._pyr.sample(coords, target, True)
+
+
+def sample_features4d(input, coords):
+    """vggsfm/models/utils.py:415-447: input [B,C,H,W], coords [B,R,2] (x,y) -> [B,R,C]; bilinear,
+    align_corners=True, border padding (``vgg_sample_features4d``)."""
+    if not input.is_cuda:
+        raise RuntimeError("vggsfm_b200.sample_features4d needs CUDA tensors (no CPU fallback)")
+    B, C, H, W = input.shape
+    R = coords.shape[1]
+    inp = input.float().contiguous()
+    crd = coords.float().contiguous()
+    out = torch.empty(B, R, C, dtype=torch.float32, device=input.device)
+    _lib.check(_lib.lib().vgg_sample_features4d(B, C, H, W, R, inp.data_ptr(), crd.data_ptr(), out.data_ptr(),
+                                                _stream(input.device)))
+    return out.to(input.dtype)

@@ -212,6 +212,37 @@ static int launch_corr(int BS, int N, int C, int L, int R, const CorrLevels& lv,
   return VGG_EINVAL;
 }
 
+
+// sample_features4d (vggsfm/models/utils.py:415-447): bilinear point sampling of an NCHW map with
+// align_corners=True and border padding.  One warp per point, lanes stride the channels; the four taps of a
+// channel are 4-byte gathers from one plane (NCHW is what the reference hands over; C is 3 for the colour
+// read-back at models/triangulator.py:324 and 128 for the tracker's query features).
+__global__ void sample_features_kernel(int B, int C, int H, int W, int R, const float* __restrict__ in,
+                                       const float* __restrict__ coords, float* __restrict__ out) {
+  const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (gw >= B * R) return;
+  const int b = gw / R;
+  float x = coords[(size_t)gw * 2], y = coords[(size_t)gw * 2 + 1];
+  // grid_sample's unnormalise(normalise(x)) round trip, then the border clamp
+  const float sx = 2.0f / (float)max(W - 1, 1), sy = 2.0f / (float)max(H - 1, 1);
+  x = ((x * sx - 1.0f) + 1.0f) * 0.5f * (float)(W - 1);
+  y = ((y * sy - 1.0f) + 1.0f) * 0.5f * (float)(H - 1);
+  x = fminf(fmaxf(x, 0.0f), (float)(W - 1));
+  y = fminf(fmaxf(y, 0.0f), (float)(H - 1));
+  const float fx = floorf(x), fy = floorf(y);
+  const int x0 = (int)fx, y0 = (int)fy;
+  const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+  const float ax = x - fx, ay = y - fy;
+  const float w00 = (1.0f - ax) * (1.0f - ay), w01 = ax * (1.0f - ay), w10 = (1.0f - ax) * ay, w11 = ax * ay;
+  const float* base = in + (size_t)b * C * H * W;
+  for (int c = lane; c < C; c += 32) {
+    const float* pl = base + (size_t)c * H * W;
+    const float v = pl[(size_t)y0 * W + x0] * w00 + pl[(size_t)y0 * W + x1] * w01 + pl[(size_t)y1 * W + x0] * w10 +
+                    pl[(size_t)y1 * W + x1] * w11;
+    out[(size_t)gw * C + c] = v;
+  }
+}
+
 }  // namespace vgg
 
 using namespace vgg;
@@ -286,6 +317,19 @@ int vgg_corr_sample(int BS, int N, int C, int H, int W, int num_levels, int radi
   }
   if (elem_size == 4) return launch_corr<float>(BS, N, C, num_levels, radius, lv, targets, coords, border_padding, out, st);
   return launch_corr<__half>(BS, N, C, num_levels, radius, lv, targets, coords, border_padding, out, st);
+}
+
+int vgg_sample_features4d(int B, int C, int H, int W, int R, const float* input_nchw, const float* coords, float* out,
+                          void* stream) {
+  VGG_REQUIRE(B >= 0 && C > 0 && H > 0 && W > 0 && R >= 0, "bad shape");
+  g_launch_count = 0;
+  if (B * R == 0) return VGG_OK;
+  VGG_REQUIRE(input_nchw && coords && out, "null pointer");
+  const long long warps = (long long)B * R;
+  sample_features_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(B, C, H, W, R, input_nchw,
+                                                                                              coords, out);
+  VGG_LAUNCH_CHECK();
+  return VGG_OK;
 }
 
 }  // extern "C"
