@@ -95,7 +95,11 @@ def test_triangulator_forward(cuda_dev, cam, shared):
     vis = to_dev(sc.vis, dev)[None]
     score = to_dev(sc.score, dev)[None]
     images = torch.rand(1, S, 3, H, W, device=dev)
-    prelim = {"fmat_inlier_mask": torch.ones(1, S - 1, N, dtype=torch.bool, device=dev)}
+    # the two-view stage upstream hands over epipolar inliers: here, pairs whose two observations are not outliers
+    from vggsfm_b200.synthetic import project_np
+    uv_gt, _ = project_np(sc.extrinsics, 1000.0, np.array([512.0, 512.0]), 0.03 if cam == "SIMPLE_RADIAL" else 0.0, sc.points3d)
+    ok = np.linalg.norm(sc.tracks - uv_gt, axis=-1) < 3.0
+    prelim = {"fmat_inlier_mask": to_dev(ok[:1] & ok[1:], dev)[None]}
     torch.manual_seed(0)
     out = Triangulator()(cams, tracks, vis, images, prelim, pred_score=score, BA_iters=2, shared_camera=shared,
                          robust_refine=2, camera_type=cam)

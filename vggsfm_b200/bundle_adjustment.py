@@ -262,7 +262,8 @@ def pad_tracks(n: int, multiple: int = 16) -> int:
 def bundle_adjustment(points3d, extrinsics, intrinsics, extra_params, tracks, masks, shared_camera=False,
                       camera_type="SIMPLE_PINHOLE", options: Optional[BAOptions] = None, max_points3D_val=3000.0,
                       allreduce=None, want_trace=False, refine_focal_length=True, refine_extra_params=True,
-                      const_pose=None, const_points=None, gauge=True, do_normalize=True, filter_reconstruction=True):
+                      const_pose=None, const_points=None, gauge=True, do_normalize=True, filter_reconstruction=True,
+                      drop_negative_depth=True):
     """Tensor-in / tensor-out equivalent of batch_matrix_to_pycolmap + pycolmap.bundle_adjustment +
     filter_reconstruction + pycolmap_to_batch_matrix (triangulation.py:1033-1063).
 
@@ -294,7 +295,10 @@ def bundle_adjustment(points3d, extrinsics, intrinsics, extra_params, tracks, ma
         mode = INTR_PER_FRAME
     if not (refine_focal_length or refine_extra_params):
         mode = INTR_CONST
-    m, alive = filter_negative_depth(poses, pts, m)
+    if drop_negative_depth:                                    # BundleAdjustmentController::Run only
+        m, alive = filter_negative_depth(poses, pts, m)
+    else:
+        alive = torch.ones(P, dtype=torch.bool, device=dev)
     point_const = ~m.any(dim=0)
     if const_points is not None:
         point_const = point_const | const_points[valid_idx]

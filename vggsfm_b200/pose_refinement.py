@@ -66,10 +66,11 @@ def pose_refinement_batched(poses, intr4, points3D, tracks2D, inlier, frame_flag
     sd = torch.zeros(S, 4, dtype=torch.float64, device=dev)
     si = torch.zeros(S, 4, dtype=torch.int32, device=dev)
     opt = options or default_pose_options()
-    stream = torch.cuda.current_stream(dev).cuda_stream
-    _lib.check(L.vgg_pose_refinement(S, P, model, uv.data_ptr(), inl.data_ptr(), flags.data_ptr(), pts.data_ptr(),
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(L.vgg_pose_refinement(S, P, model, uv.data_ptr(), inl.data_ptr(), flags.data_ptr(), pts.data_ptr(),
                                      poses.data_ptr(), intr4.data_ptr(), ctypes.byref(opt), used.data_ptr(),
-                                     sd.data_ptr(), si.data_ptr(), stream))
+                                     sd.data_ptr(), si.data_ptr(), stream), "vgg_pose_refinement")
     return PoseReport(si[:, 0], si[:, 1], si[:, 2], sd[:, 0], sd[:, 1], sd[:, 3].round().long(), used.bool(),
                       kernel_launches=1 if S > 0 else 0)
 

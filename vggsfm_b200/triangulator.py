@@ -74,6 +74,12 @@ class Triangulator(torch.nn.Module):
     def __init__(self, cfg=None):
         super().__init__()
         self.cfg = cfg
+        self.verbose = False
+
+    def _log(self, stage, extrinsics, intrinsics, extra_params, extra=""):
+        if self.verbose:
+            k = "" if extra_params is None else f" k[0]={float(extra_params[0, 0]):.5f}"
+            print(f"[Triangulator] {stage}: f[0]={float(intrinsics[0, 0, 0]):.3f} f[-1]={float(intrinsics[-1, 0, 0]):.3f}{k} {extra}")
 
     @torch.no_grad()
     def forward(self, pred_cameras, pred_tracks, pred_vis, images, preliminary_dict, pred_score=None,
@@ -109,21 +115,32 @@ class Triangulator(torch.nn.Module):
         points3D_init, extrinsics, intrinsics, extra_params, track_init_mask, reconstruction, init_idx = ba.init_BA(
             extrinsics, intrinsics, extra_params, pred_tracks, points_3d_pair, inlier_total, image_size,
             shared_camera=shared_camera, init_max_reproj_error=init_max_reproj_error, camera_type=camera_type)
+        self._log("init_BA", extrinsics, intrinsics, extra_params,
+                  f"init_idx={init_idx} inliers={int(inlier_total[init_idx].sum())} kept={int(track_init_mask.sum())} "
+                  f"its={reconstruction.summary.iterations} {reconstruction.summary.termination}")
         extrinsics, intrinsics, extra_params, _ = pr.init_refine_pose(
             extrinsics, intrinsics, extra_params, inlier_geo_vis, points3D_init, pred_tracks, track_init_mask, image_size,
             init_idx, shared_camera=shared_camera, camera_type=camera_type)
+        self._log("init_refine_pose", extrinsics, intrinsics, extra_params,
+                  f"term={pr.last_report.termination.tolist()} its={pr.last_report.iterations.tolist()}")
         points3D, extrinsics, intrinsics, extra_params, valid_tracks, reconstruction = self.triangulate_tracks_and_BA(
             pred_tracks, intrinsics, extrinsics, extra_params, pred_vis, pred_score, image_size, min_valid_track_length,
             max_reproj_error, shared_camera=shared_camera, camera_type=camera_type)
+        self._log("triangulate_tracks_and_BA", extrinsics, intrinsics, extra_params,
+                  f"valid={int(valid_tracks.sum())} its={reconstruction.summary.iterations} {reconstruction.summary.termination}")
 
         for refine_idx in range(robust_refine):
             inlier_vis_all = pred_vis > 0.05
             extrinsics, intrinsics, extra_params, _ = pr.refine_pose(
                 extrinsics, intrinsics, extra_params, inlier_vis_all, points3D, pred_tracks, valid_tracks, image_size,
                 force_estimate=(refine_idx == robust_refine - 1), shared_camera=shared_camera, camera_type=camera_type)
+            self._log(f"refine_pose {refine_idx}", extrinsics, intrinsics, extra_params,
+                      f"term={pr.last_report.termination.tolist()} inl={pr.last_report.num_inliers.tolist()}")
             points3D, extrinsics, intrinsics, extra_params, valid_tracks, reconstruction = self.triangulate_tracks_and_BA(
                 pred_tracks, intrinsics, extrinsics, extra_params, pred_vis, pred_score, image_size,
                 min_valid_track_length, max_reproj_error, shared_camera=shared_camera, camera_type=camera_type)
+            self._log(f"robust refine {refine_idx}", extrinsics, intrinsics, extra_params,
+                      f"valid={int(valid_tracks.sum())} its={reconstruction.summary.iterations} {reconstruction.summary.termination}")
 
         ba_options = ba.default_options()                       # pycolmap.BundleAdjustmentOptions(), :254
         BA_inlier_masks = None
@@ -134,6 +151,7 @@ class Triangulator(torch.nn.Module):
                 lastBA=(BA_iter == BA_iters - 1), extra_params=extra_params, shared_camera=shared_camera,
                 min_valid_track_length=min_valid_track_length, max_reproj_error=max_reproj_error, ba_options=ba_options,
                 camera_type=camera_type)
+            self._log(f"iterative BA {BA_iter}", extrinsics, intrinsics, extra_params, f"valid={int(valid_tracks.sum())}")
             max_reproj_error = max(max_reproj_error // 2, 1)     # :293-295
 
         scale = image_size.max()

@@ -1,0 +1,77 @@
+"""Sliding-window pieces of the video pipeline that sit on the geometry hot path, on device tensors.
+
+Tensor-level mirrors of the bundle-adjustment / pose-alignment blocks of ``VideoRunner``
+(vggsfm/runners/video_runner.py); the runner's dict bookkeeping (point_dict / frame_dict,
+dicts_to_reconstruction, reconstruction_to_dicts) is what these calls replace, so they take and return the
+dense [S,P] tensors the runner already holds at those points.  Everything numeric goes through
+libvggsfm_b200.so; there is no fallback.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import bundle_adjustment as ba
+from . import pose_refinement as pr
+from . import triangulation as tri
+
+
+def filter_points_and_compute_masks(points, tracks, extrinsics, intrinsics, extra_params, min_valid_track_length=3,
+                                    max_reproj_error=4):
+    """video_runner.py:907-939.  intrinsics [1,3,3] / extra_params [1,1] are the runner's shared camera.
+    Returns (filtered_points, filtered_tracks, filtered_inlier_masks, valid_tracks_mask)."""
+    S = extrinsics.shape[0]
+    _, inlier_mask = tri.filter_all_points3D(points, tracks, extrinsics, intrinsics.expand(S, -1, -1),
+                                             extra_params=extra_params.expand(S, -1) if extra_params is not None else None,
+                                             max_reproj_error=max_reproj_error, return_detail=True, hard_max=-1)
+    valid = inlier_mask.sum(dim=0) >= min_valid_track_length
+    return points[valid], tracks[:, valid], inlier_mask[:, valid], valid
+
+
+def align_next_window(extrinsics, tracks, inlier, points3D, intrinsics, extra_params=None, camera_type="SIMPLE_PINHOLE",
+                      min_vis_num=50):
+    """video_runner.py:941-1017 (use_pnp=False): every frame but the first is refined against the carried 3D
+    points with the shared camera held constant; a frame with <= min_vis_num inliers uses all points.
+    Returns refined_extrinsics [S,3,4] f64."""
+    model = ba.camera_model_id(camera_type)
+    S = extrinsics.shape[0]
+    dev = extrinsics.device
+    inl = inlier.bool().clone()
+    few = inl.sum(dim=1) <= min_vis_num
+    inl[few] = True                                                      # :973-977
+    poses = extrinsics.double().contiguous().clone()
+    K = intrinsics.expand(S, -1, -1)
+    ex = extra_params.expand(S, -1) if extra_params is not None else None
+    intr4 = pr._intr4(K, ex, model)
+    flags = torch.full((S,), pr.FLAG_ACTIVE, dtype=torch.uint8, device=dev)
+    flags[0] = 0
+    pr.last_report = pr.pose_refinement_batched(poses, intr4, points3D, tracks, inl, flags, model, pr.default_pose_options())
+    return poses
+
+
+def window_bundle_adjustment(window_points_all, extrinsics, intrinsics, extra_params, window_tracks_all,
+                             window_inlier_masks_all, exist_points_3D_num, shared_camera=True,
+                             camera_type="SIMPLE_PINHOLE"):
+    """The BA block of VideoRunner.move_window (video_runner.py:800-853) + solve_bundle_adjustment (:1321-1331):
+    window_size+1 frames, frame 0 (the last frame of the previous window) fixed, the first
+    ``exist_points_3D_num`` points (carried over) constant, the rest variable, intrinsics constant, default
+    Ceres options, no Normalize (the runner drives pycolmap.BundleAdjuster directly, not the controller).
+
+    Returns (window_points3D_opt [P,3], extrinsics [S,3,4], summary, ba_success) where ba_success is the
+    runner's ``num_residuals_reduced > 0`` test."""
+    S, P = window_inlier_masks_all.shape
+    dev = window_tracks_all.device
+    K = intrinsics.expand(S, -1, -1)
+    ex = extra_params.expand(S, -1) if extra_params is not None else None
+    const_pose = torch.zeros(S, dtype=torch.bool, device=dev)
+    const_pose[0] = True                                                 # :817-818
+    const_points = torch.arange(P, device=dev) < exist_points_3D_num     # :820-825
+    pts, extr, _, _, valid_idx, summary = ba.bundle_adjustment(
+        window_points_all, extrinsics, K, ex, window_tracks_all, window_inlier_masks_all, shared_camera=shared_camera,
+        camera_type=camera_type, options=ba.default_options(), refine_focal_length=False, refine_extra_params=False,
+        const_pose=const_pose, const_points=const_points, gauge=False, do_normalize=False, drop_negative_depth=False)
+    out = window_points_all.double().clone()
+    out[valid_idx] = pts
+    # residuals that touch at least one free parameter block: observations of free frames, or of free points
+    free_obs = window_inlier_masks_all.bool()[:, valid_idx]
+    reduced = int(free_obs[1:].sum()) + int((free_obs[:1] & ~const_points[valid_idx][None]).sum())
+    return out, extr, summary, reduced > 0
