@@ -78,7 +78,7 @@ def test_align_next_window_and_filter(cuda_dev):
         pe[s], _, _ = po.pose_refinement(extr0[s], intr[s], sc.points3d, sc.tracks[s].astype(np.float64), inl_o[s], 1, False, False)
     assert np.array_equal(got[0], extr0[0])
     assert np.allclose(got, pe, atol=1e-8), np.abs(got - pe).max()
-    assert np.abs(got[:, :, 3] - sc.extrinsics[:, :, 3]).max() < 0.03
+    assert np.abs(got[1:, :, 3] - sc.extrinsics[1:, :, 3]).max() < 0.01      # frame 0 is the (perturbed) anchor
     # filter_points_and_compute_masks: shapes and the >= 3 inlier rule
     pts, trk, msk, valid = video.filter_points_and_compute_masks(to_dev(sc.points3d, dev), to_dev(sc.tracks, dev),
                                                                  to_dev(got, dev), K1, ex1)

@@ -1,5 +1,5 @@
 """CUDA-event micro-benchmarks for A/B runs (env switches are read once per process):
-   python tools/microbench.py chol | ba | blocks [N]"""
+   python tools/microbench.py chol | ba | blocks [N] | pose [S N] | pipeline [S N]"""
 import ctypes
 import os
 import sys
@@ -29,6 +29,53 @@ def timeit(fn, reps=10, warm=3):
     torch.cuda.synchronize()
     return a.elapsed_time(b) / reps
 
+
+if mode in ("pose", "pipeline"):
+    from vggsfm_b200 import pose_refinement as pr
+    from vggsfm_b200.synthetic import project_np
+    from vggsfm_b200.triangulator import Triangulator
+    S = int(sys.argv[2]) if len(sys.argv) > 2 else 400
+    N = int(sys.argv[3]) if len(sys.argv) > 3 else 4096
+    cam, shared = "SIMPLE_RADIAL", True
+    sc = make_scene(S, N, cam, seed=3, invisible_frac=0.2, outlier_frac=0.02)
+    extr0, K0, ex0, _ = perturb(sc, rot_deg=0.4, trans_frac=0.01, focal_frac=0.02, seed=4)
+    T = lambda a, dt=None: torch.from_numpy(np.ascontiguousarray(a)).to(dev) if dt is None else torch.from_numpy(np.ascontiguousarray(a)).to(dev, dt)
+    if mode == "pose":
+        E, K, ex = T(extr0), T(K0), T(ex0)
+        X, tracks, inl = T(sc.points3d), T(sc.tracks), T(sc.mask)
+        valid = torch.ones(N, dtype=torch.bool, device=dev)
+        isz = torch.tensor([1024, 1024], device=dev)
+        for sh in (False, True):
+            ms = timeit(lambda: pr.refine_pose(E, K, ex, inl, X, tracks, valid, isz, shared_camera=sh, camera_type=cam), reps=5, warm=2)
+            its = pr.last_report.iterations.float()
+            print(f"[{tag}] refine_pose {S}x{N} shared={sh}: {ms:.3f} ms  ({S / ms * 1e3:.0f} frames/s; LM its mean {its.mean():.1f} max {int(its.max())})")
+        sys.exit(0)
+
+    class Cams:
+        pass
+    c = Cams()
+    c.focal_length = T(np.stack([K0[:, 0, 0], K0[:, 1, 1]], -1) * 2.0 / 1024, torch.float32)
+    c.R, c.T = T(extr0[:, :, :3], torch.float32), T(extr0[:, :, 3], torch.float32)
+    uv_gt, _ = project_np(sc.extrinsics, 1000.0, np.array([512.0, 512.0]), 0.05, sc.points3d)
+    ok = np.linalg.norm(sc.tracks - uv_gt, axis=-1) < 3.0
+    prelim = {"fmat_inlier_mask": T(ok[:1] & ok[1:])[None]}
+    images = torch.zeros(1, S, 3, 64, 64, device=dev)
+    tr = Triangulator()
+    tracks, vis, score = T(sc.tracks)[None], T(sc.vis)[None], T(sc.score)[None]
+    # images are only read for their shape and the colour lookup; use a 1024x1024 canvas without allocating it per call
+    images = torch.zeros(1, S, 3, 1024, 1024, device=dev) if S <= 64 else torch.zeros(1, 1, 3, 1024, 1024, device=dev).expand(1, S, 3, 1024, 1024)
+
+    def run():
+        torch.manual_seed(0)
+        return tr(c, tracks, vis, images, prelim, pred_score=score, BA_iters=2, shared_camera=shared, robust_refine=2,
+                  camera_type=cam, extract_color=S <= 64)
+    tr.verbose = True
+    out = run()
+    tr.verbose = False
+    ms = timeit(run, reps=3, warm=1)
+    print(f"[{tag}] Triangulator.forward {S}x{N} ({cam}, shared): {ms:.1f} ms  valid tracks {int(out[8].sum())} "
+          f"valid frames {int(out[6].sum())}")
+    sys.exit(0)
 
 if mode == "chol":
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 2402

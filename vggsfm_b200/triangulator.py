@@ -70,6 +70,12 @@ def find_best_initial_pair(inlier_geo_vis, cheirality_mask_pair, triangle_value_
     return inlier_total, init_tri_angle_thres
 
 
+def _hist(termination):
+    """{termination name: frames} of a pose report, for the stage log."""
+    v, c = torch.unique(termination, return_counts=True)
+    return {pr.TERMINATION.get(int(a), "?"): int(b) for a, b in zip(v, c)}
+
+
 class Triangulator(torch.nn.Module):
     def __init__(self, cfg=None):
         super().__init__()
@@ -122,7 +128,7 @@ class Triangulator(torch.nn.Module):
             extrinsics, intrinsics, extra_params, inlier_geo_vis, points3D_init, pred_tracks, track_init_mask, image_size,
             init_idx, shared_camera=shared_camera, camera_type=camera_type)
         self._log("init_refine_pose", extrinsics, intrinsics, extra_params,
-                  f"term={pr.last_report.termination.tolist()} its={pr.last_report.iterations.tolist()}")
+                  f"term={_hist(pr.last_report.termination)} its<={int(pr.last_report.iterations.max())}")
         points3D, extrinsics, intrinsics, extra_params, valid_tracks, reconstruction = self.triangulate_tracks_and_BA(
             pred_tracks, intrinsics, extrinsics, extra_params, pred_vis, pred_score, image_size, min_valid_track_length,
             max_reproj_error, shared_camera=shared_camera, camera_type=camera_type)
@@ -135,7 +141,7 @@ class Triangulator(torch.nn.Module):
                 extrinsics, intrinsics, extra_params, inlier_vis_all, points3D, pred_tracks, valid_tracks, image_size,
                 force_estimate=(refine_idx == robust_refine - 1), shared_camera=shared_camera, camera_type=camera_type)
             self._log(f"refine_pose {refine_idx}", extrinsics, intrinsics, extra_params,
-                      f"term={pr.last_report.termination.tolist()} inl={pr.last_report.num_inliers.tolist()}")
+                      f"term={_hist(pr.last_report.termination)} inliers>={int(pr.last_report.num_inliers.min())}")
             points3D, extrinsics, intrinsics, extra_params, valid_tracks, reconstruction = self.triangulate_tracks_and_BA(
                 pred_tracks, intrinsics, extrinsics, extra_params, pred_vis, pred_score, image_size,
                 min_valid_track_length, max_reproj_error, shared_camera=shared_camera, camera_type=camera_type)
