@@ -129,6 +129,14 @@ int vgg_ba_schur(const vgg_ba_problem* prob, const double* camrec, const double*
  * workspace >= ceil(n/64)*32768 + 256 bytes; *info_host = 0 or the 1-based index of the failing pivot. */
 int vgg_cholesky_lower(int n, int lda, double* A, void* workspace, size_t ws_bytes, int* info_host, void* stream);
 
+/* The same SYRK step on the tensor cores (csrc/syrk_i8.cu): Cmat[Dpad,Dpad] -= Zt^T Zt for Zt double [Kpad,Dpad]
+ * (Dpad a multiple of 128, Kpad <= 131072), FP64-equivalent through `slices` (3..7; 7 = 54 fractional bits) int8
+ * Ozaki slices on tcgen05.mma kind::i8 with exact int32 accumulation in TMEM.  Both triangles are written.
+ * Selected inside vgg_ba_solve by VGG_SYRK=ozaki[:slices]; exposed for the parity tests and profiling. */
+int vgg_syrk_ozaki_workspace_bytes(int Kpad, int Dpad, int slices, size_t* bytes);
+int vgg_syrk_ozaki(int Kpad, int Dpad, const double* Zt, double* Cmat, int slices, void* workspace, size_t ws_bytes,
+                   void* stream);
+
 /* Whole Levenberg-Marquardt solve (Ceres trust-region semantics).  `trace` is a HOST array
  * [max_num_iterations, 8] (it, cost, candidate_cost, model_change, rho, radius, step_norm, flags) or NULL. */
 int vgg_ba_solve(const vgg_ba_problem* prob, const vgg_ba_options* opt, void* workspace,

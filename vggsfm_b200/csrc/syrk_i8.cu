@@ -1,0 +1,466 @@
+// Schur SYRK on the 5th-generation tensor cores: Sraw -= Zt^T Zt in FP64-equivalent precision computed with
+// INT8 tcgen05.mma (Ozaki splitting), the step SURVEY section 0.6 / DESIGN section 4.2 name as the dominant cost
+// of a bundle-adjustment iteration (76.5 GFLOP at 400 x 4096; 2.46 ms on the FP64 pipe with DMMA).
+//
+// FP64 has no tcgen05 path on sm_100a, but INT8 does (kind::i8, 8192 MAC/clk/SM, exact int32 accumulation).
+//   1. every column d of Z (a reduced camera parameter) gets a power-of-two scale 2^e_d >= max_k |Z[k][d]|;
+//      x = Z 2^-e_d is rounded to B = 8s-2 fractional bits and written as s balanced base-256 digits
+//      (int8 "slices", most significant first): x = 2^-B sum_p d_p 256^(s-p)          (oz_slice_kernel)
+//   2. (Z^T Z)_ij = 2^(e_i+e_j-2B) sum_t 256^(2s-t) C_t,  C_t = sum_{p+q=t} sum_k d_p[k][i] d_q[k][j]:
+//      every C_t is an exact int32 (|d| <= 128, K <= 2^17: |C_t| < 2^31 for up to 7 pairs); orders t > s+1 are below
+//      the rounding of step 1 and are dropped, leaving s(s+1)/2 int8 GEMMs (28 for s = 7)  (oz_syrk_kernel)
+//   3. the epilogue recombines the C_t of a tile in FP64 registers and adds -value into Sraw with f64 RED
+//      (or multimem.red in fabric mode), exactly like the DMMA kernel's epilogue.
+//
+// oz_syrk_kernel is a persistent, warp-specialised tcgen05 kernel (one CTA per SM):
+//   warp 0   producer: the int8 slices are stored in HBM as 8 KB tile images that are already in the 64-byte
+//            swizzled K-major shared-memory layout UMMA wants, so a tile is ONE 1-D bulk copy (cp.async.bulk ->
+//            UBLKCP) completing on an mbarrier -- no tensor map, no driver API;
+//   warp 1   MMA issuer: one thread issues tcgen05.mma.cta_group::1.kind::i8 (M=128, N=128, K=32) for every
+//            (p,q) pair of the work item's order group into up to four 128-column TMEM accumulators (one per order
+//            t), tcgen05.commit releases the smem stage / publishes the accumulators;
+//   warps 2-9 epilogue: tcgen05.ld the accumulators, combine the orders in FP64 registers, release TMEM, then
+//            scale by 2^(e_i+e_j) and RED into both triangles while the next item's MMAs already run.
+// Work items (tile, order group, k range) are built on the host, longest first, and strided over the CTAs.
+#include "common.cuh"
+
+#include <algorithm>
+#include <vector>
+
+namespace vgg {
+
+namespace {
+
+constexpr int OZ_BM = 128;                       // tile rows (reduced camera parameters)
+constexpr int OZ_BK = 64;                        // k bytes per block = one 64-byte swizzle atom
+constexpr int OZ_TILE_BYTES = OZ_BM * OZ_BK;     // 8 KB
+constexpr int OZ_STAGES = 2;
+constexpr int OZ_STAGE_TILES = 14;
+constexpr int OZ_STAGE_BYTES = OZ_STAGE_TILES * OZ_TILE_BYTES;   // 112 KB
+constexpr int OZ_THREADS = 320;                  // producer warp, MMA warp, 8 epilogue warps
+constexpr int OZ_MAX_PAIRS = 20;
+constexpr int OZ_MAX_GROUPS = 3;
+constexpr int OZ_EXPO_BAD = INT32_MIN;           // column holds a non-finite value
+constexpr size_t OZ_SMEM_BYTES = (size_t)OZ_STAGES * OZ_STAGE_BYTES + 1024 + 128;
+
+struct OzGroup {
+  int n_a, n_b, n_pairs, n_acc;
+  int exp_base;                                  // 8 (2s - tmax) - 2B
+  uint8_t a_slice[8], b_slice[8];                // slice held by tile slot i / n_a + i
+  uint8_t pair_a[OZ_MAX_PAIRS], pair_b[OZ_MAX_PAIRS], pair_acc[OZ_MAX_PAIRS];
+  uint8_t acc_shift[4];                          // 8 (tmax - t) of accumulator a
+};
+struct OzPlan {
+  int slices, n_groups;
+  OzGroup g[OZ_MAX_GROUPS];
+};
+struct OzWork {
+  int bi, bj, group, kb0, kb1;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// 1. column scales
+__global__ void oz_rowmax_kernel(int Kpad, int Dpad, int k_per, const double* __restrict__ Zt,
+                                 unsigned long long* __restrict__ amax) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= Dpad) return;
+  const int k0 = blockIdx.y * k_per, k1 = min(Kpad, k0 + k_per);
+  double m = 0.0;
+  bool bad = false;
+  for (int k = k0; k < k1; ++k) {
+    const double a = fabs(Zt[(size_t)k * Dpad + d]);
+    bad |= !(a <= 1.7976931348623157e308);
+    m = fmax(m, a);
+  }
+  if (bad) m = __longlong_as_double(0x7ff0000000000000LL);
+  if (m > 0.0) atomicMax(&amax[d], (unsigned long long)__double_as_longlong(m));
+}
+
+// 2. slices, written as pre-swizzled 8 KB tile images: tile (slice p, row block rb, k block kb) holds rows
+//    d = rb*128 + r, bytes k = kb*64 + kk at offset r*64 + (((kk >> 4) ^ ((r >> 1) & 3)) << 4) + (kk & 15)
+//    (the 64-byte swizzle, Swizzle<2,4,3>, of a K-major 128 x 64 B tile whose base is 1024-byte aligned).
+__global__ void __launch_bounds__(512) oz_slice_kernel(int Kpad, int Dpad, int KB, int s,
+                                                       const double* __restrict__ Zt,
+                                                       const unsigned long long* __restrict__ amax,
+                                                       int* __restrict__ expo, int8_t* __restrict__ slices,
+                                                       size_t slice_stride) {
+  const int rb = blockIdx.x, kb = blockIdx.y;
+  const int r = threadIdx.x & 127, c = threadIdx.x >> 7;
+  const int d = rb * OZ_BM + r;
+  const double m = __longlong_as_double((long long)amax[d]);
+  int e = 0;
+  bool bad = false;
+  if (m > 0.0) {
+    if (m <= 1.7976931348623157e308) e = ilogb(m) + 1;
+    else bad = true;
+  }
+  if (kb == 0 && c == 0) expo[d] = bad ? OZ_EXPO_BAD : e;
+  const int B = 8 * s - 2;
+  uint32_t dig[7][4];
+#pragma unroll
+  for (int p = 0; p < 7; ++p) dig[p][0] = dig[p][1] = dig[p][2] = dig[p][3] = 0u;
+  const int kbase = kb * OZ_BK + c * 16;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int k = kbase + i;
+    double z = (k < Kpad && !bad) ? Zt[(size_t)k * Dpad + d] : 0.0;
+    long long X = llrint(ldexp(z, B - e));
+#pragma unroll
+    for (int p = 6; p >= 0; --p) {
+      if (p < s) {
+        const int dg = (int)((X + 128) & 255) - 128;
+        X = (X - dg) >> 8;
+        dig[p][i >> 2] |= (uint32_t)(dg & 255) << (8 * (i & 3));
+      }
+    }
+  }
+  const size_t off = ((size_t)rb * KB + kb) * OZ_TILE_BYTES + (size_t)r * OZ_BK + (size_t)((c ^ ((r >> 1) & 3)) << 4);
+#pragma unroll
+  for (int p = 0; p < 7; ++p)
+    if (p < s) *reinterpret_cast<uint4*>(slices + (size_t)p * slice_stride + off) = make_uint4(dig[p][0], dig[p][1], dig[p][2], dig[p][3]);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// tcgen05 / TMEM helpers (PTX ISA 8.6+, sm_100a)
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, int8 x int8 -> int32, M = 128, N = 128, K = 32
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// shared-memory matrix descriptor: K-major, 64-byte swizzle, 8-row atoms 512 B apart, sm_100 descriptor version
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+// instruction descriptor: D = s32, A = B = signed int8, both K-major, N = 128, M = 128
+constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+// ---------------------------------------------------------------------------------------------------------
+// 3. persistent tcgen05 SYRK
+__global__ void __launch_bounds__(OZ_THREADS, 1)
+    oz_syrk_kernel(const __grid_constant__ OzPlan plan, const OzWork* __restrict__ work, int nwork, int KB,
+                   const int8_t* __restrict__ slices, size_t slice_stride, const int* __restrict__ expo, int Dpad,
+                   double* __restrict__ Cmat, ptrdiff_t mc_off) {
+  extern __shared__ __align__(1024) uint8_t oz_smem[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(oz_smem), 1024));
+  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (size_t)OZ_STAGES * OZ_STAGE_BYTES);
+  uint64_t* empty = full + OZ_STAGES;
+  uint64_t* tmem_full = empty + OZ_STAGES;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < OZ_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 8);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== producer =====
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+        const OzWork wk = work[w];
+        const OzGroup& g = plan.g[wk.group];
+        const bool diag = wk.bi == wk.bj;
+        for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* dst = tiles + (size_t)stage * OZ_STAGE_BYTES;
+          mbar_expect_tx(&full[stage], (uint32_t)(g.n_a + g.n_b) * OZ_TILE_BYTES);
+          for (int i = 0; i < g.n_a; ++i)
+            tma_load_1d(dst + (size_t)i * OZ_TILE_BYTES,
+                        slices + (size_t)g.a_slice[i] * slice_stride + ((size_t)wk.bi * KB + kb) * OZ_TILE_BYTES,
+                        OZ_TILE_BYTES, &full[stage]);
+          for (int i = 0; i < g.n_b; ++i)
+            tma_load_1d(dst + (size_t)(g.n_a + i) * OZ_TILE_BYTES,
+                        slices + (size_t)g.b_slice[i] * slice_stride + ((size_t)wk.bj * KB + kb) * OZ_TILE_BYTES,
+                        OZ_TILE_BYTES, &full[stage]);
+          (void)diag;
+          if (++stage == OZ_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int stage = 0, phase = 0, it = 0;
+      for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
+        const OzWork wk = work[w];
+        const OzGroup& g = plan.g[wk.group];
+        mbar_wait(tmem_empty, (uint32_t)((it & 1) ^ 1));
+        tc_fence_after();
+        uint32_t acc_used = 0;
+        for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t base = smem_u32(tiles + (size_t)stage * OZ_STAGE_BYTES);
+          for (int pr = 0; pr < g.n_pairs; ++pr) {
+            const uint32_t a_addr = base + (uint32_t)g.pair_a[pr] * OZ_TILE_BYTES;
+            const uint32_t b_addr = base + (uint32_t)(g.n_a + g.pair_b[pr]) * OZ_TILE_BYTES;
+            const uint32_t acc = g.pair_acc[pr];
+#pragma unroll
+            for (int ks = 0; ks < OZ_BK / 32; ++ks) {
+              umma_i8(tmem_base + acc * 128u, smem_desc_sw64(a_addr + ks * 32), smem_desc_sw64(b_addr + ks * 32),
+                      OZ_IDESC, (acc_used >> acc) & 1u);
+              acc_used |= 1u << acc;
+            }
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == OZ_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(tmem_full);
+      }
+    }
+  } else {
+    // ===== epilogue (8 warps: TMEM lane quarter = warp % 4, column half = (warp - 2) / 4) =====
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const int row_local = quarter * 32 + lane, col0 = half * 64;
+    int it = 0;
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
+      const OzWork wk = work[w];
+      const OzGroup& g = plan.g[wk.group];
+      mbar_wait(tmem_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      double acc[64];
+#pragma unroll
+      for (int j = 0; j < 64; ++j) acc[j] = 0.0;
+      for (int a = 0; a < g.n_acc; ++a) {
+        const double wgt = (double)(1ull << g.acc_shift[a]);
+#pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * 128 + col0 + c16 * 16), v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[c16 * 16 + j] = fma((double)(int)v[j], wgt, acc[c16 * 16 + j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty);
+      // scale and accumulate into Sraw (same triangle rules as syrk_dmma_kernel)
+      const int r = wk.bi * OZ_BM + row_local;
+      const int er = expo[r];
+      const bool diag = wk.bi == wk.bj;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        const int col = wk.bj * OZ_BM + col0 + j;
+        const int ec = expo[col];
+        double v = acc[j];
+        if (er == OZ_EXPO_BAD || ec == OZ_EXPO_BAD) v = __longlong_as_double(0x7ff8000000000000LL);
+        else v = ldexp(v, er + ec + g.exp_base);
+        if (v != 0.0) {
+          if (!mc_off && (!diag || col <= r)) atomicAdd(&Cmat[(size_t)r * Dpad + col], -v);
+          if (!diag || col < r || (mc_off && col == r)) {
+            double* q = &Cmat[(size_t)col * Dpad + r];
+            if (mc_off) {
+              asm volatile("multimem.red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(q + mc_off), "d"(-v) : "memory");
+            } else {
+              atomicAdd(q, -v);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// host side: order groups and work list
+bool build_plan(int s, OzPlan* plan) {
+  if (s < 3 || s > 7) return false;
+  plan->slices = s;
+  const int B = 8 * s - 2;
+  const int tlast = s + 1;                       // orders 2 .. s+1 are kept
+  int ng = 0;
+  for (int t0 = 2; t0 <= tlast; t0 += 4) {
+    if (ng >= OZ_MAX_GROUPS) return false;
+    OzGroup& g = plan->g[ng++];
+    const int t1 = std::min(t0 + 3, tlast);
+    g.n_acc = t1 - t0 + 1;
+    g.exp_base = 8 * (2 * s - t1) - 2 * B;
+    int slot_a[8], slot_b[8];
+    for (int i = 0; i < 8; ++i) slot_a[i] = slot_b[i] = -1;
+    g.n_a = g.n_b = g.n_pairs = 0;
+    for (int t = t0; t <= t1; ++t) {
+      g.acc_shift[t - t0] = (uint8_t)(8 * (t1 - t));
+      for (int p = 1; p <= s; ++p) {
+        const int q = t - p;
+        if (q < 1 || q > s) continue;
+        if (slot_a[p] < 0) {
+          slot_a[p] = g.n_a;
+          g.a_slice[g.n_a++] = (uint8_t)(p - 1);
+        }
+        if (slot_b[q] < 0) {
+          slot_b[q] = g.n_b;
+          g.b_slice[g.n_b++] = (uint8_t)(q - 1);
+        }
+        if (g.n_pairs >= OZ_MAX_PAIRS) return false;
+        g.pair_a[g.n_pairs] = (uint8_t)slot_a[p];
+        g.pair_b[g.n_pairs] = (uint8_t)slot_b[q];
+        g.pair_acc[g.n_pairs] = (uint8_t)(t - t0);
+        ++g.n_pairs;
+      }
+    }
+    if (g.n_a + g.n_b > OZ_STAGE_TILES) return false;
+  }
+  plan->n_groups = ng;
+  return true;
+}
+
+struct OzHostState {
+  int Kpad = -1, Dpad = -1, slices = -1, sms = 0;
+  OzPlan plan;
+  std::vector<OzWork> work;
+};
+thread_local OzHostState g_oz;
+
+size_t oz_workspace_bytes(int Kpad, int Dpad, int s) {
+  const int KB = (Kpad + OZ_BK - 1) / OZ_BK;
+  const int nb = Dpad / OZ_BM;
+  size_t bytes = 0;
+  bytes += align_up((size_t)Dpad * 8, 256);                                   // amax
+  bytes += align_up((size_t)Dpad * 4, 256);                                   // expo
+  bytes += align_up((size_t)nb * (nb + 1) / 2 * OZ_MAX_GROUPS * 8 * sizeof(OzWork), 256);   // work list (upper bound)
+  bytes += align_up((size_t)s * nb * KB * OZ_TILE_BYTES, 1024) + 1024;        // slices
+  return bytes;
+}
+
+}  // namespace
+
+size_t syrk_i8_workspace_bytes(int Kpad, int Dpad, int slices) { return oz_workspace_bytes(Kpad, Dpad, slices); }
+
+// Sraw -= Zt^T Zt with s int8 slices.  Zt [Kpad][Dpad] (Dpad % 128 == 0), Cmat [Dpad][Dpad] row-major, both
+// triangles written (mirror only in fabric mode), same contract as launch_syrk.
+int launch_syrk_i8(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t mc_off, int s, void* ws,
+                   size_t ws_bytes, cudaStream_t st) {
+  VGG_REQUIRE(Dpad % OZ_BM == 0, "syrk_i8: Dpad must be a multiple of 128");
+  VGG_REQUIRE((long long)Kpad <= (1 << 17), "syrk_i8: K too large for exact int32 accumulation");
+  VGG_REQUIRE(ws_bytes >= oz_workspace_bytes(Kpad, Dpad, s), "syrk_i8: workspace too small");
+  const int KB = (Kpad + OZ_BK - 1) / OZ_BK;
+  const int nb = Dpad / OZ_BM;
+  OzHostState& hs = g_oz;
+  if (hs.Kpad != Kpad || hs.Dpad != Dpad || hs.slices != s) {
+    VGG_REQUIRE(build_plan(s, &hs.plan), "syrk_i8: slices must be in [3,7]");
+    int dev = 0;
+    VGG_CUDA_CHECK(cudaGetDevice(&dev));
+    VGG_CUDA_CHECK(cudaDeviceGetAttribute(&hs.sms, cudaDevAttrMultiProcessorCount, dev));
+    VGG_CUDA_CHECK(cudaFuncSetAttribute(oz_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES));
+    // work items: (tile, group, k range) of roughly equal MMA cost, longest first
+    long long total = 0;
+    for (int g = 0; g < hs.plan.n_groups; ++g) total += (long long)hs.plan.g[g].n_pairs * KB;
+    total *= (long long)nb * (nb + 1) / 2;
+    const long long target = std::max<long long>(1, total / ((long long)hs.sms * 4));
+    hs.work.clear();
+    std::vector<std::pair<long long, OzWork>> items;
+    for (int bi = 0; bi < nb; ++bi)
+      for (int bj = 0; bj <= bi; ++bj)
+        for (int g = 0; g < hs.plan.n_groups; ++g) {
+          const long long cost = (long long)hs.plan.g[g].n_pairs * KB;
+          int parts = (int)std::min<long long>(8, std::max<long long>(1, (cost + target / 2) / target));
+          parts = std::min(parts, KB);
+          for (int p = 0; p < parts; ++p) {
+            OzWork wk{bi, bj, g, (int)((long long)KB * p / parts), (int)((long long)KB * (p + 1) / parts)};
+            items.push_back({(long long)hs.plan.g[g].n_pairs * (wk.kb1 - wk.kb0), wk});
+          }
+        }
+    std::stable_sort(items.begin(), items.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
+    for (auto& it : items) hs.work.push_back(it.second);
+    hs.Kpad = Kpad;
+    hs.Dpad = Dpad;
+    hs.slices = s;
+  }
+  Carver c(ws, ws_bytes);
+  unsigned long long* amax = c.take<unsigned long long>(Dpad);
+  int* expo = c.take<int>(Dpad);
+  OzWork* work_d = c.take<OzWork>((size_t)nb * (nb + 1) / 2 * OZ_MAX_GROUPS * 8);
+  c.off = align_up(c.off, 1024);
+  int8_t* slices = reinterpret_cast<int8_t*>(c.base + c.off);
+  const size_t slice_stride = (size_t)nb * KB * OZ_TILE_BYTES;
+  const int nwork = (int)hs.work.size();
+
+  VGG_CUDA_CHECK(cudaMemsetAsync(amax, 0, sizeof(unsigned long long) * Dpad, st));
+  VGG_CUDA_CHECK(cudaMemcpyAsync(work_d, hs.work.data(), sizeof(OzWork) * nwork, cudaMemcpyHostToDevice, st));
+  const int ksplit = 64;
+  const int k_per = (Kpad + ksplit - 1) / ksplit;
+  oz_rowmax_kernel<<<dim3(Dpad / 128, ksplit), 128, 0, st>>>(Kpad, Dpad, k_per, Zt, amax);
+  VGG_LAUNCH_CHECK();
+  oz_slice_kernel<<<dim3(nb, KB), 512, 0, st>>>(Kpad, Dpad, KB, s, Zt, amax, expo, slices, slice_stride);
+  VGG_LAUNCH_CHECK();
+  const int grid = std::min(hs.sms, nwork);
+  oz_syrk_kernel<<<grid, OZ_THREADS, OZ_SMEM_BYTES, st>>>(hs.plan, work_d, nwork, KB, slices, slice_stride, expo, Dpad,
+                                                        Cmat, mc_off);
+  VGG_LAUNCH_CHECK();
+  return VGG_OK;
+}
+
+}  // namespace vgg
+
+extern "C" {
+
+int vgg_syrk_ozaki_workspace_bytes(int Kpad, int Dpad, int slices, size_t* bytes) {
+  using namespace vgg;
+  VGG_REQUIRE(bytes && Kpad > 0 && Dpad > 0 && Dpad % 128 == 0 && slices >= 3 && slices <= 7, "bad argument");
+  *bytes = syrk_i8_workspace_bytes(Kpad, Dpad, slices);
+  return VGG_OK;
+}
+
+int vgg_syrk_ozaki(int Kpad, int Dpad, const double* Zt, double* Cmat, int slices, void* workspace, size_t ws_bytes,
+                   void* stream) {
+  using namespace vgg;
+  g_launch_count = 0;
+  VGG_REQUIRE(Zt && Cmat && workspace, "null pointer");
+  return launch_syrk_i8(Kpad, Dpad, Zt, Cmat, 0, slices, workspace, ws_bytes, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"
