@@ -165,7 +165,7 @@ constexpr int ZB_NT = 32;
 __global__ void __launch_bounds__(128) z_build_kernel(int D, int N, int Dpad, size_t pitch, const double* __restrict__ W,
                                                       const double* __restrict__ M, const double* __restrict__ q,
                                                       double* __restrict__ Zt, double* __restrict__ rhs,
-                                                      ptrdiff_t mc_off) {
+                                                      ptrdiff_t mc_off, unsigned long long* __restrict__ amax) {
   __shared__ double sm[ZB_NT][12];
   const int row = blockIdx.x * 128 + threadIdx.x;
   const int n0 = blockIdx.y * ZB_NT;
@@ -177,6 +177,7 @@ __global__ void __launch_bounds__(128) z_build_kernel(int D, int N, int Dpad, si
   __syncthreads();
   if (row >= D) return;
   double zq = 0.0;
+  double zmax = 0.0;                  // running max |z| of this row (NaN / Inf stick): the tensor-core SYRK's column scale
   const double* wp = W + ((size_t)n0 * pitch + row) * 3;
 #pragma unroll 4
   for (int t = 0; t < nt; ++t, wp += pitch * 3) {
@@ -190,6 +191,14 @@ __global__ void __launch_bounds__(128) z_build_kernel(int D, int N, int Dpad, si
     zo[Dpad] = z1;
     zo[2 * (size_t)Dpad] = z2;
     zq += z0 * m[9] + z1 * m[10] + z2 * m[11];
+    const double a0 = fabs(z0), a1 = fabs(z1), a2 = fabs(z2);
+    zmax = (a0 > zmax || a0 != a0) ? a0 : zmax;
+    zmax = (a1 > zmax || a1 != a1) ? a1 : zmax;
+    zmax = (a2 > zmax || a2 != a2) ? a2 : zmax;
+  }
+  if (amax) {
+    if (!(zmax <= 1.7976931348623157e308)) zmax = __longlong_as_double(0x7ff0000000000000LL);
+    if (zmax > 0.0) atomicMax(&amax[row], (unsigned long long)__double_as_longlong(zmax));
   }
   if (zq != 0.0) ar_add(&rhs[row], mc_off ? &rhs[row] + mc_off : nullptr, zq);
 }
@@ -418,18 +427,26 @@ __global__ void scale_damp_kernel(int D, int Dpad, double* __restrict__ A, const
     if (i == j) v += fmin(fmax(hdiag[i] * sc[i] * sc[i], min_diag), max_diag) / radius;
   }
   A[(size_t)i * Dpad + j] = v;
-  if (i == j) bvec[i] = ci ? 0.0 : rhs[i] * sc[i];
+  if (i == j) {
+    // The scaled right-hand side also goes into column D of the buffer (row D of its column-major view): the
+    // factorisation of the bordered matrix [[A, b], [b^T, c]] = [[L, 0], [y^T, .]] leaves y = L^-1 b there, i.e.
+    // the forward substitution comes out of potrf for free (csrc/ba_solve.cu).  c only has to exceed y^T y.
+    const double b = ci ? 0.0 : rhs[i] * sc[i];
+    bvec[i] = b;
+    A[(size_t)i * Dpad + D] = b;
+    if (i == 0) A[(size_t)D * Dpad + D] = 1e300;
+  }
 }
 
 // d_c = sc * dcs ; scal[0] += sum dcs^2 dcc/r (free) - d_c.g ; scal[1] += |d_c|^2 ; scal[7] non-finite flag
-__global__ void cam_step_kernel(int D, const double* __restrict__ dcs, const double* __restrict__ sc,
+__global__ void cam_step_kernel(int D, const double* __restrict__ dcs, size_t dcs_stride, const double* __restrict__ sc,
                                 const double* __restrict__ hdiag, const double* __restrict__ gvec,
                                 const uint8_t* __restrict__ pconst, double radius, double min_diag, double max_diag,
                                 double* __restrict__ d_c, double* __restrict__ scal) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   double a = 0, b = 0, bad = 0;
   if (i < D) {
-    const double x = pconst[i] ? 0.0 : dcs[i];
+    const double x = pconst[i] ? 0.0 : dcs[(size_t)i * dcs_stride];
     const double dc = x * sc[i];
     d_c[i] = dc;
     if (!isfinite(x)) bad = 1.0;
@@ -604,10 +621,10 @@ int launch_assemble_hc(int S, int dc, int ns, int KR, int Dpad, const double* ca
   return VGG_OK;
 }
 int launch_z_transpose(int D, int N, int Dpad, const double* W, const double* M, const double* q, double* Zt,
-                       double* rhs, ptrdiff_t mc_off, cudaStream_t st) {
+                       double* rhs, ptrdiff_t mc_off, cudaStream_t st, unsigned long long* amax) {
   const size_t pitch = (size_t)(D + (D & 1));
   dim3 grid((D + 127) / 128, (N + ZB_NT - 1) / ZB_NT);
-  z_build_kernel<<<grid, 128, 0, st>>>(D, N, Dpad, pitch, W, M, q, Zt, rhs, mc_off);
+  z_build_kernel<<<grid, 128, 0, st>>>(D, N, Dpad, pitch, W, M, q, Zt, rhs, mc_off, amax);
   VGG_LAUNCH_CHECK();
   return VGG_OK;
 }
@@ -646,10 +663,10 @@ int launch_scale_damp(int D, int Dpad, double* A, const double* rhs, const doubl
   VGG_LAUNCH_CHECK();
   return VGG_OK;
 }
-int launch_cam_step(int D, const double* dcs, const double* sc, const double* hdiag, const double* gvec,
+int launch_cam_step(int D, const double* dcs, size_t dcs_stride, const double* sc, const double* hdiag, const double* gvec,
                     const uint8_t* pconst, double radius, double min_diag, double max_diag, double* d_c, double* scal,
                     cudaStream_t st) {
-  cam_step_kernel<<<(D + 255) / 256, 256, 0, st>>>(D, dcs, sc, hdiag, gvec, pconst, radius, min_diag, max_diag, d_c, scal);
+  cam_step_kernel<<<(D + 255) / 256, 256, 0, st>>>(D, dcs, dcs_stride, sc, hdiag, gvec, pconst, radius, min_diag, max_diag, d_c, scal);
   VGG_LAUNCH_CHECK();
   return VGG_OK;
 }

@@ -2,6 +2,7 @@
 // the C-ABI entry points of the bundle-adjustment path.  The loop body is ~14 kernel launches per
 // iteration on one stream and ONE small device->host read (accept/reject scalars); track shards on
 // other GPUs join through the caller's all-reduce hook (NCCL over NVLink, see vggsfm_b200/dist.py).
+#include <cublas_v2.h>
 #include <cusolverDn.h>
 #include <math.h>
 #include <stdlib.h>
@@ -31,15 +32,17 @@ int launch_point_prep(int N, const double* H_pp, const double* g_p, const double
 int launch_assemble_hc(int S, int dc, int ns, int KR, int Dpad, const double* camrec, const double* shared_in,
                        double* Sraw, double* rhs, double* hdiag, double* gvec, ptrdiff_t mc_off, cudaStream_t st);
 int launch_z_transpose(int D, int N, int Dpad, const double* W, const double* M, const double* q, double* Zt,
-                       double* rhs, ptrdiff_t mc_off, cudaStream_t st);
+                       double* rhs, ptrdiff_t mc_off, cudaStream_t st, unsigned long long* amax);
 int launch_syrk(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t mc_off, cudaStream_t st);
 size_t syrk_i8_workspace_bytes(int Kpad, int Dpad, int slices);
 int launch_syrk_i8(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t mc_off, int slices, void* ws,
-                   size_t ws_bytes, cudaStream_t st);
+                   size_t ws_bytes, cudaStream_t st, bool amax_ready);
+unsigned long long* syrk_i8_amax(void* ws);
+int syrk_i8_reset_amax(void* ws, int Dpad, cudaStream_t st);
 int launch_scale_damp(int D, int Dpad, double* A, const double* rhs, const double* hdiag, const double* sc,
                       const uint8_t* pconst, double radius, double min_diag, double max_diag, double* bvec,
                       cudaStream_t st);
-int launch_cam_step(int D, const double* dcs, const double* sc, const double* hdiag, const double* gvec,
+int launch_cam_step(int D, const double* dcs, size_t dcs_stride, const double* sc, const double* hdiag, const double* gvec,
                     const uint8_t* pconst, double radius, double min_diag, double max_diag, double* d_c, double* scal,
                     cudaStream_t st);
 int launch_backsub(int D, int N, const double* W, const double* d_c, double* wacc, cudaStream_t st);
@@ -186,6 +189,14 @@ static cusolverDnHandle_t get_cusolver() {
   return h;
 }
 
+static cublasHandle_t get_cublas() {
+  static thread_local cublasHandle_t h = nullptr;
+  if (!h) {
+    if (cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) h = nullptr;
+  }
+  return h;
+}
+
 static int potrf_lwork(int D, int Dpad, size_t* lwork) {
   cusolverDnHandle_t h = get_cusolver();
   if (!h) {
@@ -193,7 +204,7 @@ static int potrf_lwork(int D, int Dpad, size_t* lwork) {
     return VGG_ESOLVER;
   }
   int lw = 0;
-  if (cusolverDnDpotrf_bufferSize(h, CUBLAS_FILL_MODE_LOWER, D, nullptr, Dpad, &lw) != CUSOLVER_STATUS_SUCCESS) {
+  if (cusolverDnDpotrf_bufferSize(h, CUBLAS_FILL_MODE_LOWER, D + 1, nullptr, Dpad, &lw) != CUSOLVER_STATUS_SUCCESS) {
     set_error("cusolverDnDpotrf_bufferSize failed");
     return VGG_ESOLVER;
   }
@@ -217,9 +228,11 @@ static int schur_build(const Layout& L, const BlockSet& b, const uint8_t* point_
   // fabric mode: every rank's copy must be zero before anyone's multimem reductions land in it
   if (mc_off && barrier && (rc = barrier(barrier_user, nullptr, 0, 2, st))) return rc;
   if ((rc = launch_assemble_hc(L.S, L.dc, L.ns, L.KR, L.Dpad, b.camrec, b.shared, Sraw, rhs, hdiag, gvec, mc_off, st))) return rc;
-  if ((rc = launch_z_transpose(L.D, L.N, L.Dpad, b.W, L.M, L.q, L.Zt, rhs, mc_off, st))) return rc;
-  const int oz = syrk_i8_slices();
-  if (oz && L.oz_bytes) rc = launch_syrk_i8(L.Kpad, L.Dpad, L.Zt, Sraw, mc_off, oz, L.oz_ws, L.oz_bytes, st);
+  const int oz = L.oz_bytes ? syrk_i8_slices() : 0;
+  if (oz && (rc = syrk_i8_reset_amax(L.oz_ws, L.Dpad, st))) return rc;
+  if ((rc = launch_z_transpose(L.D, L.N, L.Dpad, b.W, L.M, L.q, L.Zt, rhs, mc_off, st, oz ? syrk_i8_amax(L.oz_ws) : nullptr)))
+    return rc;
+  if (oz) rc = launch_syrk_i8(L.Kpad, L.Dpad, L.Zt, Sraw, mc_off, oz, L.oz_ws, L.oz_bytes, st, true);
   else rc = launch_syrk(L.Kpad, L.Dpad, L.Zt, Sraw, mc_off, st);
   if (rc) return rc;
   // ... and all reductions must have landed before anyone reads its copy
@@ -497,6 +510,10 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
     }();
     const int cm = (mc_off && chol_mode == 2) ? 0 : chol_mode;      // fabric mode reduces one triangle only
     const cublasFillMode_t uplo = (cm == 2) ? CUBLAS_FILL_MODE_UPPER : CUBLAS_FILL_MODE_LOWER;
+    // Library paths factor the BORDERED matrix of order D+1 (scale_damp put the right-hand side in column D of the
+    // buffer = row D of the column-major view): potrf then leaves y = L^-1 b in that row, and only the backward
+    // substitution L^T x = y remains (one cublasDtrsv on the strided row instead of potrs' two: -0.17 ms at C3).
+    const int nfac = D + 1;
     if (cm == 0) {
       static thread_local cusolverDnParams_t xp = nullptr;
       static thread_local void* xdev = nullptr;
@@ -504,20 +521,20 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
       static thread_local size_t xdev_b = 0, xhost_b = 0;
       if (!xp) cusolverDnCreateParams(&xp);
       size_t db = 0, hb = 0;
-      if (cusolverDnXpotrf_bufferSize(cs, xp, uplo, D, CUDA_R_64F, Sraw, L.Dpad, CUDA_R_64F, &db, &hb) !=
+      if (cusolverDnXpotrf_bufferSize(cs, xp, uplo, nfac, CUDA_R_64F, Sraw, L.Dpad, CUDA_R_64F, &db, &hb) !=
           CUSOLVER_STATUS_SUCCESS) {
         set_error("cusolverDnXpotrf_bufferSize failed");
         return VGG_ESOLVER;
       }
       if (db > xdev_b) { if (xdev) cudaFree(xdev); VGG_CUDA_CHECK(cudaMalloc(&xdev, db)); xdev_b = db; }
       if (hb > xhost_b) { free(xhost); xhost = malloc(hb); xhost_b = hb; }
-      if (cusolverDnXpotrf(cs, xp, uplo, D, CUDA_R_64F, Sraw, L.Dpad, CUDA_R_64F, xdev, db, xhost, hb, L.dev_info) !=
+      if (cusolverDnXpotrf(cs, xp, uplo, nfac, CUDA_R_64F, Sraw, L.Dpad, CUDA_R_64F, xdev, db, xhost, hb, L.dev_info) !=
           CUSOLVER_STATUS_SUCCESS) {
         set_error("cusolverDnXpotrf failed to launch");
         return VGG_ESOLVER;
       }
     } else if (cm == 1) {
-      if (cusolverDnDpotrf(cs, uplo, D, Sraw, L.Dpad, L.potrf_work, (int)L.potrf_lwork, L.dev_info) !=
+      if (cusolverDnDpotrf(cs, uplo, nfac, Sraw, L.Dpad, L.potrf_work, (int)L.potrf_lwork, L.dev_info) !=
           CUSOLVER_STATUS_SUCCESS) {
         set_error("cusolverDnDpotrf failed to launch");
         return VGG_ESOLVER;
@@ -525,12 +542,30 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
     } else if ((rc = chol_lower_inplace(D, L.Dpad, Sraw, L.chol_diag, L.dev_info, st))) {
       return rc;
     }
-    if (cusolverDnDpotrs(cs, uplo, D, 1, Sraw, L.Dpad, L.bvec, L.Dpad, L.dev_info + 1) != CUSOLVER_STATUS_SUCCESS) {
-      set_error("cusolverDnDpotrs failed to launch");
-      return VGG_ESOLVER;
+    const double* dcs = L.bvec;
+    size_t dcs_stride = 1;
+    if (cm == 2) {
+      if (cusolverDnDpotrs(cs, uplo, D, 1, Sraw, L.Dpad, L.bvec, L.Dpad, L.dev_info + 1) != CUSOLVER_STATUS_SUCCESS) {
+        set_error("cusolverDnDpotrs failed to launch");
+        return VGG_ESOLVER;
+      }
+    } else {
+      cublasHandle_t cb = get_cublas();
+      if (!cb || cublasSetStream(cb, st) != CUBLAS_STATUS_SUCCESS) {
+        set_error("cublasCreate / cublasSetStream failed");
+        return VGG_ESOLVER;
+      }
+      VGG_CUDA_CHECK(cudaMemsetAsync(L.dev_info + 1, 0, sizeof(int), st));
+      if (cublasDtrsv(cb, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, D, Sraw, L.Dpad, Sraw + D, L.Dpad) !=
+          CUBLAS_STATUS_SUCCESS) {
+        set_error("cublasDtrsv failed to launch");
+        return VGG_ESOLVER;
+      }
+      dcs = Sraw + D;
+      dcs_stride = (size_t)L.Dpad;
     }
     g_launch_count += 1;
-    if ((rc = launch_cam_step(D, L.bvec, L.sc_c, hdiag, gvec, prob->param_const, radius, opt.min_lm_diagonal,
+    if ((rc = launch_cam_step(D, dcs, dcs_stride, L.sc_c, hdiag, gvec, prob->param_const, radius, opt.min_lm_diagonal,
                               opt.max_lm_diagonal, L.d_c, L.scal, st)))
       return rc;
     if (mc_off) {

@@ -48,6 +48,7 @@ struct OzGroup {
   int exp_base;                                  // 8 (2s - tmax) - 2B
   uint8_t a_slice[8], b_slice[8];                // slice held by tile slot i / n_a + i
   uint8_t pair_a[OZ_MAX_PAIRS], pair_b[OZ_MAX_PAIRS], pair_acc[OZ_MAX_PAIRS];
+  uint8_t pair_b_diag[OZ_MAX_PAIRS];             // on diagonal tiles B_q is the A slot that holds slice q
   uint8_t acc_shift[4];                          // 8 (tmax - t) of accumulator a
 };
 struct OzPlan {
@@ -79,42 +80,58 @@ __global__ void oz_rowmax_kernel(int Kpad, int Dpad, int k_per, const double* __
 // 2. slices, written as pre-swizzled 8 KB tile images: tile (slice p, row block rb, k block kb) holds rows
 //    d = rb*128 + r, bytes k = kb*64 + kk at offset r*64 + (((kk >> 4) ^ ((r >> 1) & 3)) << 4) + (kk & 15)
 //    (the 64-byte swizzle, Swizzle<2,4,3>, of a K-major 128 x 64 B tile whose base is 1024-byte aligned).
+//    Balanced base-256 digits come from ONE 64-bit add: with X = rint(x 2^B), |X| <= 2^B, the bytes of
+//    X + 0x80..80 (s bytes of 0x80) are d_p + 128, so d_p = byte ^ 0x80.  A warp owns 8 rows x 4 chunks: its loads are
+//    4 x 64-byte segments per k and its stores 512 contiguous bytes per slice.
 __global__ void __launch_bounds__(512) oz_slice_kernel(int Kpad, int Dpad, int KB, int s,
                                                        const double* __restrict__ Zt,
                                                        const unsigned long long* __restrict__ amax,
-                                                       int* __restrict__ expo, int8_t* __restrict__ slices,
-                                                       size_t slice_stride) {
+                                                       int* __restrict__ expo, double* __restrict__ pow2,
+                                                       int8_t* __restrict__ slices, size_t slice_stride) {
   const int rb = blockIdx.x, kb = blockIdx.y;
-  const int r = threadIdx.x & 127, c = threadIdx.x >> 7;
+  const int r = (threadIdx.x >> 5) * 8 + ((threadIdx.x & 31) >> 2), cphys = threadIdx.x & 3;
+  const int c = cphys ^ ((r >> 1) & 3);
   const int d = rb * OZ_BM + r;
   const double m = __longlong_as_double((long long)amax[d]);
   int e = 0;
-  bool bad = false;
+  bool bad = false, zero = true;
   if (m > 0.0) {
-    if (m <= 1.7976931348623157e308) e = ilogb(m) + 1;
-    else bad = true;
+    if (m <= 1.7976931348623157e308) {
+      e = ilogb(m) + 1;
+      zero = e < -900;                 // columns below 2^-900 are treated as exact zeros (keeps 2^(B-e) finite)
+      if (zero) e = 0;
+    } else {
+      bad = true;
+    }
   }
-  if (kb == 0 && c == 0) expo[d] = bad ? OZ_EXPO_BAD : e;
+  if (kb == 0 && cphys == 0) {
+    expo[d] = bad ? OZ_EXPO_BAD : e;
+    pow2[d] = bad ? 0.0 : ldexp(1.0, e);
+  }
   const int B = 8 * s - 2;
+  const double scale = (bad || zero) ? 0.0 : __longlong_as_double((long long)(1023 + B - e) << 52);   // 2^(B-e), exact
+  const unsigned long long bias = 0x0080808080808080ull >> (8 * (7 - s));
   uint32_t dig[7][4];
 #pragma unroll
   for (int p = 0; p < 7; ++p) dig[p][0] = dig[p][1] = dig[p][2] = dig[p][3] = 0u;
   const int kbase = kb * OZ_BK + c * 16;
+  double z[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) z[i] = (kbase + i < Kpad) ? Zt[(size_t)(kbase + i) * Dpad + d] : 0.0;
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    const int k = kbase + i;
-    double z = (k < Kpad && !bad) ? Zt[(size_t)k * Dpad + d] : 0.0;
-    long long X = llrint(ldexp(z, B - e));
+    const unsigned long long Y = ((unsigned long long)__double2ll_rn(z[i] * scale) + bias) ^ bias;   // byte j = digit of 256^j
+    const uint32_t lo = (uint32_t)Y, hi = (uint32_t)(Y >> 32);
 #pragma unroll
-    for (int p = 6; p >= 0; --p) {
+    for (int p = 0; p < 7; ++p) {
       if (p < s) {
-        const int dg = (int)((X + 128) & 255) - 128;
-        X = (X - dg) >> 8;
-        dig[p][i >> 2] |= (uint32_t)(dg & 255) << (8 * (i & 3));
+        const int j = s - 1 - p;                           // slice p (most significant first) is byte j
+        const uint32_t byte = ((j < 4 ? lo >> (8 * j) : hi >> (8 * (j - 4))) & 255u);
+        dig[p][i >> 2] |= byte << (8 * (i & 3));
       }
     }
   }
-  const size_t off = ((size_t)rb * KB + kb) * OZ_TILE_BYTES + (size_t)r * OZ_BK + (size_t)((c ^ ((r >> 1) & 3)) << 4);
+  const size_t off = ((size_t)rb * KB + kb) * OZ_TILE_BYTES + (size_t)r * OZ_BK + (size_t)(cphys << 4);
 #pragma unroll
   for (int p = 0; p < 7; ++p)
     if (p < s) *reinterpret_cast<uint4*>(slices + (size_t)p * slice_stride + off) = make_uint4(dig[p][0], dig[p][1], dig[p][2], dig[p][3]);
@@ -171,8 +188,8 @@ constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) 
 // 3. persistent tcgen05 SYRK
 __global__ void __launch_bounds__(OZ_THREADS, 1)
     oz_syrk_kernel(const __grid_constant__ OzPlan plan, const OzWork* __restrict__ work, int nwork, int KB,
-                   const int8_t* __restrict__ slices, size_t slice_stride, const int* __restrict__ expo, int Dpad,
-                   double* __restrict__ Cmat, ptrdiff_t mc_off) {
+                   const int8_t* __restrict__ slices, size_t slice_stride, const int* __restrict__ expo,
+                   const double* __restrict__ pow2, int Dpad, double* __restrict__ Cmat, ptrdiff_t mc_off) {
   extern __shared__ __align__(1024) uint8_t oz_smem[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(oz_smem), 1024));
   uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (size_t)OZ_STAGES * OZ_STAGE_BYTES);
@@ -208,16 +225,15 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
         for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* dst = tiles + (size_t)stage * OZ_STAGE_BYTES;
-          mbar_expect_tx(&full[stage], (uint32_t)(g.n_a + g.n_b) * OZ_TILE_BYTES);
+          mbar_expect_tx(&full[stage], (uint32_t)(g.n_a + (diag ? 0 : g.n_b)) * OZ_TILE_BYTES);
           for (int i = 0; i < g.n_a; ++i)
             tma_load_1d(dst + (size_t)i * OZ_TILE_BYTES,
                         slices + (size_t)g.a_slice[i] * slice_stride + ((size_t)wk.bi * KB + kb) * OZ_TILE_BYTES,
                         OZ_TILE_BYTES, &full[stage]);
-          for (int i = 0; i < g.n_b; ++i)
+          for (int i = 0; i < (diag ? 0 : g.n_b); ++i)
             tma_load_1d(dst + (size_t)(g.n_a + i) * OZ_TILE_BYTES,
                         slices + (size_t)g.b_slice[i] * slice_stride + ((size_t)wk.bj * KB + kb) * OZ_TILE_BYTES,
                         OZ_TILE_BYTES, &full[stage]);
-          (void)diag;
           if (++stage == OZ_STAGES) {
             stage = 0;
             phase ^= 1;
@@ -232,6 +248,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
       for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
         const OzWork wk = work[w];
         const OzGroup& g = plan.g[wk.group];
+        const bool diag = wk.bi == wk.bj;
         mbar_wait(tmem_empty, (uint32_t)((it & 1) ^ 1));
         tc_fence_after();
         uint32_t acc_used = 0;
@@ -241,7 +258,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
           const uint32_t base = smem_u32(tiles + (size_t)stage * OZ_STAGE_BYTES);
           for (int pr = 0; pr < g.n_pairs; ++pr) {
             const uint32_t a_addr = base + (uint32_t)g.pair_a[pr] * OZ_TILE_BYTES;
-            const uint32_t b_addr = base + (uint32_t)(g.n_a + g.pair_b[pr]) * OZ_TILE_BYTES;
+            const uint32_t b_addr = base + (uint32_t)(diag ? g.pair_b_diag[pr] : g.n_a + g.pair_b[pr]) * OZ_TILE_BYTES;
             const uint32_t acc = g.pair_acc[pr];
 #pragma unroll
             for (int ks = 0; ks < OZ_BK / 32; ++ks) {
@@ -289,12 +306,16 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
       const int r = wk.bi * OZ_BM + row_local;
       const int er = expo[r];
       const bool diag = wk.bi == wk.bj;
+      // 2^(e_r + e_c + exp_base) as two exact multiplications while the exponents are tame, ldexp otherwise
+      const bool tame = er != OZ_EXPO_BAD && er > -400 && er < 400;
+      const double sr = tame ? __longlong_as_double((long long)(1023 + er + g.exp_base) << 52) : 0.0;
 #pragma unroll
       for (int j = 0; j < 64; ++j) {
         const int col = wk.bj * OZ_BM + col0 + j;
         const int ec = expo[col];
         double v = acc[j];
         if (er == OZ_EXPO_BAD || ec == OZ_EXPO_BAD) v = __longlong_as_double(0x7ff8000000000000LL);
+        else if (tame && ec > -400 && ec < 400) v = v * sr * pow2[col];
         else v = ldexp(v, er + ec + g.exp_base);
         if (v != 0.0) {
           if (!mc_off && (!diag || col <= r)) atomicAdd(&Cmat[(size_t)r * Dpad + col], -v);
@@ -352,6 +373,11 @@ bool build_plan(int s, OzPlan* plan) {
         ++g.n_pairs;
       }
     }
+    for (int pr = 0; pr < g.n_pairs; ++pr) {              // the order groups are symmetric in (p, q): slice q has an A slot
+      const int q = g.b_slice[g.pair_b[pr]] + 1;
+      if (slot_a[q] < 0) return false;
+      g.pair_b_diag[pr] = (uint8_t)slot_a[q];
+    }
     if (g.n_a + g.n_b > OZ_STAGE_TILES) return false;
   }
   plan->n_groups = ng;
@@ -362,6 +388,8 @@ struct OzHostState {
   int Kpad = -1, Dpad = -1, slices = -1, sms = 0;
   OzPlan plan;
   std::vector<OzWork> work;
+  OzWork* pinned = nullptr;       // page-locked copy of `work`, so the per-call upload is a true async copy
+  size_t pinned_cap = 0;
 };
 thread_local OzHostState g_oz;
 
@@ -371,6 +399,7 @@ size_t oz_workspace_bytes(int Kpad, int Dpad, int s) {
   size_t bytes = 0;
   bytes += align_up((size_t)Dpad * 8, 256);                                   // amax
   bytes += align_up((size_t)Dpad * 4, 256);                                   // expo
+  bytes += align_up((size_t)Dpad * 8, 256);                                   // pow2
   bytes += align_up((size_t)nb * (nb + 1) / 2 * OZ_MAX_GROUPS * 8 * sizeof(OzWork), 256);   // work list (upper bound)
   bytes += align_up((size_t)s * nb * KB * OZ_TILE_BYTES, 1024) + 1024;        // slices
   return bytes;
@@ -380,10 +409,18 @@ size_t oz_workspace_bytes(int Kpad, int Dpad, int s) {
 
 size_t syrk_i8_workspace_bytes(int Kpad, int Dpad, int slices) { return oz_workspace_bytes(Kpad, Dpad, slices); }
 
+// The column maxima can be produced by whoever writes Zt (z_build_kernel does): zero them with syrk_i8_reset_amax,
+// hand syrk_i8_amax(ws) to the producer, then call launch_syrk_i8 with amax_ready = true.
+unsigned long long* syrk_i8_amax(void* ws) { return static_cast<unsigned long long*>(ws); }
+int syrk_i8_reset_amax(void* ws, int Dpad, cudaStream_t st) {
+  VGG_CUDA_CHECK(cudaMemsetAsync(ws, 0, sizeof(unsigned long long) * Dpad, st));
+  return VGG_OK;
+}
+
 // Sraw -= Zt^T Zt with s int8 slices.  Zt [Kpad][Dpad] (Dpad % 128 == 0), Cmat [Dpad][Dpad] row-major, both
 // triangles written (mirror only in fabric mode), same contract as launch_syrk.
 int launch_syrk_i8(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t mc_off, int s, void* ws,
-                   size_t ws_bytes, cudaStream_t st) {
+                   size_t ws_bytes, cudaStream_t st, bool amax_ready) {
   VGG_REQUIRE(Dpad % OZ_BM == 0, "syrk_i8: Dpad must be a multiple of 128");
   VGG_REQUIRE((long long)Kpad <= (1 << 17), "syrk_i8: K too large for exact int32 accumulation");
   VGG_REQUIRE(ws_bytes >= oz_workspace_bytes(Kpad, Dpad, s), "syrk_i8: workspace too small");
@@ -416,6 +453,12 @@ int launch_syrk_i8(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t
         }
     std::stable_sort(items.begin(), items.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
     for (auto& it : items) hs.work.push_back(it.second);
+    if (hs.work.size() > hs.pinned_cap) {
+      if (hs.pinned) cudaFreeHost(hs.pinned);
+      hs.pinned_cap = hs.work.size();
+      VGG_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&hs.pinned), sizeof(OzWork) * hs.pinned_cap, cudaHostAllocDefault));
+    }
+    std::copy(hs.work.begin(), hs.work.end(), hs.pinned);
     hs.Kpad = Kpad;
     hs.Dpad = Dpad;
     hs.slices = s;
@@ -423,23 +466,26 @@ int launch_syrk_i8(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t
   Carver c(ws, ws_bytes);
   unsigned long long* amax = c.take<unsigned long long>(Dpad);
   int* expo = c.take<int>(Dpad);
+  double* pow2 = c.take<double>(Dpad);
   OzWork* work_d = c.take<OzWork>((size_t)nb * (nb + 1) / 2 * OZ_MAX_GROUPS * 8);
   c.off = align_up(c.off, 1024);
   int8_t* slices = reinterpret_cast<int8_t*>(c.base + c.off);
   const size_t slice_stride = (size_t)nb * KB * OZ_TILE_BYTES;
   const int nwork = (int)hs.work.size();
 
-  VGG_CUDA_CHECK(cudaMemsetAsync(amax, 0, sizeof(unsigned long long) * Dpad, st));
-  VGG_CUDA_CHECK(cudaMemcpyAsync(work_d, hs.work.data(), sizeof(OzWork) * nwork, cudaMemcpyHostToDevice, st));
-  const int ksplit = 64;
-  const int k_per = (Kpad + ksplit - 1) / ksplit;
-  oz_rowmax_kernel<<<dim3(Dpad / 128, ksplit), 128, 0, st>>>(Kpad, Dpad, k_per, Zt, amax);
-  VGG_LAUNCH_CHECK();
-  oz_slice_kernel<<<dim3(nb, KB), 512, 0, st>>>(Kpad, Dpad, KB, s, Zt, amax, expo, slices, slice_stride);
+  VGG_CUDA_CHECK(cudaMemcpyAsync(work_d, hs.pinned, sizeof(OzWork) * nwork, cudaMemcpyHostToDevice, st));
+  if (!amax_ready) {
+    VGG_CUDA_CHECK(cudaMemsetAsync(amax, 0, sizeof(unsigned long long) * Dpad, st));
+    const int ksplit = 64;
+    const int k_per = (Kpad + ksplit - 1) / ksplit;
+    oz_rowmax_kernel<<<dim3(Dpad / 128, ksplit), 128, 0, st>>>(Kpad, Dpad, k_per, Zt, amax);
+    VGG_LAUNCH_CHECK();
+  }
+  oz_slice_kernel<<<dim3(nb, KB), 512, 0, st>>>(Kpad, Dpad, KB, s, Zt, amax, expo, pow2, slices, slice_stride);
   VGG_LAUNCH_CHECK();
   const int grid = std::min(hs.sms, nwork);
-  oz_syrk_kernel<<<grid, OZ_THREADS, OZ_SMEM_BYTES, st>>>(hs.plan, work_d, nwork, KB, slices, slice_stride, expo, Dpad,
-                                                        Cmat, mc_off);
+  oz_syrk_kernel<<<grid, OZ_THREADS, OZ_SMEM_BYTES, st>>>(hs.plan, work_d, nwork, KB, slices, slice_stride, expo, pow2,
+                                                        Dpad, Cmat, mc_off);
   VGG_LAUNCH_CHECK();
   return VGG_OK;
 }
@@ -460,7 +506,7 @@ int vgg_syrk_ozaki(int Kpad, int Dpad, const double* Zt, double* Cmat, int slice
   using namespace vgg;
   g_launch_count = 0;
   VGG_REQUIRE(Zt && Cmat && workspace, "null pointer");
-  return launch_syrk_i8(Kpad, Dpad, Zt, Cmat, 0, slices, workspace, ws_bytes, static_cast<cudaStream_t>(stream));
+  return launch_syrk_i8(Kpad, Dpad, Zt, Cmat, 0, slices, workspace, ws_bytes, static_cast<cudaStream_t>(stream), false);
 }
 
 }  // extern "C"
