@@ -12,6 +12,15 @@ sys.path.insert(0, ROOT)
 from vggsfm_b200 import _lib       # noqa: E402
 
 dev = torch.device("cuda:0")
+if len(sys.argv) > 1 and sys.argv[1] == "rate":
+    L = _lib.lib()
+    torch.zeros(1, device=dev)
+    for mode, name in [(0, "SW64  N=128"), (1, "SW64  N=256"), (2, "SW128 N=128"), (3, "SW128 N=256"), (4, "none  N=128"), (5, "none  N=256")]:
+        c = ctypes.c_double()
+        _lib.check(L.vgg_syrk_ozaki_mma_rate(4096, mode, ctypes.byref(c), None), "rate")
+        n = 256 if mode & 1 else 128
+        print(f"kind::i8 M=128 {name} K=32: {c.value:7.1f} cycles/MMA -> {128 * n * 32 / c.value:7.0f} MAC/clk/SM")
+    sys.exit(0)
 Dpad = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 Kpad = int(sys.argv[2]) if len(sys.argv) > 2 else 640
 s = int(sys.argv[3]) if len(sys.argv) > 3 else 7

@@ -336,6 +336,55 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// tensor-pipe rate probe (tools/syrk_i8_check.py rate): back-to-back kind::i8 MMAs on resident shared-memory tiles,
+// cycles per MMA for the three shared-memory layouts / two N.  Data content is irrelevant.
+__global__ void __launch_bounds__(128, 1) oz_mma_rate_kernel(int iters, int mode, long long* out) {
+  extern __shared__ __align__(1024) uint8_t oz_smem[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(oz_smem), 1024));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tptr;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < 65536 / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(tiles)[i] = 0x01010101u;
+  fence_proxy_async();
+  if (threadIdx.x < 32) tmem_alloc(&tptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tptr;
+  if (threadIdx.x == 0) {
+    const uint32_t base = smem_u32(tiles);
+    const int n = (mode & 1) ? 256 : 128;
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
+    const int layout = mode >> 1;            // 0: SW64 (64 B rows), 1: SW128 (128 B rows), 2: no swizzle
+    const long long t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const uint32_t a = base + (uint32_t)(it & 1) * 32, b = base + 32768 + (uint32_t)(it & 1) * 32;
+      uint64_t da, db;
+      if (layout == 0) {
+        da = smem_desc_sw64(a); db = smem_desc_sw64(b);
+      } else if (layout == 1) {
+        da = (uint64_t)((a >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+        db = (uint64_t)((b >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+      } else {
+        da = (uint64_t)((a >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
+        db = (uint64_t)((b >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
+      }
+      umma_i8(tb, da, db, idesc, 1u);
+    }
+    umma_commit(&bar);
+    mbar_wait(&bar, 0);
+    out[0] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (threadIdx.x < 32) tmem_dealloc(tb, 512);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // host side: order groups and work list
 bool build_plan(int s, OzPlan* plan) {
@@ -498,6 +547,24 @@ int vgg_syrk_ozaki_workspace_bytes(int Kpad, int Dpad, int slices, size_t* bytes
   using namespace vgg;
   VGG_REQUIRE(bytes && Kpad > 0 && Dpad > 0 && Dpad % 128 == 0 && slices >= 3 && slices <= 7, "bad argument");
   *bytes = syrk_i8_workspace_bytes(Kpad, Dpad, slices);
+  return VGG_OK;
+}
+
+/* cycles per tcgen05.mma.kind::i8 (M=128, K=32) issued back to back; mode bit0: N=256 instead of 128, mode>>1: smem
+ * layout 0 = 64-byte swizzle, 1 = 128-byte swizzle, 2 = none.  out_cycles is a HOST pointer. */
+int vgg_syrk_ozaki_mma_rate(int iters, int mode, double* out_cycles, void* stream) {
+  using namespace vgg;
+  g_launch_count = 0;
+  VGG_REQUIRE(iters > 0 && out_cycles, "bad argument");
+  long long* d = nullptr;
+  VGG_CUDA_CHECK(cudaMalloc(&d, sizeof(long long)));
+  VGG_CUDA_CHECK(cudaFuncSetAttribute(oz_mma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 66 * 1024 + 1024));
+  oz_mma_rate_kernel<<<1, 128, 66 * 1024 + 1024, static_cast<cudaStream_t>(stream)>>>(iters, mode, d);
+  VGG_LAUNCH_CHECK();
+  long long h = 0;
+  VGG_CUDA_CHECK(cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  *out_cycles = (double)h / iters;
   return VGG_OK;
 }
 
