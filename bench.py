@@ -166,6 +166,48 @@ def run_reference(args):
 # GPU arm
 # --------------------------------------------------------------------------------------------------
 
+def syrk_roofline(D, K3, dev, clocks):
+    """Times vgg_syrk_ozaki (slice + tcgen05 SYRK) at this rank's Schur shape with CUDA events.  Algorithmic work =
+    28 int8 GEMM pairs x 2 K Dpad (Dpad+128)/2 ops on the lower tiles; peak = 148 SMs x 8192 MAC/clk (the kind::i8 rate
+    measured with N=256, tools/syrk_i8_check.py rate) x 2 x the SM clock sampled during the run."""
+    import ctypes
+    L = _lib.lib()
+    Dpad = (D + 2 + 127) // 128 * 128
+    Kpad = (K3 + 15) // 16 * 16
+    slices = 7
+    g = torch.Generator(device=dev).manual_seed(0)
+    Zt = torch.randn(Kpad, Dpad, dtype=torch.float64, device=dev, generator=g)
+    Zt[:, D:] = 0
+    C = torch.zeros(Dpad, Dpad, dtype=torch.float64, device=dev)
+    nb = ctypes.c_size_t()
+    _lib.check(L.vgg_syrk_ozaki_workspace_bytes(Kpad, Dpad, slices, ctypes.byref(nb)), "vgg_syrk_ozaki_workspace_bytes")
+    ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    call = lambda: _lib.check(L.vgg_syrk_ozaki(Kpad, Dpad, Zt.data_ptr(), C.data_ptr(), slices, ws.data_ptr(), ws.numel(), st),
+                              "vgg_syrk_ozaki")
+    for _ in range(3):
+        call()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    a.record()
+    for _ in range(reps):
+        call()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / reps
+    pairs = slices * (slices + 1) // 2
+    ops = pairs * 2.0 * Kpad * Dpad * (Dpad + 128) / 2
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    peak = 148 * 8192 * 2 * sm_mhz * 1e6 / 1e12
+    ach = ops / (ms * 1e-3) / 1e12
+    return {"kernel": "oz_slice_kernel + oz_syrk_kernel (tcgen05.mma kind::i8, 7 Ozaki slices)", "bound": "tensor",
+            "achieved": ach, "peak": peak, "unit": "TOP/s", "frac": ach / peak, "ms_per_call": ms,
+            "peak_source": "148 SMs x 8192 int8 MAC/clk/SM (measured kind::i8 N=256 issue rate) x sampled SM clock",
+            "fp64_equivalent_tflops": 2.0 * Kpad * Dpad * (Dpad + 128) / 2 / (ms * 1e-3) / 1e12,
+            "note": "time includes the column-max and slicing kernels; in the LM loop the column max is fused into z_build"}
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -313,6 +355,7 @@ def run_gpu(args):
 
     # ---- roofline of the fused residual+Jacobian+block kernel (the HBM-bound kernel of the path), live
     roof = None
+    roof_syrk = None
     cpu_base = None
     if rank == 0:
         peak, peak_src = load_peaks()
@@ -362,6 +405,11 @@ def run_gpu(args):
             del uv_s, mk_s, X_s
         except Exception as e:     # out of memory on a shared box: keep the C3-size number
             roof["scaled"] = {"error": str(e)[:200]}
+        # ---- tensor-core roofline of the Schur SYRK (the largest of this library's kernels per LM iteration), live
+        try:
+            roof_syrk = syrk_roofline(S_FRAMES * dc + ns, 3 * n_loc, dev, clocks)
+        except Exception as e:
+            roof_syrk = {"error": str(e)[:200]}
         if world == 1:
             v, dt = cpu_ba_sample(sc, extr, K, extra, pts, 2)
             tv, tdt = cpu_tri_sample(sc, 16)
@@ -381,8 +429,10 @@ def run_gpu(args):
                        "final_cost": final_cost},
             "tracks_per_s": tracks_per_s, "tri_ms_per_pass": tri_ms / args.steps, "tri_median_point_error": tri_median_err,
             "e2e": {"value": e2e_value, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu_base,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_syrk": roof_syrk,
+            "cpu_baseline": cpu_base,
         }
+        line["config"]["syrk"] = os.environ.get("VGG_SYRK", "ozaki:7") + " (default: tcgen05 kind::i8, 7 Ozaki slices, FP64-equivalent)"
         if hook is not None:
             line["config"]["allreduce_calls"] = hook.calls
             line["config"]["allreduce_bytes"] = hook.bytes

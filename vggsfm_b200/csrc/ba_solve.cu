@@ -55,6 +55,9 @@ int launch_extract_gvec(int S, int dc, int ns, int KR, const double* camrec, con
 int launch_gradmax(int D, int N, const double* gvec, const uint8_t* pconst, const double* g_p,
                    const uint8_t* point_const, double* scal, cudaStream_t st);
 
+size_t trsv_workspace_ints(int n);
+int launch_trsv_upper(int n, int lda, const double* A, const double* y, size_t y_stride, double* x, int* flags, int epoch,
+                      cudaStream_t st);
 size_t chol_workspace_doubles(int n);
 int chol_lower_inplace(int n, int lda, double* A, double* Ldiag, int* info, cudaStream_t st);
 
@@ -108,6 +111,7 @@ struct Layout {
   double *potrf_work;
   double *chol_diag;
   int *dev_info;
+  int *trsv_flags;
   uint8_t* oz_ws;    // int8 slices + scales of the tensor-core SYRK (csrc/syrk_i8.cu)
   size_t oz_bytes;
   size_t potrf_lwork;
@@ -170,6 +174,7 @@ static int make_layout(int S, int N, int model, int mode, void* base, size_t cap
   L->potrf_work = c.take<double>(potrf_lwork);
   L->chol_diag = c.take<double>(chol_workspace_doubles(L->D));
   L->dev_info = c.take<int>(4);
+  L->trsv_flags = c.take<int>(trsv_workspace_ints(L->D));
   L->oz_bytes = (L->Kpad <= (1 << 17)) ? syrk_i8_workspace_bytes(L->Kpad, L->Dpad, 7) : 0;
   c.off = align_up(c.off, 1024);
   L->oz_ws = c.take<uint8_t>(L->oz_bytes);
@@ -550,19 +555,28 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
         return VGG_ESOLVER;
       }
     } else {
-      cublasHandle_t cb = get_cublas();
-      if (!cb || cublasSetStream(cb, st) != CUBLAS_STATUS_SUCCESS) {
-        set_error("cublasCreate / cublasSetStream failed");
-        return VGG_ESOLVER;
-      }
+      static const bool lib_trsv = [] {
+        const char* e = getenv("VGG_TRSV");
+        return e && e[0] == 'c';                     // VGG_TRSV=cublas keeps the library call for A/B
+      }();
       VGG_CUDA_CHECK(cudaMemsetAsync(L.dev_info + 1, 0, sizeof(int), st));
-      if (cublasDtrsv(cb, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, D, Sraw, L.Dpad, Sraw + D, L.Dpad) !=
-          CUBLAS_STATUS_SUCCESS) {
-        set_error("cublasDtrsv failed to launch");
-        return VGG_ESOLVER;
+      if (lib_trsv || D > 7000) {                     // own kernel: one co-resident wave of D/64 CTAs
+        cublasHandle_t cb = get_cublas();
+        if (!cb || cublasSetStream(cb, st) != CUBLAS_STATUS_SUCCESS) {
+          set_error("cublasCreate / cublasSetStream failed");
+          return VGG_ESOLVER;
+        }
+        if (cublasDtrsv(cb, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, D, Sraw, L.Dpad, Sraw + D, L.Dpad) !=
+            CUBLAS_STATUS_SUCCESS) {
+          set_error("cublasDtrsv failed to launch");
+          return VGG_ESOLVER;
+        }
+        dcs = Sraw + D;
+        dcs_stride = (size_t)L.Dpad;
+      } else {
+        // own backward substitution (csrc/trsv.cu): one launch, block rows chained through flags
+        if ((rc = launch_trsv_upper(D, L.Dpad, Sraw, Sraw + D, (size_t)L.Dpad, L.bvec, L.trsv_flags, 1, st))) return rc;
       }
-      dcs = Sraw + D;
-      dcs_stride = (size_t)L.Dpad;
     }
     g_launch_count += 1;
     if ((rc = launch_cam_step(D, dcs, dcs_stride, L.sc_c, hdiag, gvec, prob->param_const, radius, opt.min_lm_diagonal,

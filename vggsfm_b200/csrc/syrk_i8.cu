@@ -39,6 +39,7 @@ constexpr int OZ_STAGE_TILES = 14;
 constexpr int OZ_STAGE_BYTES = OZ_STAGE_TILES * OZ_TILE_BYTES;   // 112 KB
 constexpr int OZ_THREADS = 320;                  // producer warp, MMA warp, 8 epilogue warps
 constexpr int OZ_MAX_PAIRS = 20;
+constexpr int OZ_PREFETCH = 4;                   // k blocks of L2 prefetch distance ahead of the bulk copies
 constexpr int OZ_MAX_GROUPS = 3;
 constexpr int OZ_EXPO_BAD = INT32_MIN;           // column holds a non-finite value
 constexpr size_t OZ_SMEM_BYTES = (size_t)OZ_STAGES * OZ_STAGE_BYTES + 1024 + 128;
@@ -166,6 +167,10 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
 }
+// pull a global range into L2 ahead of the bulk copy that will read it (hides the HBM latency of first-touch tiles)
+__device__ __forceinline__ void l2_prefetch(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -223,6 +228,13 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
         const OzGroup& g = plan.g[wk.group];
         const bool diag = wk.bi == wk.bj;
         for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
+          const int kpf = kb + OZ_PREFETCH;
+          if (kpf < wk.kb1) {
+            for (int i = 0; i < g.n_a; ++i)
+              l2_prefetch(slices + (size_t)g.a_slice[i] * slice_stride + ((size_t)wk.bi * KB + kpf) * OZ_TILE_BYTES, OZ_TILE_BYTES);
+            for (int i = 0; i < (diag ? 0 : g.n_b); ++i)
+              l2_prefetch(slices + (size_t)g.b_slice[i] * slice_stride + ((size_t)wk.bj * KB + kpf) * OZ_TILE_BYTES, OZ_TILE_BYTES);
+          }
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* dst = tiles + (size_t)stage * OZ_STAGE_BYTES;
           mbar_expect_tx(&full[stage], (uint32_t)(g.n_a + (diag ? 0 : g.n_b)) * OZ_TILE_BYTES);

@@ -1,0 +1,165 @@
+// Backward substitution U x = y for the reduced camera system (n = 2402 at 400 frames), one launch.
+//
+// After the bordered factorisation (csrc/ba_solve.cu) the forward substitution is already done; what is left is
+// x = L^-T y.  The library call for it (cublasDtrsv, 0.24 ms at n = 2402) is bound by its dependency chain, not by the
+// 23 MB it reads.  Here block row b (64 rows) belongs to CTA b of one co-resident grid (38 CTAs):
+//   * every CTA inverts its 64 x 64 diagonal block in shared memory while it would otherwise wait (independent of x);
+//   * it then walks the block columns j = last .. b+1: poll x_j itself (the output buffer is pre-filled with a sentinel
+//     NaN pattern, so the data is its own flag: no fence, no second round trip), acc -= U[b][j] x_j, with the next tile
+//     already in registers (tiles do not depend on x, only x_j does);
+//   * x_b = inv(U_bb) acc (four threads per row), stored element-wise with volatile 8-byte stores.
+// Block rows are handed out in reverse CTA order, so a CTA waits only for CTAs the hardware dispatched before it.
+// Critical path per block: one 64 x 64 tile update + one 64 x 64 mat-vec + one flag hand-off (~1.5 us), 38 blocks.
+// U is the row-major upper triangle (what a column-major LOWER potrf leaves in a row-major buffer): U[i][j] = A[i*lda+j].
+#include "common.cuh"
+
+namespace vgg {
+
+namespace {
+
+constexpr int TS_NB = 64;
+constexpr int TS_THREADS = 256;
+constexpr unsigned long long TS_SENTINEL = 0xffffffffffffffffull;   // x is pre-filled with this NaN pattern
+
+__global__ void __launch_bounds__(TS_THREADS, 1)
+    trsv_upper_kernel(int n, int lda, const double* __restrict__ A, const double* __restrict__ y, size_t y_stride,
+                      double* __restrict__ x, int* flags, int epoch) {
+  extern __shared__ __align__(16) double ts_smem[];
+  double(*Ud)[TS_NB + 1] = reinterpret_cast<double(*)[TS_NB + 1]>(ts_smem);                            // diagonal block
+  double(*Vi)[TS_NB + 1] = reinterpret_cast<double(*)[TS_NB + 1]>(ts_smem + TS_NB * (TS_NB + 1));      // its inverse
+  double* xs = ts_smem + 2 * TS_NB * (TS_NB + 1);
+  double* accs = xs + TS_NB;
+  const int nb = gridDim.x;
+  const int b = nb - 1 - (int)blockIdx.x;     // CTA 0 owns the last block row: a CTA only ever waits for lower-numbered CTAs
+  const int r0 = b * TS_NB;
+  const int rows = min(TS_NB, n - r0);
+  const int tid = threadIdx.x;
+  const int r = tid >> 2, seg = tid & 3;      // row of the block, 16-column segment
+
+  // ---- diagonal block and its inverse (upper triangular; padded rows/cols = identity)
+  for (int e = tid; e < TS_NB * TS_NB; e += TS_THREADS) {
+    const int i = e / TS_NB, j = e % TS_NB;
+    double v = (i == j) ? 1.0 : 0.0;
+    if (i < rows && j < rows && j >= i) v = A[(size_t)(r0 + i) * lda + r0 + j];
+    Ud[i][j] = v;
+  }
+  __syncthreads();
+  if (tid < TS_NB) xs[tid] = 1.0 / Ud[tid][tid];       // reciprocal pivots (xs is free until the first hop)
+  __syncthreads();
+  if (tid < TS_NB) {
+    // column tid of inv(U): back substitution U v = e_tid (entries below the diagonal are zero); two partial sums
+    const int c = tid;
+    for (int i = TS_NB - 1; i >= 0; --i) {
+      double v = 0.0;
+      if (i <= c) {
+        double s0 = (i == c) ? 1.0 : 0.0, s1 = 0.0;
+        int k = i + 1;
+        for (; k + 1 <= c; k += 2) {
+          s0 = fma(-Ud[i][k], Vi[k][c], s0);
+          s1 = fma(-Ud[i][k + 1], Vi[k + 1][c], s1);
+        }
+        if (k <= c) s0 = fma(-Ud[i][k], Vi[k][c], s0);
+        v = (s0 + s1) * xs[i];
+      }
+      Vi[i][c] = v;
+    }
+  }
+  __syncthreads();
+  // ---- right-hand side rows of this block
+  if (tid < TS_NB) accs[tid] = (tid < rows) ? y[(size_t)(r0 + tid) * y_stride] : 0.0;
+  __syncthreads();
+
+  // ---- block columns to the right, last first; tile j+... prefetched into registers before its x is awaited
+  // three tiles are kept in flight in registers (tiles do not depend on x, only x_j does)
+  double t0[16], t1[16], t2[16];
+  auto load_tile = [&](double (&tile)[16], int j) {
+    const int c0 = j * TS_NB + seg * 16;
+    const double* src = A + (size_t)(r0 + (r < rows ? r : 0)) * lda + c0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) tile[k] = (j > b && r < rows && c0 + k < n) ? src[k] : 0.0;
+  };
+  double acc = 0.0;                            // this thread's partial of row r (its 16-column segment), over all j
+  auto hop = [&](const double (&tile)[16], int j) {
+    // x_j arrives as data: the buffer was pre-filled with a sentinel NaN pattern, every element is polled by one thread
+    // (8-byte stores are single-copy atomic, so no flag, no fence and no second round trip are needed)
+    if (tid < TS_NB) {
+      double v = 0.0;
+      if (j * TS_NB + tid < n) {
+        const volatile unsigned long long* src = reinterpret_cast<const volatile unsigned long long*>(&x[j * TS_NB + tid]);
+        unsigned long long bits;
+        do {
+          bits = *src;
+        } while (bits == TS_SENTINEL);
+        v = __longlong_as_double((long long)bits);
+      }
+      xs[tid] = v;
+    }
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) s = fma(tile[k], xs[seg * 16 + k], s);
+    acc += s;
+    __syncthreads();                           // xs is rewritten in the next round
+  };
+  int j = nb - 1;
+  load_tile(t0, j);
+  load_tile(t1, j - 1);
+  load_tile(t2, j - 2);
+  while (j > b) {
+    hop(t0, j);
+    load_tile(t0, j - 3);
+    if (--j <= b) break;
+    hop(t1, j);
+    load_tile(t1, j - 3);
+    if (--j <= b) break;
+    hop(t2, j);
+    load_tile(t2, j - 3);
+    --j;
+  }
+  // reduce the four segments of a row, subtract from the right-hand side
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  if (seg == 0) accs[r] -= acc;
+  __syncthreads();
+  // ---- x_b = inv(U_bb) acc: four threads per row, published element by element
+  {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int c = seg * 16 + k;
+      s = fma(c >= r ? Vi[r][c] : 0.0, accs[c], s);
+    }
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    if (seg == 0 && r < rows) {
+      unsigned long long bits = (unsigned long long)__double_as_longlong(s);
+      if (s != s) bits = 0x7ff8000000000000ull;        // never publish the sentinel pattern
+      *reinterpret_cast<volatile unsigned long long*>(&x[r0 + r]) = bits;
+    }
+  }
+}
+
+}  // namespace
+
+size_t trsv_workspace_ints(int n) { return (size_t)((n + TS_NB - 1) / TS_NB) + 1; }
+
+// x = U^-1 y; flags: workspace of trsv_workspace_ints(n) ints that must be zero before the first call and is
+// otherwise left to this function (the last int counts calls so that no reset is needed between them).
+int launch_trsv_upper(int n, int lda, const double* A, const double* y, size_t y_stride, double* x, int* flags,
+                      int epoch, cudaStream_t st) {
+  const int nb = (n + TS_NB - 1) / TS_NB;
+  VGG_REQUIRE(nb <= 120, "trsv_upper: n too large for one co-resident wave");
+  const size_t smem = sizeof(double) * (2 * TS_NB * (TS_NB + 1) + 2 * TS_NB);
+  static bool attr = false;
+  if (!attr) {
+    VGG_CUDA_CHECK(cudaFuncSetAttribute(trsv_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  (void)flags;
+  VGG_CUDA_CHECK(cudaMemsetAsync(x, 0xFF, sizeof(double) * (size_t)n, st));     // sentinel fill: x_j is polled as data
+  trsv_upper_kernel<<<nb, TS_THREADS, smem, st>>>(n, lda, A, y, y_stride, x, flags, epoch);
+  VGG_LAUNCH_CHECK();
+  return VGG_OK;
+}
+
+}  // namespace vgg
