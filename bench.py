@@ -52,19 +52,27 @@ class ClockSampler:
         self.index, self.rows, self._stop, self.th = index, [], threading.Event(), None
         self.err = None
 
-    def start(self):
+    def prepare(self):
         try:
             import pynvml
             pynvml.nvmlInit()
             self.nv = pynvml
             self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
-            self.th = threading.Thread(target=self._run, daemon=True)
-            self.th.start()
+            pynvml.nvmlDeviceGetClockInfo(self.h, pynvml.NVML_CLOCK_SM)     # first query pays the one-time cost here
         except Exception as e:       # NVML missing: report it, do not fail the bench
             self.err = str(e)[:100]
+            self.nv = None
+
+    def start(self):
+        if getattr(self, "nv", None) is None:
+            return
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
 
     def _run(self):
         nv = self.nv
+        if self._stop.wait(0.04):          # first sample 40 ms into the region, then every 250 ms
+            return
         while not self._stop.is_set():
             try:
                 sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
@@ -167,6 +175,8 @@ def run_reference(args):
 # --------------------------------------------------------------------------------------------------
 
 def syrk_roofline(D, K3, dev, clocks):
+    import torch
+    from vggsfm_b200 import _lib
     """Times vgg_syrk_ozaki (slice + tcgen05 SYRK) at this rank's Schur shape with CUDA events.  Algorithmic work =
     28 int8 GEMM pairs x 2 K Dpad (Dpad+128)/2 ops on the lower tiles; peak = 148 SMs x 8192 MAC/clk (the kind::i8 rate
     measured with N=256, tools/syrk_i8_check.py rate) x 2 x the SM clock sampled during the run."""
@@ -270,12 +280,15 @@ def run_gpu(args):
 
     # ---- timed region 1: BA
     launches = 0
-    for _ in range(args.warmup):
-        ba_step()
     sampler = ClockSampler(local)
+    if rank == 0 and os.environ.get("VGG_BENCH_NOCLOCKS") != "1":
+        sampler.prepare()                  # NVML init + device handle outside the timed region
+    for _ in range(args.warmup):
+        flush.fill_(1.0)                   # also loads the fill kernel's module before the timed region
+        ba_step()
+    barrier()
     if rank == 0:
         sampler.start()
-    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     its = 0
@@ -445,7 +458,7 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     args = ap.parse_args()
