@@ -84,3 +84,50 @@ def test_align_next_window_and_filter(cuda_dev):
                                                                  to_dev(got, dev), K1, ex1)
     assert pts.shape[0] == int(valid.sum()) == trk.shape[1] == msk.shape[1]
     assert bool((msk.sum(0) >= 3).all()) and int(valid.sum()) > 0.9 * P
+
+
+def test_joint_BA(cuda_dev):
+    """video.joint_BA (video_runner.py:494-541): shared camera refined, outlier observations cleared by the 2 px filter,
+    scene normalised (camera-centre extent 5), reprojection RMS at the noise floor."""
+    import torch
+    from vggsfm_b200 import triangulation as tri
+    from vggsfm_b200 import video
+    S, P = 20, 600
+    sc = make_scene(S, P, "SIMPLE_RADIAL", seed=41, invisible_frac=0.15, outlier_frac=0.01)
+    extr0, K0, ex0, pts0 = perturb(sc, rot_deg=0.3, trans_frac=0.01, focal_frac=0.02, point_sigma=0.02, seed=42)
+    dev = cuda_dev
+    pts, E, K, ex, masks, valid = video.joint_BA(to_dev(pts0, dev), to_dev(extr0, dev), to_dev(K0[:1], dev), to_dev(ex0[:1], dev),
+                                                 to_dev(sc.tracks, dev), to_dev(sc.mask, dev), camera_type="SIMPLE_RADIAL")
+    assert K.shape == (1, 3, 3) and ex.shape == (1, 1) and masks.shape == (S, P) and valid.shape == (P,)
+    assert abs(K[0, 0, 0].item() - 1000.0) < 3.0 and abs(ex[0, 0].item() - 0.05) < 0.01
+    assert int(valid.sum()) > 0.97 * P
+    assert not bool(masks[:, ~valid].any()) and not bool((masks & ~to_dev(sc.mask, dev)).any())
+    uvh = tri.project_3D_points(pts, E, K.expand(S, -1, -1), ex.expand(S, -1))
+    err = ((uvh - to_dev(sc.tracks, dev).double()) ** 2).sum(-1)
+    assert torch.sqrt(err[masks].mean()).item() < 0.5 and err[masks].max().item() <= 4.0 + 1e-9      # 2 px filter
+    dropped = to_dev(sc.mask, dev) & ~masks & valid[None]
+    assert int(dropped.sum()) > 0.5 * 0.01 * S * P * 0.85                                          # the planted outliers
+    En = E.cpu().numpy()
+    C = -np.einsum("sji,sj->si", En[:, :, :3], En[:, :, 3])
+    Cs = np.sort(C.astype(np.float32), axis=0)
+    ext = np.linalg.norm(Cs[int(0.9 * (S - 1))] - Cs[int(0.1 * (S - 1))])
+    assert abs(ext - 5.0) < 1e-3, ext
+
+
+def test_pose_refinement_degenerate_inputs(cuda_dev):
+    """No correspondences / no frames: nothing is touched, every frame reports FEW_INLIERS."""
+    import torch
+    from vggsfm_b200 import pose_refinement as pr
+    poses = torch.eye(3, 4, dtype=torch.float64, device=cuda_dev).repeat(3, 1, 1).contiguous()
+    intr = torch.tensor([[500.0, 320, 240, 0]] * 3, dtype=torch.float64, device=cuda_dev)
+    rep = pr.pose_refinement_batched(poses, intr, torch.zeros(0, 3, dtype=torch.float64, device=cuda_dev),
+                                     torch.zeros(3, 0, 2, device=cuda_dev), torch.zeros(3, 0, dtype=torch.bool, device=cuda_dev),
+                                     torch.full((3,), 7, dtype=torch.uint8, device=cuda_dev), 0)
+    assert rep.termination.tolist() == [7, 7, 7] and rep.inlier_used.shape == (3, 0)
+    assert torch.equal(poses[0], torch.eye(3, 4, dtype=torch.float64, device=cuda_dev))
+    # all correspondences masked out: the kernel runs and leaves the frame alone
+    X = torch.randn(50, 3, dtype=torch.float64, device=cuda_dev) + torch.tensor([0, 0, 5.0], dtype=torch.float64, device=cuda_dev)
+    rep = pr.pose_refinement_batched(poses, intr, X, torch.zeros(3, 50, 2, device=cuda_dev),
+                                     torch.zeros(3, 50, dtype=torch.bool, device=cuda_dev),
+                                     torch.full((3,), 7, dtype=torch.uint8, device=cuda_dev), 0)
+    assert rep.termination.tolist() == [7, 7, 7] and int(rep.num_inliers.sum()) == 0

@@ -57,6 +57,11 @@ def pose_refinement_batched(poses, intr4, points3D, tracks2D, inlier, frame_flag
     L = _lib.lib()
     dev = poses.device
     S, P = inlier.shape
+    if S == 0 or P == 0:                     # nothing to refine: every frame is reported as having too few inliers
+        z = torch.zeros(S, dtype=torch.float64, device=dev)
+        return PoseReport(torch.zeros(S, dtype=torch.int32, device=dev), torch.zeros(S, dtype=torch.int32, device=dev),
+                          torch.full((S,), 7, dtype=torch.int32, device=dev), z, z.clone(),
+                          torch.zeros(S, dtype=torch.int64, device=dev), torch.zeros(S, P, dtype=torch.bool, device=dev))
     assert poses.dtype == torch.float64 and poses.is_contiguous() and intr4.dtype == torch.float64 and intr4.is_contiguous()
     pts = points3D.double().contiguous()
     uv = tracks2D.float().contiguous()

@@ -75,3 +75,41 @@ def window_bundle_adjustment(window_points_all, extrinsics, intrinsics, extra_pa
     free_obs = window_inlier_masks_all.bool()[:, valid_idx]
     reduced = int(free_obs[1:].sum()) + int((free_obs[:1] & ~const_points[valid_idx][None]).sum())
     return out, extr, summary, reduced > 0
+
+
+def joint_BA(points3D, extrinsics, intrinsics, extra_params, tracks, masks, camera_type="SIMPLE_PINHOLE", reproj_error=2.0,
+             tri_angle=1.5, normalize=True):
+    """Tensor form of VideoRunner.joint_BA (video_runner.py:494-541): all frames so far, all points, ONE shared
+    camera, default Ceres options through the COLMAP controller (gauge + negative-depth filter + Normalize), then the
+    2 px / 1.5 degree point filter and a second normalisation.  The runner keeps this state in its point_dict /
+    frame_dict; here it is the dense [S,P] form those dicts unroll to.
+
+    points3D [P,3], extrinsics [S,3,4], intrinsics [1,3,3], extra_params [1,1]|None, tracks [S,P,2], masks [S,P].
+    Returns (points3D [P,3], extrinsics [S,3,4], intrinsics [1,3,3], extra_params [1,1]|None, masks [S,P],
+    valid_points [P]) -- filtered observations are cleared in `masks`, deleted points are False in `valid_points`.
+    The observation filter is the reference's own filter_all_points3D rule (reprojection <= reproj_error and positive
+    depth per observation, >= 2 survivors, one camera pair with >= tri_angle), which is what COLMAP's
+    ObservationManager.filter_all_points3D + filter_observations_with_negative_depth compute [3P-memory]."""
+    S, P = masks.shape
+    K = intrinsics.expand(S, -1, -1)
+    ex = extra_params.expand(S, -1) if extra_params is not None else None
+    poses, pts = extrinsics.double(), points3D.double()
+    if normalize:
+        poses, pts = ba.normalize(poses, pts, 5.0, 0.1, 0.9)                             # :503-504
+    pts_o, extr, K_o, ex_o, valid_idx, summary = ba.bundle_adjustment(
+        pts, poses, K, ex, tracks, masks, shared_camera=True, camera_type=camera_type, options=ba.default_options(),
+        filter_reconstruction=False)
+    out = pts.clone()
+    out[valid_idx] = pts_o
+    _, detail = tri.filter_all_points3D(out, tracks, extr, K_o, extra_params=ex_o, max_reproj_error=reproj_error,
+                                        min_tri_angle=tri_angle, check_triangle=False, return_detail=True, hard_max=-1)
+    in_problem = torch.zeros(P, dtype=torch.bool, device=masks.device)
+    in_problem[valid_idx] = True
+    new_masks = masks.bool() & detail & in_problem[None]
+    ok_tri, _ = tri.filter_all_points3D(out, tracks, extr, K_o, extra_params=ex_o, max_reproj_error=reproj_error,
+                                        min_tri_angle=tri_angle, check_triangle=True, hard_max=-1)
+    valid_points = (new_masks.sum(dim=0) >= 2) & ok_tri
+    new_masks = new_masks & valid_points[None]
+    if normalize:
+        extr, out = ba.normalize(extr, out, 5.0, 0.1, 0.9, valid_points)                 # :513-514
+    return out, extr, K_o[:1].clone(), (ex_o[:1].clone() if ex_o is not None else None), new_masks, valid_points
