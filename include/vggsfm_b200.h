@@ -130,7 +130,7 @@ int vgg_ba_schur(const vgg_ba_problem* prob, const double* camrec, const double*
 int vgg_cholesky_lower(int n, int lda, double* A, void* workspace, size_t ws_bytes, int* info_host, void* stream);
 
 /* The same SYRK step on the tensor cores (csrc/syrk_i8.cu): Cmat[Dpad,Dpad] -= Zt^T Zt for Zt double [Kpad,Dpad]
- * (Dpad a multiple of 128, Kpad <= 131072), FP64-equivalent through `slices` (3..7; 7 = 54 fractional bits) int8
+ * (Dpad a multiple of 128), FP64-equivalent through `slices` (3..7; 7 = 54 fractional bits) int8
  * Ozaki slices on tcgen05.mma kind::i8 with exact int32 accumulation in TMEM.  Both triangles are written.
  * Selected inside vgg_ba_solve by VGG_SYRK=ozaki[:slices]; exposed for the parity tests and profiling. */
 int vgg_syrk_ozaki_workspace_bytes(int Kpad, int Dpad, int slices, size_t* bytes);

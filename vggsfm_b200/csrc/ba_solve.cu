@@ -175,7 +175,7 @@ static int make_layout(int S, int N, int model, int mode, void* base, size_t cap
   L->chol_diag = c.take<double>(chol_workspace_doubles(L->D));
   L->dev_info = c.take<int>(4);
   L->trsv_flags = c.take<int>(trsv_workspace_ints(L->D));
-  L->oz_bytes = (L->Kpad <= (1 << 17)) ? syrk_i8_workspace_bytes(L->Kpad, L->Dpad, 7) : 0;
+  L->oz_bytes = syrk_i8_workspace_bytes(L->Kpad, L->Dpad, 7);
   c.off = align_up(c.off, 1024);
   L->oz_ws = c.take<uint8_t>(L->oz_bytes);
   L->bytes = align_up(c.off, 256);

@@ -7,7 +7,7 @@
 //      x = Z 2^-e_d is rounded to B = 8s-2 fractional bits and written as s balanced base-256 digits
 //      (int8 "slices", most significant first): x = 2^-B sum_p d_p 256^(s-p)          (oz_slice_kernel)
 //   2. (Z^T Z)_ij = 2^(e_i+e_j-2B) sum_t 256^(2s-t) C_t,  C_t = sum_{p+q=t} sum_k d_p[k][i] d_q[k][j]:
-//      every C_t is an exact int32 (|d| <= 128, K <= 2^17: |C_t| < 2^31 for up to 7 pairs); orders t > s+1 are below
+//      every C_t is an exact int32 (|d| <= 128, at most 7 pairs and 16384 k per work item: |C_t| < 2^31); orders t > s+1 are below
 //      the rounding of step 1 and are dropped, leaving s(s+1)/2 int8 GEMMs (28 for s = 7)  (oz_syrk_kernel)
 //   3. the epilogue recombines the C_t of a tile in FP64 registers and adds -value into Sraw with f64 RED
 //      (or multimem.red in fabric mode), exactly like the DMMA kernel's epilogue.
@@ -39,6 +39,7 @@ constexpr int OZ_STAGE_TILES = 14;
 constexpr int OZ_STAGE_BYTES = OZ_STAGE_TILES * OZ_TILE_BYTES;   // 112 KB
 constexpr int OZ_THREADS = 320;                  // producer warp, MMA warp, 8 epilogue warps
 constexpr int OZ_MAX_PAIRS = 20;
+constexpr int OZ_MAX_ITEM_KB = 256;               // k blocks per work item: 7 pairs x 128^2 x 256 x 64 < 2^31 (exact int32 accumulators)
 constexpr int OZ_PREFETCH = 4;                   // k blocks of L2 prefetch distance ahead of the bulk copies
 constexpr int OZ_MAX_GROUPS = 3;
 constexpr int OZ_EXPO_BAD = INT32_MIN;           // column holds a non-finite value
@@ -454,6 +455,8 @@ struct OzHostState {
 };
 thread_local OzHostState g_oz;
 
+int oz_max_parts(int KB) { return std::max(8, (KB + OZ_MAX_ITEM_KB - 1) / OZ_MAX_ITEM_KB); }
+
 size_t oz_workspace_bytes(int Kpad, int Dpad, int s) {
   const int KB = (Kpad + OZ_BK - 1) / OZ_BK;
   const int nb = Dpad / OZ_BM;
@@ -461,7 +464,7 @@ size_t oz_workspace_bytes(int Kpad, int Dpad, int s) {
   bytes += align_up((size_t)Dpad * 8, 256);                                   // amax
   bytes += align_up((size_t)Dpad * 4, 256);                                   // expo
   bytes += align_up((size_t)Dpad * 8, 256);                                   // pow2
-  bytes += align_up((size_t)nb * (nb + 1) / 2 * OZ_MAX_GROUPS * 8 * sizeof(OzWork), 256);   // work list (upper bound)
+  bytes += align_up((size_t)nb * (nb + 1) / 2 * OZ_MAX_GROUPS * oz_max_parts(KB) * sizeof(OzWork), 256);   // work list (upper bound)
   bytes += align_up((size_t)s * nb * KB * OZ_TILE_BYTES, 1024) + 1024;        // slices
   return bytes;
 }
@@ -483,7 +486,6 @@ int syrk_i8_reset_amax(void* ws, int Dpad, cudaStream_t st) {
 int launch_syrk_i8(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t mc_off, int s, void* ws,
                    size_t ws_bytes, cudaStream_t st, bool amax_ready) {
   VGG_REQUIRE(Dpad % OZ_BM == 0, "syrk_i8: Dpad must be a multiple of 128");
-  VGG_REQUIRE((long long)Kpad <= (1 << 17), "syrk_i8: K too large for exact int32 accumulation");
   VGG_REQUIRE(ws_bytes >= oz_workspace_bytes(Kpad, Dpad, s), "syrk_i8: workspace too small");
   const int KB = (Kpad + OZ_BK - 1) / OZ_BK;
   const int nb = Dpad / OZ_BM;
@@ -506,6 +508,7 @@ int launch_syrk_i8(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t
         for (int g = 0; g < hs.plan.n_groups; ++g) {
           const long long cost = (long long)hs.plan.g[g].n_pairs * KB;
           int parts = (int)std::min<long long>(8, std::max<long long>(1, (cost + target / 2) / target));
+          parts = std::max(parts, (KB + OZ_MAX_ITEM_KB - 1) / OZ_MAX_ITEM_KB);      // int32 accumulators stay exact
           parts = std::min(parts, KB);
           for (int p = 0; p < parts; ++p) {
             OzWork wk{bi, bj, g, (int)((long long)KB * p / parts), (int)((long long)KB * (p + 1) / parts)};
@@ -528,7 +531,7 @@ int launch_syrk_i8(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t
   unsigned long long* amax = c.take<unsigned long long>(Dpad);
   int* expo = c.take<int>(Dpad);
   double* pow2 = c.take<double>(Dpad);
-  OzWork* work_d = c.take<OzWork>((size_t)nb * (nb + 1) / 2 * OZ_MAX_GROUPS * 8);
+  OzWork* work_d = c.take<OzWork>((size_t)nb * (nb + 1) / 2 * OZ_MAX_GROUPS * oz_max_parts(KB));
   c.off = align_up(c.off, 1024);
   int8_t* slices = reinterpret_cast<int8_t*>(c.base + c.off);
   const size_t slice_stride = (size_t)nb * KB * OZ_TILE_BYTES;
