@@ -341,14 +341,19 @@ run_ba = bundle_adjustment   # the name BASELINE.json's north_star uses for this
 class Reconstruction:
     """Tensor-backed stand-in for the ``pycolmap.Reconstruction`` the reference returns as the last tuple
     element (triangulation.py:1073,1208).  Holds what downstream code reads back through
-    pycolmap_to_batch_matrix (tensor_to_pycolmap.py:163-214); the COLMAP binary writer is listed as next
-    in DESIGN.md section 8."""
+    pycolmap_to_batch_matrix (tensor_to_pycolmap.py:163-214) and writes the COLMAP binary model (``.write``)."""
 
     def __init__(self, points3D, extrinsics, intrinsics, extra_params, tracks, masks, image_size, camera_type,
                  shared_camera, summary=None):
         self.points3D_xyz, self.extrinsics, self.intrinsics, self.extra_params = points3D, extrinsics, intrinsics, extra_params
         self.tracks, self.masks, self.image_size = tracks, masks, image_size
         self.camera_type, self.shared_camera, self.summary = camera_type, shared_camera, summary
+        self.points3D_rgb = None
+
+    def write(self, path):
+        """``pycolmap.Reconstruction.write(path)``: cameras.bin / images.bin / points3D.bin (vggsfm_b200/colmap_io.py)."""
+        from .colmap_io import write_reconstruction
+        write_reconstruction(self, path)
 
     def num_points3D(self):
         return int(self.points3D_xyz.shape[0])
