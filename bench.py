@@ -414,7 +414,10 @@ def run_gpu(args):
             ab_s = algo_bytes(S_FRAMES, NS_)
             ach_s = ab_s / (ms_s * 1e-3) / 1e9
             roof["scaled"] = {"workload": "400 x 131072 tracks", "achieved": ach_s, "frac": ach_s / peak,
-                              "bytes_per_launch": ab_s, "ms_per_launch": ms_s}
+                              "bytes_per_launch": ab_s, "ms_per_launch": ms_s,
+                              # dram__bytes_read.sum + dram__bytes_write.sum of this launch shape from the ncu --set full
+                              # capture kept in profiles/r01_ncu_full_summary_k1_scaled.txt (0.58 GB + 7.51 GB)
+                              "traffic": 8.09e9}
             del uv_s, mk_s, X_s
         except Exception as e:     # out of memory on a shared box: keep the C3-size number
             roof["scaled"] = {"error": str(e)[:200]}

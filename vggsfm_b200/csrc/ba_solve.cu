@@ -202,6 +202,8 @@ static cublasHandle_t get_cublas() {
   return h;
 }
 
+// Doubles of device scratch the factorisation needs at order D+1 (bordered system): the larger of the 32-bit
+// cusolverDnDpotrf and the 64-bit cusolverDnXpotrf requirement, so one carved region serves either call.
 static int potrf_lwork(int D, int Dpad, size_t* lwork) {
   cusolverDnHandle_t h = get_cusolver();
   if (!h) {
@@ -213,7 +215,14 @@ static int potrf_lwork(int D, int Dpad, size_t* lwork) {
     set_error("cusolverDnDpotrf_bufferSize failed");
     return VGG_ESOLVER;
   }
-  *lwork = (size_t)lw;
+  size_t need = (size_t)lw;
+  static thread_local cusolverDnParams_t xp = nullptr;
+  if (!xp) cusolverDnCreateParams(&xp);
+  size_t db = 0, hb = 0;
+  if (xp && cusolverDnXpotrf_bufferSize(h, xp, CUBLAS_FILL_MODE_LOWER, D + 1, CUDA_R_64F, nullptr, Dpad, CUDA_R_64F, &db, &hb) ==
+                CUSOLVER_STATUS_SUCCESS)
+    need = need > (db + 7) / 8 ? need : (db + 7) / 8;
+  *lwork = need;
   return VGG_OK;
 }
 
@@ -521,7 +530,7 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
     const int nfac = D + 1;
     if (cm == 0) {
       static thread_local cusolverDnParams_t xp = nullptr;
-      static thread_local void* xdev = nullptr;
+      static thread_local void* xdev_fallback = nullptr;
       static thread_local void* xhost = nullptr;
       static thread_local size_t xdev_b = 0, xhost_b = 0;
       if (!xp) cusolverDnCreateParams(&xp);
@@ -531,7 +540,13 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
         set_error("cusolverDnXpotrf_bufferSize failed");
         return VGG_ESOLVER;
       }
-      if (db > xdev_b) { if (xdev) cudaFree(xdev); VGG_CUDA_CHECK(cudaMalloc(&xdev, db)); xdev_b = db; }
+      // device scratch comes out of the caller's workspace (sized by potrf_lwork); the cudaMalloc below only runs if
+      // a library version asks for more at solve time than it reported when the workspace was sized
+      void* xdev = L.potrf_work;
+      if (db > L.potrf_lwork * sizeof(double)) {
+        if (db > xdev_b) { if (xdev_fallback) cudaFree(xdev_fallback); VGG_CUDA_CHECK(cudaMalloc(&xdev_fallback, db)); xdev_b = db; }
+        xdev = xdev_fallback;
+      }
       if (hb > xhost_b) { free(xhost); xhost = malloc(hb); xhost_b = hb; }
       if (cusolverDnXpotrf(cs, xp, uplo, nfac, CUDA_R_64F, Sraw, L.Dpad, CUDA_R_64F, xdev, db, xhost, hb, L.dev_info) !=
           CUSOLVER_STATUS_SUCCESS) {
