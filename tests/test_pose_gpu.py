@@ -172,3 +172,13 @@ def test_sample_features4d(cuda_dev):
     got = sample_features4d(inp.to(cuda_dev), coords.to(cuda_dev)).cpu()
     assert got.shape == (B, R, C)
     assert (got - ref).abs().max().item() < 2e-5
+
+
+def test_sample_features4d_reference_golden(cuda_dev):
+    """Same kernel against the output of the reference's own sample_features4d (tools/make_golden_host.py)."""
+    import os
+    import torch
+    from vggsfm_b200.corr import sample_features4d
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "host_sample_features4d.npz"))
+    got = sample_features4d(torch.from_numpy(d["input"]).to(cuda_dev), torch.from_numpy(d["coords"]).to(cuda_dev)).cpu().numpy()
+    assert got.shape == d["out"].shape and np.abs(got - d["out"]).max() < 2e-5
