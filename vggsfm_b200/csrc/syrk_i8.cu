@@ -350,6 +350,256 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
 }
 
 
+
+// ---------------------------------------------------------------------------------------------------------
+// 3b. CTA-pair variant (VGG_SYRK_PAIR=1): a cluster of two CTAs owns two row blocks (bi0, bi1) of one column block bj and
+// issues tcgen05.mma.cta_group::2 (M = 256 = 128 rows per CTA, N = 128, K = 32).  Each CTA stages its own A tiles and
+// only HALF of every B tile (64 of the 128 rows: the first / second 4 KB of the pre-swizzled tile image), so per-CTA
+// shared-memory and L2->SM traffic drop by a quarter and the MMA issues at the full-rate M=256 shape.
+//   * loads: every CTA's producer fills its own stage and its own full barrier; the peer's warp 1 relays "my stage is
+//     full" to the leader with a remote mbarrier arrive (a 1-D bulk copy cannot signal another CTA's barrier);
+//   * MMAs are issued by the leader only; tcgen05.commit multicasts the arrival to both CTAs' empty / tmem_full barriers;
+//   * both epilogues read their own TMEM (their 128 rows) and arrive on the leader's tmem_empty barrier.
+struct OzWork2 {
+  int bi0, bi1, bj, group, kb0, kb1, dup;       // dup: bi1 repeats bi0 (odd tile count in a column); CTA 1 discards
+};
+constexpr int OZ2_STAGE_BYTES = 7 * OZ_TILE_BYTES + 7 * (OZ_TILE_BYTES / 2);   // 84 KB
+constexpr int OZ2_STAGES = 2;
+constexpr size_t OZ2_SMEM_BYTES = (size_t)OZ2_STAGES * OZ2_STAGE_BYTES + 1024 + 256;
+constexpr uint32_t OZ_IDESC2 = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP_C:\n"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_C;\n"
+      "bra WAIT_LOOP_C;\n"
+      "DONE_C:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_i8_2cta(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZ_THREADS, 1)
+    oz_syrk_pair_kernel(const __grid_constant__ OzPlan plan, const OzWork2* __restrict__ work, int nwork, int KB,
+                        const int8_t* __restrict__ slices, size_t slice_stride, const int* __restrict__ expo,
+                        const double* __restrict__ pow2, int Dpad, double* __restrict__ Cmat, ptrdiff_t mc_off) {
+  extern __shared__ __align__(1024) uint8_t oz_smem[];
+  uint8_t* tiles = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(oz_smem), 1024));
+  uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (size_t)OZ2_STAGES * OZ2_STAGE_BYTES);
+  uint64_t* empty = full + OZ2_STAGES;
+  uint64_t* peer_full = empty + OZ2_STAGES;      // leader only: "the peer's stage is full"
+  uint64_t* tmem_full = peer_full + OZ2_STAGES;
+  uint64_t* tmem_empty = tmem_full + 1;          // leader only: 16 epilogue warps of the pair
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int cluster_id = blockIdx.x >> 1, nclusters = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < OZ2_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+      mbar_init(&peer_full[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 16);
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc2(tmem_ptr, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===== producer (both CTAs): own A tiles, own half of every B tile =====
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int w = cluster_id; w < nwork; w += nclusters) {
+        const OzWork2 wk = work[w];
+        const OzGroup& g = plan.g[wk.group];
+        const int bi = rank ? wk.bi1 : wk.bi0;
+        for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* dst = tiles + (size_t)stage * OZ2_STAGE_BYTES;
+          mbar_expect_tx(&full[stage], (uint32_t)(g.n_a * OZ_TILE_BYTES + g.n_b * (OZ_TILE_BYTES / 2)));
+          for (int i = 0; i < g.n_a; ++i)
+            tma_load_1d(dst + (size_t)i * OZ_TILE_BYTES,
+                        slices + (size_t)g.a_slice[i] * slice_stride + ((size_t)bi * KB + kb) * OZ_TILE_BYTES, OZ_TILE_BYTES,
+                        &full[stage]);
+          for (int i = 0; i < g.n_b; ++i)
+            tma_load_1d(dst + (size_t)g.n_a * OZ_TILE_BYTES + (size_t)i * (OZ_TILE_BYTES / 2),
+                        slices + (size_t)g.b_slice[i] * slice_stride + ((size_t)wk.bj * KB + kb) * OZ_TILE_BYTES +
+                            (size_t)rank * (OZ_TILE_BYTES / 2),
+                        OZ_TILE_BYTES / 2, &full[stage]);
+          if (++stage == OZ2_STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int stage = 0, phase = 0, it = 0;
+      if (rank == 0) {
+        // ===== MMA issuer (leader) =====
+        for (int w = cluster_id; w < nwork; w += nclusters, ++it) {
+          const OzWork2 wk = work[w];
+          const OzGroup& g = plan.g[wk.group];
+          mbar_wait_cluster(tmem_empty, (uint32_t)((it & 1) ^ 1));
+          tc_fence_after();
+          uint32_t acc_used = 0;
+          for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
+            mbar_wait(&full[stage], phase);
+            mbar_wait_cluster(&peer_full[stage], phase);
+            tc_fence_after();
+            const uint32_t base = smem_u32(tiles + (size_t)stage * OZ2_STAGE_BYTES);
+            for (int pr = 0; pr < g.n_pairs; ++pr) {
+              const uint32_t a_addr = base + (uint32_t)g.pair_a[pr] * OZ_TILE_BYTES;
+              const uint32_t b_addr = base + (uint32_t)g.n_a * OZ_TILE_BYTES + (uint32_t)g.pair_b[pr] * (OZ_TILE_BYTES / 2);
+              const uint32_t acc = g.pair_acc[pr];
+#pragma unroll
+              for (int ks = 0; ks < OZ_BK / 32; ++ks) {
+                umma_i8_2cta(tmem_base + acc * 128u, smem_desc_sw64(a_addr + ks * 32), smem_desc_sw64(b_addr + ks * 32),
+                             OZ_IDESC2, (acc_used >> acc) & 1u);
+                acc_used |= 1u << acc;
+              }
+            }
+            umma_commit_2cta(&empty[stage]);
+            if (++stage == OZ2_STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          umma_commit_2cta(tmem_full);
+        }
+      } else {
+        // ===== relay (peer): my stage is full -> tell the leader =====
+        const uint32_t remote = mapa_shared(smem_u32(peer_full), 0);
+        for (int w = cluster_id; w < nwork; w += nclusters) {
+          const OzWork2 wk = work[w];
+          for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
+            mbar_wait(&full[stage], phase);
+            mbar_arrive_cluster(remote + (uint32_t)stage * 8u);
+            if (++stage == OZ2_STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else {
+    // ===== epilogue (8 warps per CTA; this CTA's 128 rows) =====
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const int row_local = quarter * 32 + lane, col0 = half * 64;
+    const uint32_t tmem_empty_leader = mapa_shared(smem_u32(tmem_empty), 0);
+    int it = 0;
+    for (int w = cluster_id; w < nwork; w += nclusters, ++it) {
+      const OzWork2 wk = work[w];
+      const OzGroup& g = plan.g[wk.group];
+      const int bi = rank ? wk.bi1 : wk.bi0;
+      const bool discard = rank && wk.dup;
+      mbar_wait(tmem_full, (uint32_t)(it & 1));
+      tc_fence_after();
+      double acc[64];
+#pragma unroll
+      for (int j = 0; j < 64; ++j) acc[j] = 0.0;
+      for (int a = 0; a < g.n_acc; ++a) {
+        const double wgt = (double)(1ull << g.acc_shift[a]);
+#pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(a * 128 + col0 + c16 * 16), v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) acc[c16 * 16 + j] = fma((double)(int)v[j], wgt, acc[c16 * 16 + j]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(tmem_empty_leader);
+      if (discard) continue;
+      const int r = bi * OZ_BM + row_local;
+      const int er = expo[r];
+      const bool diag = bi == wk.bj;
+      const bool tame = er != OZ_EXPO_BAD && er > -400 && er < 400;
+      const double sr = tame ? __longlong_as_double((long long)(1023 + er + g.exp_base) << 52) : 0.0;
+#pragma unroll
+      for (int j = 0; j < 64; ++j) {
+        const int col = wk.bj * OZ_BM + col0 + j;
+        const int ec = expo[col];
+        double v = acc[j];
+        if (er == OZ_EXPO_BAD || ec == OZ_EXPO_BAD) v = __longlong_as_double(0x7ff8000000000000LL);
+        else if (tame && ec > -400 && ec < 400) v = v * sr * pow2[col];
+        else v = ldexp(v, er + ec + g.exp_base);
+        if (v != 0.0) {
+          if (!mc_off && (!diag || col <= r)) atomicAdd(&Cmat[(size_t)r * Dpad + col], -v);
+          if (!diag || col < r || (mc_off && col == r)) {
+            double* q = &Cmat[(size_t)col * Dpad + r];
+            if (mc_off) {
+              asm volatile("multimem.red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(q + mc_off), "d"(-v) : "memory");
+            } else {
+              atomicAdd(q, -v);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                          // nobody leaves while the partner may still address this CTA
+  if (warp == 1) tmem_dealloc2(tmem_base, 512);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // tensor-pipe rate probe (tools/syrk_i8_check.py rate): back-to-back kind::i8 MMAs on resident shared-memory tiles,
 // cycles per MMA for the three shared-memory layouts / two N.  Data content is irrelevant.
@@ -446,16 +696,69 @@ bool build_plan(int s, OzPlan* plan) {
   return true;
 }
 
+
+// Work items are handed out statically (item w goes to CTA / cluster w mod n, longest first), so the finishing time is
+// the heaviest residue class.  The k-split granularity is chosen by simulating that assignment for a few candidate
+// targets and keeping the best makespan (+ a small charge per item for its epilogue).
+struct OzTileJob {
+  int bi0, bi1, bj, dup;
+};
+template <class Work, class Make>
+void build_work_list(const OzPlan& plan, const std::vector<OzTileJob>& jobs, int KB, int nworkers, Make make,
+                     std::vector<Work>* out) {
+  long long total = 0;
+  for (int g = 0; g < plan.n_groups; ++g) total += (long long)plan.g[g].n_pairs * KB;
+  total *= (long long)jobs.size();
+  const long long epilogue_cost = 24;            // pair-kblock equivalents of one item's TMEM drain + REDs (not overlapped part)
+  long long best = -1;
+  for (int div = 2; div <= 10; ++div) {
+    const long long target = std::max<long long>(1, total / ((long long)nworkers * div));
+    std::vector<std::pair<long long, Work>> items;
+    for (const OzTileJob& jb : jobs)
+      for (int g = 0; g < plan.n_groups; ++g) {
+        const long long cost = (long long)plan.g[g].n_pairs * KB;
+        int parts = (int)std::min<long long>(16, std::max<long long>(1, (cost + target / 2) / target));
+        parts = std::max(parts, (KB + OZ_MAX_ITEM_KB - 1) / OZ_MAX_ITEM_KB);      // int32 accumulators stay exact
+        parts = std::min(parts, KB);
+        for (int p = 0; p < parts; ++p) {
+          const int k0 = (int)((long long)KB * p / parts), k1 = (int)((long long)KB * (p + 1) / parts);
+          items.push_back({(long long)plan.g[g].n_pairs * (k1 - k0), make(jb, g, k0, k1)});
+        }
+      }
+    std::stable_sort(items.begin(), items.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
+    std::vector<long long> load(nworkers, 0);
+    for (size_t i = 0; i < items.size(); ++i) load[i % nworkers] += items[i].first + epilogue_cost;
+    const long long makespan = *std::max_element(load.begin(), load.end());
+    if (best < 0 || makespan < best) {
+      best = makespan;
+      out->clear();
+      for (auto& it : items) out->push_back(it.second);
+    }
+  }
+}
+
 struct OzHostState {
   int Kpad = -1, Dpad = -1, slices = -1, sms = 0;
   OzPlan plan;
   std::vector<OzWork> work;
   OzWork* pinned = nullptr;       // page-locked copy of `work`, so the per-call upload is a true async copy
   size_t pinned_cap = 0;
+  std::vector<OzWork2> work2;     // CTA-pair variant
+  OzWork2* pinned2 = nullptr;
+  size_t pinned2_cap = 0;
 };
+
+bool use_pair_kernel() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("VGG_SYRK_PAIR");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
 thread_local OzHostState g_oz;
 
-int oz_max_parts(int KB) { return std::max(8, (KB + OZ_MAX_ITEM_KB - 1) / OZ_MAX_ITEM_KB); }
+int oz_max_parts(int KB) { return std::max(16, (KB + OZ_MAX_ITEM_KB - 1) / OZ_MAX_ITEM_KB); }
 
 size_t oz_workspace_bytes(int Kpad, int Dpad, int s) {
   const int KB = (Kpad + OZ_BK - 1) / OZ_BK;
@@ -464,7 +767,7 @@ size_t oz_workspace_bytes(int Kpad, int Dpad, int s) {
   bytes += align_up((size_t)Dpad * 8, 256);                                   // amax
   bytes += align_up((size_t)Dpad * 4, 256);                                   // expo
   bytes += align_up((size_t)Dpad * 8, 256);                                   // pow2
-  bytes += align_up((size_t)nb * (nb + 1) / 2 * OZ_MAX_GROUPS * oz_max_parts(KB) * sizeof(OzWork), 256);   // work list (upper bound)
+  bytes += align_up((size_t)nb * (nb + 1) / 2 * OZ_MAX_GROUPS * oz_max_parts(KB) * sizeof(OzWork2), 256);   // work list (upper bound, either variant)
   bytes += align_up((size_t)s * nb * KB * OZ_TILE_BYTES, 1024) + 1024;        // slices
   return bytes;
 }
@@ -496,33 +799,40 @@ int launch_syrk_i8(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t
     VGG_CUDA_CHECK(cudaGetDevice(&dev));
     VGG_CUDA_CHECK(cudaDeviceGetAttribute(&hs.sms, cudaDevAttrMultiProcessorCount, dev));
     VGG_CUDA_CHECK(cudaFuncSetAttribute(oz_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES));
-    // work items: (tile, group, k range) of roughly equal MMA cost, longest first
-    long long total = 0;
-    for (int g = 0; g < hs.plan.n_groups; ++g) total += (long long)hs.plan.g[g].n_pairs * KB;
-    total *= (long long)nb * (nb + 1) / 2;
-    const long long target = std::max<long long>(1, total / ((long long)hs.sms * 4));
-    hs.work.clear();
-    std::vector<std::pair<long long, OzWork>> items;
-    for (int bi = 0; bi < nb; ++bi)
-      for (int bj = 0; bj <= bi; ++bj)
-        for (int g = 0; g < hs.plan.n_groups; ++g) {
-          const long long cost = (long long)hs.plan.g[g].n_pairs * KB;
-          int parts = (int)std::min<long long>(8, std::max<long long>(1, (cost + target / 2) / target));
-          parts = std::max(parts, (KB + OZ_MAX_ITEM_KB - 1) / OZ_MAX_ITEM_KB);      // int32 accumulators stay exact
-          parts = std::min(parts, KB);
-          for (int p = 0; p < parts; ++p) {
-            OzWork wk{bi, bj, g, (int)((long long)KB * p / parts), (int)((long long)KB * (p + 1) / parts)};
-            items.push_back({(long long)hs.plan.g[g].n_pairs * (wk.kb1 - wk.kb0), wk});
-          }
-        }
-    std::stable_sort(items.begin(), items.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
-    for (auto& it : items) hs.work.push_back(it.second);
+    // work items: (tile, group, k range), longest first (build_work_list picks the k-split granularity)
+    {
+      std::vector<OzTileJob> jobs;
+      for (int bi = 0; bi < nb; ++bi)
+        for (int bj = 0; bj <= bi; ++bj) jobs.push_back({bi, bi, bj, 0});
+      build_work_list<OzWork>(hs.plan, jobs, KB, hs.sms,
+                              [](const OzTileJob& j, int g, int k0, int k1) { return OzWork{j.bi0, j.bj, g, k0, k1}; }, &hs.work);
+    }
     if (hs.work.size() > hs.pinned_cap) {
       if (hs.pinned) cudaFreeHost(hs.pinned);
       hs.pinned_cap = hs.work.size();
       VGG_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&hs.pinned), sizeof(OzWork) * hs.pinned_cap, cudaHostAllocDefault));
     }
     std::copy(hs.work.begin(), hs.work.end(), hs.pinned);
+    // CTA-pair variant: row blocks of one column paired two by two (an odd one out is paired with itself, second half discarded)
+    {
+      VGG_CUDA_CHECK(cudaFuncSetAttribute(oz_syrk_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ2_SMEM_BYTES));
+      const int nclusters = std::max(1, hs.sms / 2);
+      std::vector<OzTileJob> jobs;
+      for (int bj = 0; bj < nb; ++bj)
+        for (int bi = bj; bi < nb; bi += 2) {
+          const bool dup = bi + 1 >= nb;
+          jobs.push_back({bi, dup ? bi : bi + 1, bj, dup ? 1 : 0});
+        }
+      build_work_list<OzWork2>(hs.plan, jobs, KB, nclusters,
+                               [](const OzTileJob& j, int g, int k0, int k1) { return OzWork2{j.bi0, j.bi1, j.bj, g, k0, k1, j.dup}; },
+                               &hs.work2);
+      if (hs.work2.size() > hs.pinned2_cap) {
+        if (hs.pinned2) cudaFreeHost(hs.pinned2);
+        hs.pinned2_cap = hs.work2.size();
+        VGG_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&hs.pinned2), sizeof(OzWork2) * hs.pinned2_cap, cudaHostAllocDefault));
+      }
+      std::copy(hs.work2.begin(), hs.work2.end(), hs.pinned2);
+    }
     hs.Kpad = Kpad;
     hs.Dpad = Dpad;
     hs.slices = s;
@@ -531,13 +841,16 @@ int launch_syrk_i8(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t
   unsigned long long* amax = c.take<unsigned long long>(Dpad);
   int* expo = c.take<int>(Dpad);
   double* pow2 = c.take<double>(Dpad);
-  OzWork* work_d = c.take<OzWork>((size_t)nb * (nb + 1) / 2 * OZ_MAX_GROUPS * oz_max_parts(KB));
+  OzWork2* work_raw = c.take<OzWork2>((size_t)nb * (nb + 1) / 2 * OZ_MAX_GROUPS * oz_max_parts(KB));
+  OzWork* work_d = reinterpret_cast<OzWork*>(work_raw);
   c.off = align_up(c.off, 1024);
   int8_t* slices = reinterpret_cast<int8_t*>(c.base + c.off);
   const size_t slice_stride = (size_t)nb * KB * OZ_TILE_BYTES;
   const int nwork = (int)hs.work.size();
 
-  VGG_CUDA_CHECK(cudaMemcpyAsync(work_d, hs.pinned, sizeof(OzWork) * nwork, cudaMemcpyHostToDevice, st));
+  const bool pair = use_pair_kernel() && hs.sms >= 2;
+  if (pair) VGG_CUDA_CHECK(cudaMemcpyAsync(work_raw, hs.pinned2, sizeof(OzWork2) * hs.work2.size(), cudaMemcpyHostToDevice, st));
+  else VGG_CUDA_CHECK(cudaMemcpyAsync(work_d, hs.pinned, sizeof(OzWork) * nwork, cudaMemcpyHostToDevice, st));
   if (!amax_ready) {
     VGG_CUDA_CHECK(cudaMemsetAsync(amax, 0, sizeof(unsigned long long) * Dpad, st));
     const int ksplit = 64;
@@ -547,9 +860,16 @@ int launch_syrk_i8(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t
   }
   oz_slice_kernel<<<dim3(nb, KB), 512, 0, st>>>(Kpad, Dpad, KB, s, Zt, amax, expo, pow2, slices, slice_stride);
   VGG_LAUNCH_CHECK();
-  const int grid = std::min(hs.sms, nwork);
-  oz_syrk_kernel<<<grid, OZ_THREADS, OZ_SMEM_BYTES, st>>>(hs.plan, work_d, nwork, KB, slices, slice_stride, expo, pow2,
-                                                        Dpad, Cmat, mc_off);
+  if (pair) {
+    const int nwork2 = (int)hs.work2.size();
+    const int nclusters = std::min(std::max(1, hs.sms / 2), nwork2);
+    oz_syrk_pair_kernel<<<2 * nclusters, OZ_THREADS, OZ2_SMEM_BYTES, st>>>(hs.plan, work_raw, nwork2, KB, slices, slice_stride,
+                                                                         expo, pow2, Dpad, Cmat, mc_off);
+  } else {
+    const int grid = std::min(hs.sms, nwork);
+    oz_syrk_kernel<<<grid, OZ_THREADS, OZ_SMEM_BYTES, st>>>(hs.plan, work_d, nwork, KB, slices, slice_stride, expo, pow2,
+                                                          Dpad, Cmat, mc_off);
+  }
   VGG_LAUNCH_CHECK();
   return VGG_OK;
 }
