@@ -51,8 +51,10 @@ def _worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_two_rank_sharded_lm_equals_unsharded():
-    world = 2
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_lm_equals_unsharded(world):
+    """world 2: even shards; world 3: the 16-aligned split of 64 tracks is 32 / 32 / 0 -- a rank without tracks still
+    takes part in every reduction and ends with the same cameras."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
@@ -74,6 +76,7 @@ def test_two_rank_sharded_lm_equals_unsharded():
         assert summ["iterations"] == s0["iterations"] and summ["successful"] == s0["successful"]
         assert np.allclose(costs, [t.get("candidate_cost") for t in tr], rtol=1e-9)
         assert np.abs(p - p0).max() < 1e-9 and np.abs(i - i0).max() < 1e-8
-        assert np.abs(x - x0[lo:hi]).max() < 1e-9
-    # both ranks hold identical cameras
-    assert np.array_equal(res[0][1], res[1][1])
+        assert hi == lo or np.abs(x - x0[lo:hi]).max() < 1e-9      # world 3 leaves the last rank an EMPTY shard: still in step
+    # every rank holds identical cameras
+    for r in res[1:]:
+        assert np.array_equal(res[0][1], r[1])
