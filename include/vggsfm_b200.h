@@ -140,6 +140,8 @@ int vgg_syrk_ozaki(int Kpad, int Dpad, const double* Zt, double* Cmat, int slice
  * bit0 selects N=256 (else 128), mode>>1 the shared-memory layout (0 = 64 B swizzle, 1 = 128 B swizzle, 2 = none).
  * out_cycles is a host pointer. */
 int vgg_syrk_ozaki_mma_rate(int iters, int mode, double* out_cycles, void* stream);
+/* Cluster hardware-rule probe used while developing the CTA-pair SYRK (bounded, cannot hang): out_host[0..2] int. */
+int vgg_probe_remote_mbarrier(int* out_host, void* stream);
 
 /* Whole Levenberg-Marquardt solve (Ceres trust-region semantics).  `trace` is a HOST array
  * [max_num_iterations, 8] (it, cost, candidate_cost, model_change, rho, radius, step_norm, flags) or NULL. */

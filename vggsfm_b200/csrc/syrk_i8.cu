@@ -600,6 +600,63 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZ_THREADS, 1)
   if (warp == 1) tmem_dealloc2(tmem_base, 512);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// hardware-rule probe (tools/syrk_i8_check.py probe): may a 1-D bulk copy whose destination is the issuing CTA's own
+// shared memory complete on an mbarrier that lives in the OTHER CTA of the cluster?  Measured on B200 (r01): NO -- the
+// bytes land, the remote barrier never completes (out = 0, 1, 1); the barrier has to be in the destination CTA, which
+// is why the CTA-pair SYRK relays "stage full" through a second barrier.  Bounded spin: the probe cannot hang.  out[0] = leader's barrier completed, out[1] = the
+// peer's bytes landed in the peer's buffer, out[2] = the leader's own bytes landed.
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32, 1)
+    oz_probe_remote_mbar_kernel(const uint8_t* __restrict__ src, int* __restrict__ out) {
+  __shared__ __align__(128) uint8_t buf[256];
+  __shared__ uint64_t bar;
+  const uint32_t rank = cluster_ctarank();
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 256; i += 32) buf[i] = 0;
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_fence_init();
+  }
+  fence_proxy_async();
+  __syncthreads();
+  cluster_sync_all();
+  if (tid == 0) {
+    if (rank == 0) {
+      mbar_expect_tx(&bar, 512);
+      tma_load_1d(buf, src, 256, &bar);
+    } else {
+      const uint32_t remote_bar = mapa_shared(smem_u32(&bar), 0);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                       smem_u32(buf)),
+                   "l"(src + 256), "r"(256), "r"(remote_bar)
+                   : "memory");
+    }
+  }
+  if (rank == 0 && tid == 0) {
+    int done = 0;
+    for (int i = 0; i < 2000000 && !done; ++i) {
+      uint32_t ok;
+      asm volatile(
+          "{\n.reg .pred p;\nmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+          : "=r"(ok)
+          : "r"(smem_u32(&bar)), "r"(0)
+          : "memory");
+      done = (int)ok;
+    }
+    out[0] = done;
+  }
+  // give the copies time either way, then look at the buffers
+  for (int i = 0; i < 200000; ++i) __nanosleep(20);
+  cluster_sync_all();
+  if (tid == 0) {
+    int ok = 1;
+    for (int i = 0; i < 256; ++i) ok &= (buf[i] == src[rank * 256 + i]);
+    out[rank == 0 ? 2 : 1] = ok;
+  }
+  cluster_sync_all();
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // tensor-pipe rate probe (tools/syrk_i8_check.py rate): back-to-back kind::i8 MMAs on resident shared-memory tiles,
 // cycles per MMA for the three shared-memory layouts / two N.  Data content is irrelevant.
@@ -900,6 +957,28 @@ int vgg_syrk_ozaki_mma_rate(int iters, int mode, double* out_cycles, void* strea
   VGG_CUDA_CHECK(cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost));
   cudaFree(d);
   *out_cycles = (double)h / iters;
+  return VGG_OK;
+}
+
+/* Hardware-rule probe for the CTA-pair kernel: out_host[0..2] = (leader barrier completed by a peer-issued bulk copy,
+ * peer bytes landed, leader bytes landed).  Bounded spin, cannot hang. */
+int vgg_probe_remote_mbarrier(int* out_host, void* stream) {
+  using namespace vgg;
+  g_launch_count = 0;
+  VGG_REQUIRE(out_host, "null pointer");
+  uint8_t* src = nullptr;
+  int* out = nullptr;
+  VGG_CUDA_CHECK(cudaMalloc(&src, 512));
+  VGG_CUDA_CHECK(cudaMalloc(&out, 16));
+  uint8_t h[512];
+  for (int i = 0; i < 512; ++i) h[i] = (uint8_t)(i * 7 + 3);
+  VGG_CUDA_CHECK(cudaMemcpy(src, h, 512, cudaMemcpyHostToDevice));
+  VGG_CUDA_CHECK(cudaMemset(out, 0xFF, 16));
+  oz_probe_remote_mbar_kernel<<<2, 32, 0, static_cast<cudaStream_t>(stream)>>>(src, out);
+  VGG_LAUNCH_CHECK();
+  VGG_CUDA_CHECK(cudaMemcpy(out_host, out, 12, cudaMemcpyDeviceToHost));
+  cudaFree(src);
+  cudaFree(out);
   return VGG_OK;
 }
 
