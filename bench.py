@@ -15,9 +15,17 @@ camera system is all-reduced over NCCL once per iteration (strong scaling: total
 """
 from __future__ import annotations
 
+import os
+import sys
+
+if "reference" in sys.argv:
+    # The CPU arm uses every host core -- also under torchrun, which exports OMP_NUM_THREADS=1 for its workers; the
+    # BLAS / OpenMP runtimes read these at import time, so this has to happen before numpy is imported.
+    for _k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_k] = str(os.cpu_count() or 1)
+
 import argparse
 import json
-import os
 import subprocess
 import sys
 import threading
