@@ -136,13 +136,6 @@ int vgg_cholesky_lower(int n, int lda, double* A, void* workspace, size_t ws_byt
 int vgg_syrk_ozaki_workspace_bytes(int Kpad, int Dpad, int slices, size_t* bytes);
 int vgg_syrk_ozaki(int Kpad, int Dpad, const double* Zt, double* Cmat, int slices, void* workspace, size_t ws_bytes,
                    void* stream);
-/* Tensor-pipe probe used for the SYRK's roofline: cycles per back-to-back tcgen05.mma.kind::i8 (M=128, K=32); mode
- * bit0 selects N=256 (else 128), mode>>1 the shared-memory layout (0 = 64 B swizzle, 1 = 128 B swizzle, 2 = none).
- * out_cycles is a host pointer. */
-int vgg_syrk_ozaki_mma_rate(int iters, int mode, double* out_cycles, void* stream);
-/* Cluster hardware-rule probe used while developing the CTA-pair SYRK (bounded, cannot hang): out_host[0..2] int. */
-int vgg_probe_remote_mbarrier(int* out_host, void* stream);
-
 /* Whole Levenberg-Marquardt solve (Ceres trust-region semantics).  `trace` is a HOST array
  * [max_num_iterations, 8] (it, cost, candidate_cost, model_change, rho, radius, step_norm, flags) or NULL. */
 int vgg_ba_solve(const vgg_ba_problem* prob, const vgg_ba_options* opt, void* workspace,

@@ -330,6 +330,31 @@ def _full_W(blk, S, dc, ns):
     return W
 
 
+def _x_norm(poses, intr, points, S, dc, ns, param_const, point_const):
+    """|x| of Ceres' reduced program in AMBIENT coordinates (TrustRegionMinimizer::ParameterToleranceReached uses
+    x_norm_ = x_.norm()): every non-constant parameter block counts in full -- unit quaternion (1.0) and translation per
+    image whose block is not constant (a block held partly constant through a SubsetManifold, e.g. the second image's
+    translation or a camera with a fixed principal point, is still non-constant), camera parameter blocks (f,cx,cy[,k])
+    unless no intrinsic is refined, free points. [3P-memory]"""
+    pc = np.asarray(param_const, dtype=bool)
+    ni = dc - 6 if ns == 0 else ns
+    nparam = 3 + (1 if ni == 2 else 0) if ni else 0
+    tot = 0.0
+    for s in range(S):
+        c = pc[s * dc:(s + 1) * dc]
+        if not c[0:3].all():
+            tot += 1.0
+        if not c[3:6].all():
+            tot += float(np.sum(poses[s][:, 3] ** 2))
+        if dc > 6 and not c[6:dc].all():
+            tot += float(np.sum(intr[s][:3] ** 2)) + (float(intr[s][3] ** 2) if dc == 8 else 0.0)
+    if ns and not pc[S * dc:].all():
+        tot += float(np.sum(intr[0][:3] ** 2)) + (float(intr[0][3] ** 2) if ns == 2 else 0.0)
+    free = ~np.asarray(point_const, dtype=bool)
+    tot += float(np.sum(points[free] ** 2))
+    return np.sqrt(tot)
+
+
 def lm_solve(poses, intr, points, uv, mask, model, mode, param_const=None, point_const=None,
              options: LMOptions | None = None, trace: list | None = None, allreduce=None, use_c=False):
     """Ceres-style trust-region LM (TrustRegionMinimizer + LevenbergMarquardtStrategy) with the
@@ -463,12 +488,12 @@ def lm_solve(poses, intr, points, uv, mask, model, mode, param_const=None, point
         if trace is not None:
             trace.append({"it": it, "cost": cost, "candidate_cost": c_cost, "model_change": model_change,
                           "rho": rho, "radius": radius, "step_norm": step_norm})
-        if step_norm <= opt.parameter_tolerance * opt.parameter_tolerance:   # x_norm dropped (tol is 0 or tiny)
+        if step_norm <= opt.parameter_tolerance * (_x_norm(poses, intr, points, S, dc, ns, param_const, point_const)
+                                                   + opt.parameter_tolerance):
             summary["termination"] = "CONVERGENCE_PARAMETER"
             break
         if abs(cost_change) <= opt.function_tolerance * cost:
-            if rho > opt.min_relative_decrease:
-                poses, intr, points, cost = c_poses, c_intr, c_points, c_cost
+            # Ceres 2.x: FunctionToleranceReached() returns before HandleSuccessfulStep() -> candidate discarded
             summary["termination"] = "CONVERGENCE_FUNCTION"
             break
         if rho > opt.min_relative_decrease:

@@ -202,9 +202,7 @@ def pose_refinement(pose, intr, points3D, points2D, inlier_mask, model, refine_f
             summary["termination"] = CONV_PARAMETER
             break
         if abs(cost_change) <= opt.function_tolerance * cost:
-            if rho > opt.min_relative_decrease:
-                pose, intr, cost = c_pose, c_intr, c_cost
-                summary["successful"] += 1
+            # Ceres 2.x: FunctionToleranceReached() returns before HandleSuccessfulStep() -> candidate discarded
             summary["termination"] = CONV_FUNCTION
             break
         if rho > opt.min_relative_decrease:

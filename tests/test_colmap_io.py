@@ -1,4 +1,4 @@
-"""COLMAP binary export of the tensor-backed Reconstruction (vggsfm_b200/colmap_io.py): ids and ordering follow
+"""COLMAP binary export of vggsfm_b200.reconstruction.Reconstruction (vggsfm_b200/colmap_io.py): ids and ordering follow
 batch_matrix_to_pycolmap (vggsfm/utils/tensor_to_pycolmap.py:16-160), byte layout follows COLMAP's model format;
 checked by an independent byte-level parse and a write -> read round trip.  CPU only."""
 import struct
@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from vggsfm_b200 import colmap_io as cio
-from vggsfm_b200.bundle_adjustment import Reconstruction
+from vggsfm_b200.reconstruction import Reconstruction
 from vggsfm_b200.synthetic import make_scene
 
 
@@ -19,26 +19,31 @@ def _rec(cam, shared, S=5, P=40):
     masks[1:, 9] = False                      # a track with a single observation: not a COLMAP point
     xyz = sc.points3d.copy()
     xyz[11] = 0.0                             # a point the BA deleted (reads back as zeros)
+    alive = np.ones(P, dtype=bool)
+    alive[11] = False
     t = torch.from_numpy
-    rec = Reconstruction(t(xyz), t(sc.extrinsics), t(sc.intrinsics), t(sc.extra_params) if sc.extra_params is not None else None,
-                         t(sc.tracks), t(masks), torch.tensor([1024, 768]), cam, shared)
+    rec = Reconstruction.from_batch_matrix(t(xyz), t(sc.extrinsics), t(sc.intrinsics), t(sc.tracks), t(masks),
+                                           torch.tensor([1024, 768]), shared_camera=shared, camera_type=cam,
+                                           extra_params=t(sc.extra_params) if sc.extra_params is not None else None,
+                                           alive=t(alive))
     return rec, sc, masks, xyz
 
 
 @pytest.mark.parametrize("cam,shared", [("SIMPLE_PINHOLE", False), ("SIMPLE_RADIAL", True)])
 def test_round_trip_and_ids(tmp_path, cam, shared):
     rec, sc, masks, xyz = _rec(cam, shared)
-    rec.points3D_rgb = torch.linspace(0, 1, 40)[:, None].repeat(1, 3)
+    rec.set_point_colors(torch.linspace(0, 1, 40)[:, None].repeat(1, 3))       # ids 1..max id
     rec.write(str(tmp_path))
     m = cio.read_model(str(tmp_path))
     S, P = masks.shape
     keep = (masks.sum(0) >= 2) & (np.abs(xyz).sum(1) > 0)
     assert not keep[7] and not keep[9] and not keep[11]
-    assert sorted(m["points3D"]) == list(range(1, int(keep.sum()) + 1))            # ids 1..P' in track order
-    order = np.nonzero(keep)[0]
+    order = np.nonzero(masks.sum(0) >= 2)[0]                                     # ids 1..P' in track order (:62-70)
+    dead = int(np.nonzero(order == 11)[0][0]) + 1                               # the deleted point keeps its id, unused
+    assert sorted(m["points3D"]) == [i for i in range(1, len(order) + 1) if i != dead]
     for pid, p in m["points3D"].items():
         assert np.array_equal(p["xyz"], xyz[order[pid - 1]])
-        assert p["rgb"][0] == int(round(order[pid - 1] / 39 * 255)) and p["error"] == -1.0
+        assert p["rgb"][0] == int(round((pid - 1) / 39 * 255)) and p["error"] == -1.0
         assert len(p["track"]) == int(masks[:, order[pid - 1]].sum())
         for (iid, idx2d) in p["track"]:                                          # element -> that image's point2D -> back
             assert m["images"][iid]["point3D_ids"][idx2d] == pid
@@ -94,7 +99,8 @@ def test_quaternion_branches():
 
 
 def test_unsupported_camera_type(tmp_path):
-    rec, *_ = _rec("SIMPLE_PINHOLE", False)
-    rec.camera_type = "OPENCV"
-    with pytest.raises(ValueError, match="is not supported yet"):
-        rec.write(str(tmp_path))
+    sc = make_scene(3, 8, "SIMPLE_PINHOLE", seed=3)
+    t = torch.from_numpy
+    with pytest.raises(ValueError, match="is not supported yet"):      # tensor_to_pycolmap.py:97-100
+        Reconstruction.from_batch_matrix(t(sc.points3d), t(sc.extrinsics), t(sc.intrinsics), t(sc.tracks), t(sc.mask),
+                                         torch.tensor([1024, 768]), camera_type="OPENCV")

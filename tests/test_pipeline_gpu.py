@@ -65,7 +65,29 @@ def test_triangulate_then_ba(cuda_dev, cam, shared):
     assert np.median(res) < 5e-3
     # focal close to the ground truth 1000 px
     assert abs(K2[:, 0, 0].mean().item() - 1000.0) < 10.0
-    assert rec2 is not None and ba.get_valid_frame_mask(K2, E2, ex2, 1024).all()
+    assert ba.get_valid_frame_mask(K2, E2, ex2, 1024).all()
+    # the lastBA reconstruction (triangulation.py:1186-1199): P points x S images, normalised once more, serialisable
+    import tempfile
+    from vggsfm_b200 import colmap_io as cio
+    P = p2.shape[0]
+    back = rec2.to_batch_matrix(device="cpu", camera_type=cam)
+    assert back[0].shape == (P, 3) and back[1].shape == (S, 3, 4) and back[2].shape == (S, 3, 3)
+    e_n, p_n = ba.normalize(E2, p2, 5.0, 0.1, 0.9)
+    assert (back[0] - p_n.cpu()).abs().max().item() < 1e-12 and (back[1] - e_n.cpu()).abs().max().item() < 1e-12
+    assert (back[2] - K2.cpu()).abs().max().item() == 0.0
+    with tempfile.TemporaryDirectory() as d:
+        rec2.write(d)
+        m = cio.read_model(d)
+    assert len(m["points3D"]) == P and sorted(m["images"]) == list(range(S))
+    assert len(m["cameras"]) == (1 if shared else S)
+    xyz = np.stack([m["points3D"][i + 1]["xyz"] for i in range(P)])
+    assert np.array_equal(xyz, back[0].numpy())
+    obs = masks3.cpu().numpy()
+    for s_ in (0, S - 1):
+        assert len(m["images"][s_]["point3D_ids"]) == int(obs[s_].sum())
+        assert np.allclose(cio.qvec_to_rotmat(m["images"][s_]["qvec"]), back[1][s_, :, :3].numpy(), atol=1e-12)
+    # the intermediate (lastBA=False) call also hands back the BA'd reconstruction, like the reference (:1146)
+    assert rec.num_points3D() > 0 and rec.num_images() == S
 
 
 class _Cameras:

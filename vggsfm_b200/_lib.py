@@ -17,11 +17,15 @@ EXPORTS = [
     "vgg_ba_default_options", "vgg_ba_dims", "vgg_ba_workspace_bytes", "vgg_ba_camrec_len",
     "vgg_ba_build_blocks", "vgg_ba_schur", "vgg_cholesky_lower", "vgg_ba_solve",
     "vgg_ba_reduced_system_doubles", "vgg_ba_solve_fabric",
-    "vgg_pose_default_options", "vgg_pose_refinement", "vgg_syrk_ozaki_workspace_bytes", "vgg_syrk_ozaki", "vgg_syrk_ozaki_mma_rate", "vgg_probe_remote_mbarrier",
+    "vgg_pose_default_options", "vgg_pose_refinement", "vgg_syrk_ozaki_workspace_bytes", "vgg_syrk_ozaki",
     "vgg_tri_workspace_bytes", "vgg_triangulate_tracks", "vgg_triangulate_by_pair", "vgg_filter_points3d",
     "vgg_project_points", "vgg_normalize_tracks", "vgg_undistort_simple_radial",
     "vgg_corr_pyramid_bytes", "vgg_corr_build_pyramid", "vgg_corr_sample", "vgg_sample_features4d",
 ]
+
+
+# development probes (csrc/dev_probes.h): exported, not part of the public header
+DEV_EXPORTS = ["vgg_syrk_ozaki_mma_rate", "vgg_probe_remote_mbarrier"]
 
 
 class BAProblem(ctypes.Structure):

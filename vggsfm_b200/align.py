@@ -1,6 +1,7 @@
 """Similarity alignment of camera sets -- the window-to-window alignment of the video runner.
 
-Mirrors ``align_camera_extrinsics`` / ``apply_transformation`` (vggsfm/utils/align.py:145-252), OpenCV convention,
+Close transcription of ``align_camera_extrinsics`` / ``apply_transformation`` (vggsfm/utils/align.py:145-252; the same
+dozen tensor statements, kept statement for statement because the semantics must match), OpenCV convention,
 extrinsics [B,3,4] = R|t.  A dozen 3x3 operations on at most window_size+1 cameras: host-side glue, written with
 torch so that it runs wherever the caller's tensors live.
 """

@@ -179,6 +179,8 @@ class Summary:
     device_ms: float
     kernel_launches: int
     trace: Optional[torch.Tensor] = None
+    alive: Optional[torch.Tensor] = None      # [P'] points the negative-depth filter kept (bundle_adjustment only)
+    mask: Optional[torch.Tensor] = None       # [S,P'] observations that were in the problem (bundle_adjustment only)
 
 
 def lm_solve(uv, mask, poses, intr, points, model, mode, param_const=None, point_const=None,
@@ -321,6 +323,7 @@ def bundle_adjustment(points3d, extrinsics, intrinsics, extra_params, tracks, ma
         if filter_reconstruction:
             poses, pts = normalize(poses, pts, 5.0, 0.1, 0.9, alive)    # filter_reconstruction (triangulation.py:1217)
     pts = torch.where(alive[:, None], pts, torch.zeros_like(pts))
+    summary.alive, summary.mask = alive, m
     K = torch.zeros(S, 3, 3, dtype=torch.float64, device=dev)
     K[:, 0, 0] = intr[:, 0]
     K[:, 1, 1] = intr[:, 0]
@@ -338,28 +341,14 @@ run_ba = bundle_adjustment   # the name BASELINE.json's north_star uses for this
 # mirrors of the reference's BA drivers (vggsfm/utils/triangulation.py:1020-1242)
 # --------------------------------------------------------------------------------------------------
 
-class Reconstruction:
-    """Tensor-backed stand-in for the ``pycolmap.Reconstruction`` the reference returns as the last tuple
-    element (triangulation.py:1073,1208).  Holds what downstream code reads back through
-    pycolmap_to_batch_matrix (tensor_to_pycolmap.py:163-214) and writes the COLMAP binary model (``.write``)."""
+from .reconstruction import Reconstruction   # noqa: E402  (pycolmap-shaped scene object, vggsfm_b200/reconstruction.py)
 
-    def __init__(self, points3D, extrinsics, intrinsics, extra_params, tracks, masks, image_size, camera_type,
-                 shared_camera, summary=None):
-        self.points3D_xyz, self.extrinsics, self.intrinsics, self.extra_params = points3D, extrinsics, intrinsics, extra_params
-        self.tracks, self.masks, self.image_size = tracks, masks, image_size
-        self.camera_type, self.shared_camera, self.summary = camera_type, shared_camera, summary
-        self.points3D_rgb = None
 
-    def write(self, path):
-        """``pycolmap.Reconstruction.write(path)``: cameras.bin / images.bin / points3D.bin (vggsfm_b200/colmap_io.py)."""
-        from .colmap_io import write_reconstruction
-        write_reconstruction(self, path)
-
-    def num_points3D(self):
-        return int(self.points3D_xyz.shape[0])
-
-    def num_images(self):
-        return int(self.extrinsics.shape[0])
+def _reconstruction(pts, extr, K, extra, tracks, masks, image_size, camera_type, shared_camera, summary, alive=None):
+    """The ``pycolmap.Reconstruction`` the reference returns, as its duck-typed stand-in (lazy: a few array
+    references until a caller touches ``.images / .cameras / .points3D``)."""
+    return Reconstruction.from_batch_matrix(pts, extr, K, tracks, masks, image_size, shared_camera=shared_camera,
+                                            camera_type=camera_type, extra_params=extra, summary=summary, alive=alive)
 
 
 def _revert_negative_focal(extr_new, K_new, extra_new, extr_old, K_old, extra_old):
@@ -384,8 +373,8 @@ def global_BA(triangulated_points, valid_tracks, pred_tracks, inlier_mask, extri
         BA_points, extrinsics, intrinsics, extra_params, BA_tracks, BA_inlier_masks, shared_camera=shared_camera,
         camera_type=camera_type, options=prepare_ba_options(), allreduce=allreduce)
     extr, K, extra = _revert_negative_focal(extr, K, extra, extrinsics, intrinsics, extra_params)
-    rec = Reconstruction(pts, extr, K, extra, BA_tracks[:, valid_idx], BA_inlier_masks[:, valid_idx], image_size,
-                         camera_type, shared_camera, summary)
+    rec = _reconstruction(pts, extr, K, extra, BA_tracks[:, valid_idx], summary.mask, image_size, camera_type,
+                          shared_camera, summary, summary.alive)
     return pts, extr, K, extra, rec
 
 
@@ -411,7 +400,8 @@ def init_BA(extrinsics, intrinsics, extra_params, tracks, points_3d_pair, inlier
     pts, extr, K, extra, valid_idx, summary = bundle_adjustment(
         toBA_points, toBA_extrinsics, toBA_intrinsics, toBA_extra, toBA_tracks, toBA_masks, shared_camera=shared_camera,
         camera_type=camera_type, options=prepare_ba_options(), filter_reconstruction=False)
-    rec = Reconstruction(pts, extr, K, extra, toBA_tracks, toBA_masks, image_size, camera_type, shared_camera, summary)
+    rec = _reconstruction(pts, extr, K, extra, toBA_tracks[:, valid_idx], summary.mask, image_size, camera_type,
+                          shared_camera, summary, summary.alive)
     ok, _ = tri.filter_all_points3D(pts, toBA_tracks, extr, K, extra, check_triangle=False,
                                     max_reproj_error=init_max_reproj_error)
     points3D_opt = pts[ok]
@@ -456,6 +446,8 @@ def iterative_global_BA(pred_tracks, intrinsics, extrinsics, pred_vis, pred_scor
     pts, extr, K, extra, valid_idx, summary = bundle_adjustment(
         BA_points, extrinsics, intrinsics, extra_params, BA_tracks, BA_inlier_masks, shared_camera=shared_camera,
         camera_type=camera_type, options=ba_options or default_options(), allreduce=allreduce)
+    rec = _reconstruction(pts, extr, K, extra, BA_tracks[:, valid_idx], summary.mask, image_size, camera_type,
+                          shared_camera, summary, summary.alive)        # the BA'd, filter_reconstruction'd object (:1146)
     if valid_idx.numel() != BA_points.shape[0]:
         # tracks with < 2 inliers never reach this point (min_valid_track_length >= 2), kept for safety
         full = torch.zeros(BA_points.shape[0], 3, dtype=pts.dtype, device=pts.device)
@@ -470,9 +462,10 @@ def iterative_global_BA(pred_tracks, intrinsics, extrinsics, pred_vis, pred_scor
     valid_tracks = valid_tmp
     pts = pts[valid_after]
     BA_inlier_masks = filtered[:, valid_after]
-    rec = None
     if lastBA:
-        p2, e2 = normalize(extr, pts, 5.0, 0.1, 0.9)                                    # filter_reconstruction (:1199)
-        rec = Reconstruction(p2, e2, K, extra, pred_tracks[:, valid_tracks], BA_inlier_masks, image_size, camera_type,
-                             shared_camera, summary)
+        # :1186-1199: rebuilt from the filtered tensors, then filter_reconstruction's normalize(5.0, 0.1, 0.9, True);
+        # normalize() takes and returns (poses, points)
+        e2, p2 = normalize(extr, pts, 5.0, 0.1, 0.9)
+        rec = _reconstruction(p2, e2, K, extra, pred_tracks[:, valid_tracks], BA_inlier_masks, image_size, camera_type,
+                              shared_camera, summary)
     return pts, extr, K, extra, valid_tracks, BA_inlier_masks, rec

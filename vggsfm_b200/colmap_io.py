@@ -1,9 +1,9 @@
-"""COLMAP model export for the tensor-backed ``Reconstruction`` -- the data format on the far side of the path.
+"""COLMAP binary model files for ``vggsfm_b200.reconstruction.Reconstruction`` -- the data format on the far side of the path.
 
 The reference hands a live ``pycolmap.Reconstruction`` to its caller, which ends in ``reconstruction.write(dir)``
 (``cameras.bin`` / ``images.bin`` / ``points3D.bin``; vggsfm/runners/runner.py:592-599).  pycolmap is not a dependency
-of this path, so the three files are written directly from the tensors, with the ids and ordering
-``batch_matrix_to_pycolmap`` would have produced (vggsfm/utils/tensor_to_pycolmap.py:16-160):
+of this path, so the three files are written directly from the plain-dict model ``Reconstruction.to_model()`` builds,
+with the ids and ordering ``batch_matrix_to_pycolmap`` would have produced (vggsfm/utils/tensor_to_pycolmap.py:16-160):
   * point3D ids 1..P' in track order (tracks with >= 2 inlier observations), colour 0 unless ``points3D_rgb`` is set;
   * image ids = frame index, names ``image_{idx}``, one camera per frame (camera id = frame index) or camera 0 for
     ``shared_camera``; SIMPLE_PINHOLE params (f, cx, cy), SIMPLE_RADIAL (f, cx, cy, k);
@@ -62,44 +62,6 @@ def _np(t):
     return t.detach().cpu().numpy() if hasattr(t, "detach") else np.asarray(t)
 
 
-def model_from_reconstruction(rec):
-    """Tensor stand-in -> plain dict model {cameras, images, points3D} with COLMAP's ids (see module docstring)."""
-    xyz = _np(rec.points3D_xyz).astype(np.float64)
-    extr = _np(rec.extrinsics).astype(np.float64)
-    K = _np(rec.intrinsics).astype(np.float64)
-    extra = _np(rec.extra_params).astype(np.float64) if rec.extra_params is not None else None
-    tracks = _np(rec.tracks).astype(np.float64)
-    masks = _np(rec.masks).astype(bool)
-    size = _np(rec.image_size).astype(np.int64)
-    rgb = getattr(rec, "points3D_rgb", None)
-    rgb = None if rgb is None else np.round(np.clip(_np(rgb).astype(np.float64), 0, 1) * 255).astype(np.uint8)
-    S, P = masks.shape
-    if rec.camera_type not in ("SIMPLE_PINHOLE", "SIMPLE_RADIAL"):
-        raise ValueError(f"Camera type {rec.camera_type} is not supported yet")
-    model_id = CAMERA_MODEL_IDS[rec.camera_type]
-    keep = (masks.sum(axis=0) >= 2) & (np.abs(xyz).sum(axis=1) > 0)         # deleted points read back as zeros
-    ids = np.zeros(P, dtype=np.int64)
-    ids[keep] = np.arange(1, int(keep.sum()) + 1)
-    cameras, images, points = {}, {}, {}
-    for p in np.nonzero(keep)[0]:
-        points[int(ids[p])] = {"xyz": xyz[p], "rgb": rgb[p] if rgb is not None else np.zeros(3, np.uint8), "error": -1.0,
-                               "track": []}
-    for s in range(S):
-        cam_id = 0 if rec.shared_camera else s
-        if cam_id not in cameras:
-            params = [K[s, 0, 0], K[s, 0, 2], K[s, 1, 2]]
-            if rec.camera_type == "SIMPLE_RADIAL":
-                params.append(extra[s, 0])
-            cameras[cam_id] = {"model_id": model_id, "width": int(size[0]), "height": int(size[1]),
-                               "params": np.array(params, dtype=np.float64)}
-        obs = np.nonzero(masks[s] & keep)[0]
-        for idx2d, p in enumerate(obs):
-            points[int(ids[p])]["track"].append((s, idx2d))
-        images[s] = {"qvec": rotmat_to_qvec(extr[s, :, :3]), "tvec": extr[s, :, 3], "camera_id": cam_id,
-                     "name": f"image_{s}", "xys": tracks[s, obs], "point3D_ids": ids[obs]}
-    return {"cameras": cameras, "images": images, "points3D": points}
-
-
 def write_model(model, path):
     """cameras.bin, images.bin, points3D.bin in COLMAP's binary layout (little endian)."""
     os.makedirs(path, exist_ok=True)
@@ -126,11 +88,6 @@ def write_model(model, path):
             f.write(struct.pack("<Q", len(p["track"])))
             if p["track"]:
                 f.write(np.asarray(p["track"], dtype="<i4").tobytes())
-
-
-def write_reconstruction(rec, path):
-    """``reconstruction.write(path)`` of the reference (runner.py:598) for the tensor stand-in."""
-    write_model(model_from_reconstruction(rec), path)
 
 
 def read_model(path):

@@ -106,6 +106,7 @@ def sample_features4d(input, coords):
     inp = input.float().contiguous()
     crd = coords.float().contiguous()
     out = torch.empty(B, R, C, dtype=torch.float32, device=input.device)
-    _lib.check(_lib.lib().vgg_sample_features4d(B, C, H, W, R, inp.data_ptr(), crd.data_ptr(), out.data_ptr(),
-                                                _stream(input.device)), "vgg_sample_features4d")
+    with torch.cuda.device(input.device):
+        _lib.check(_lib.lib().vgg_sample_features4d(B, C, H, W, R, inp.data_ptr(), crd.data_ptr(), out.data_ptr(),
+                                                    _stream(input.device)), "vgg_sample_features4d")
     return out.to(input.dtype)

@@ -62,14 +62,68 @@ size_t chol_workspace_doubles(int n);
 int chol_lower_inplace(int n, int lda, double* A, double* Ldiag, int* info, cudaStream_t st);
 
 // gathers the accept/reject scalars into one 24-double record so the host reads them with ONE copy:
-// [0..7] = scal[0..7], [8..15] = small[0..7], [16] = potrf info, [17] = potrs info
+// [0..7] = scal[0..7], [8..15] = small[0..7], [16] = potrf info, [17] = potrs info, [18] = |x|^2
 __global__ void pack_scalars_kernel(const double* __restrict__ scal, const double* __restrict__ small,
                                     const int* __restrict__ info, double* __restrict__ out) {
   const int i = threadIdx.x;
   if (i < 8) out[i] = scal[i];
   else if (i < 16) out[i] = small[i - 8];
   else if (i < 18) out[i] = (double)info[i - 16];
+  else if (i == 18) out[i] = scal[8];              // |x|^2 (xnorm_kernel), 0 unless parameter_tolerance > 0
 }
+
+// |x|^2 of Ceres' reduced program in ambient coordinates (ParameterToleranceReached: step_norm <= tol * (|x| + tol)):
+// unit quaternion + translation of every image whose block is not constant, non-constant camera blocks (f,cx,cy[,k]),
+// free points.  Only launched when parameter_tolerance > 0 (COLMAP's BA default is 0).  One CTA; out[0] = |x|^2.
+__global__ void xnorm_kernel(int S, int N, int dc, int ns, int model, const uint8_t* __restrict__ pconst,
+                             const uint8_t* __restrict__ point_const, const double* __restrict__ poses,
+                             const double* __restrict__ intr, const double* __restrict__ pts, double* __restrict__ out) {
+  double acc = 0.0;
+  const int np = model == VGG_SIMPLE_RADIAL ? 4 : 3;
+  for (int s = threadIdx.x; s < S; s += blockDim.x) {
+    const uint8_t* c = pconst + (size_t)s * dc;
+    if (!(c[0] && c[1] && c[2])) acc += 1.0;
+    if (!(c[3] && c[4] && c[5])) {
+      const double* P = poses + (size_t)s * 12;
+      acc += P[3] * P[3] + P[7] * P[7] + P[11] * P[11];
+    }
+    if (dc > 6) {
+      bool all_const = true;
+      for (int i = 6; i < dc; ++i) all_const = all_const && c[i];
+      if (!all_const)
+        for (int i = 0; i < np; ++i) acc += intr[(size_t)s * 4 + i] * intr[(size_t)s * 4 + i];
+    }
+  }
+  if (threadIdx.x == 0 && ns > 0) {
+    bool all_const = true;
+    for (int i = 0; i < ns; ++i) all_const = all_const && pconst[(size_t)S * dc + i];
+    if (!all_const)
+      for (int i = 0; i < np; ++i) acc += intr[i] * intr[i];
+  }
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    if (point_const && point_const[n]) continue;
+    acc += pts[3 * (size_t)n] * pts[3 * (size_t)n] + pts[3 * (size_t)n + 1] * pts[3 * (size_t)n + 1] +
+           pts[3 * (size_t)n + 2] * pts[3 * (size_t)n + 2];
+  }
+  __shared__ double red[32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    double v = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+    v = warp_sum(v);
+    if (threadIdx.x == 0) out[0] = v;
+  }
+}
+
+// CUDA events of one solve, destroyed on every exit path
+struct EventPair {
+  cudaEvent_t a = nullptr, b = nullptr;
+  ~EventPair() {
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+  }
+};
 
 static double* pinned_scalars() {
   static thread_local double* h = nullptr;
@@ -426,9 +480,10 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
   double* hdiag = rhs + L.Dpad;
   double* gvec = hdiag + L.Dpad;
 
-  cudaEvent_t ev0, ev1;
-  VGG_CUDA_CHECK(cudaEventCreate(&ev0));
-  VGG_CUDA_CHECK(cudaEventCreate(&ev1));
+  EventPair evs;
+  VGG_CUDA_CHECK(cudaEventCreate(&evs.a));
+  VGG_CUDA_CHECK(cudaEventCreate(&evs.b));
+  const cudaEvent_t ev0 = evs.a, ev1 = evs.b;
   VGG_CUDA_CHECK(cudaEventRecord(ev0, st));
 
   int cur = 0;
@@ -623,6 +678,13 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
     if (allreduce && (rc = allreduce(ar_user, L.small, 8 + (size_t)L.Dpad, 0, st))) return rc;
     if ((rc = launch_gradmax(D, N, L.small + 8, prob->param_const, L.blk[cand].g_p, prob->point_const, L.scal, st))) return rc;
     if (allreduce && (rc = allreduce(ar_user, L.scal + 5, 1, 1, st))) return rc;
+    if (opt.parameter_tolerance > 0.0) {
+      // |x| of THIS rank's points + the replicated cameras; with track shards the point part is a partial sum, which
+      // only makes the test stricter by under-estimating |x| (parameter_tolerance is 0 in every COLMAP preset)
+      xnorm_kernel<<<1, 1024, 0, st>>>(S, N, dc, ns, prob->camera_model, prob->param_const, prob->point_const,
+                                        L.poses[cur], L.intr[cur], L.points[cur], L.scal + 8);
+      VGG_LAUNCH_CHECK();
+    }
     if ((rc = read_scalars())) return rc;
     const int h_info[2] = {(int)h_scal[16], (int)h_scal[17]};
 
@@ -650,13 +712,17 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
     const double cost_change = cost - c_cost;
     const double rho = cost_change / model_change;
     if (tr) tr[4] = rho;
-    if (step_norm <= opt.parameter_tolerance * opt.parameter_tolerance) {
+    // Ceres ParameterToleranceReached(): step_norm <= tol * (|x| + tol), |x| over the non-constant blocks in ambient
+    // coordinates (h_scal[18], xnorm_kernel; only evaluated when the tolerance is non-zero -- COLMAP's default is 0)
+    const double x_norm = opt.parameter_tolerance > 0.0 ? sqrt(h_scal[18]) : 0.0;
+    if (step_norm <= opt.parameter_tolerance * (x_norm + opt.parameter_tolerance)) {
       summary->termination = VGG_BA_CONVERGENCE_PARAMETER;
       break;
     }
     const bool success = rho > opt.min_relative_decrease;
     if (fabs(cost_change) <= opt.function_tolerance * cost) {
-      if (success) { cur = cand; cost = c_cost; }
+      // Ceres 2.x TrustRegionMinimizer::Minimize returns from FunctionToleranceReached() before IsStepSuccessful() /
+      // HandleSuccessfulStep(): the candidate of the terminating iteration is discarded
       summary->termination = VGG_BA_CONVERGENCE_FUNCTION;
       break;
     }
@@ -685,8 +751,6 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
   VGG_CUDA_CHECK(cudaEventSynchronize(ev1));
   float ms = 0;
   VGG_CUDA_CHECK(cudaEventElapsedTime(&ms, ev0, ev1));
-  cudaEventDestroy(ev0);
-  cudaEventDestroy(ev1);
   summary->iterations = it;
   summary->final_cost = cost;
   summary->final_radius = radius;

@@ -360,12 +360,8 @@ __global__ void __launch_bounds__(PT) pose_refine_kernel(int S, int P, const flo
         sh.termination = VGG_BA_CONVERGENCE_PARAMETER;
         sh.state = ST_DONE;
       } else if (fabs(cost_change) <= opt.function_tolerance * sh.cost) {
-        if (good) {
-          for (int i = 0; i < 12; ++i) sh.pose[i] = sh.pose_c[i];
-          for (int i = 0; i < 4; ++i) sh.intr[i] = sh.intr_c[i];
-          sh.cost = c_cost;
-          sh.successful++;
-        }
+        // Ceres 2.x TrustRegionMinimizer::Minimize returns from FunctionToleranceReached() BEFORE IsStepSuccessful() /
+        // HandleSuccessfulStep(): the candidate of the terminating iteration is discarded, x stays the last accepted point
         sh.termination = VGG_BA_CONVERGENCE_FUNCTION;
         sh.state = ST_DONE;
       } else if (good) {

@@ -23,6 +23,7 @@
 //            scale by 2^(e_i+e_j) and RED into both triangles while the next item's MMAs already run.
 // Work items (tile, order group, k range) are built on the host, longest first, and strided over the CTAs.
 #include "common.cuh"
+#include "dev_probes.h"
 
 #include <algorithm>
 #include <vector>

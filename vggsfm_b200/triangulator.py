@@ -8,8 +8,13 @@ cfgs/demo.yaml:105-106): same ``forward`` arguments and the same 9-tuple back
   -> triangulate_tracks_and_BA -> robust_refine x (refine_pose -> triangulate_tracks_and_BA)
   -> BA_iters x iterative_global_BA -> validity masks (-> colours)
 
-The returned ``reconstruction`` is the tensor-backed stand-in of bundle_adjustment.Reconstruction, not a
-``pycolmap.Reconstruction`` (pycolmap is not a dependency of this path).
+The returned ``reconstruction`` is the pycolmap-shaped object of vggsfm_b200/reconstruction.py (same ``.images /
+.cameras / .points3D / .add_point3D / .deregister_image / .write`` surface the runner touches, runner.py:555-631),
+not a ``pycolmap.Reconstruction`` (pycolmap is not a dependency of this path).
+
+``get_EFP``, ``find_best_initial_pair`` and ``create_intri_matrix`` below are close transcriptions of the reference's
+dozen tensor statements each (models/utils.py:38-72, models/triangulator.py:442-476): host glue whose semantics must
+match statement for statement; they are pinned to goldens produced by the reference (tests/test_host_mirrors.py).
 """
 from __future__ import annotations
 
@@ -173,7 +178,10 @@ class Triangulator(torch.nn.Module):
             valid_track_rgb = pred_track_rgb[:, valid_tracks]
             sum_rgb = (BA_inlier_masks.float()[..., None] * valid_track_rgb).sum(dim=0)
             points3D_rgb = sum_rgb / BA_inlier_masks.sum(dim=0)[:, None]
-            reconstruction.points3D_rgb = points3D_rgb
+            if points3D_rgb.shape[0] == max(reconstruction.point3D_ids()):           # :333-340
+                reconstruction.set_point_colors(points3D_rgb)
+            else:
+                print("Cannot save point rgb colors to colmap reconstruction object.")
         return (extrinsics, intrinsics, extra_params, points3D, points3D_rgb, reconstruction, valid_frame_mask,
                 valid_2D_mask, valid_tracks)
 
