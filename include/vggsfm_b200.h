@@ -125,13 +125,14 @@ int vgg_ba_schur(const vgg_ba_problem* prob, const double* camrec, const double*
                  double* Sraw, double* rhs, int* Dpad_out, void* stream);
 
 /* Blocked Cholesky of the reduced camera system (csrc/chol.cu): in-place factorisation of the row-major
- * lower triangle of A [n x n], leading dimension lda (even), replacing the potrf inside Ceres' DENSE_SCHUR.
- * workspace >= ceil(n/64)*32768 + 256 bytes; *info_host = 0 or the 1-based index of the failing pivot. */
+ * lower triangle of A [n x n], leading dimension lda (even), replacing the potrf inside Ceres' DENSE_SCHUR.  On
+ * return the lower triangle holds L and the strict upper triangle L^T.
+ * workspace >= ceil(n/128)*131072 + 256 bytes; *info_host = 0 or the 1-based index of the failing pivot. */
 int vgg_cholesky_lower(int n, int lda, double* A, void* workspace, size_t ws_bytes, int* info_host, void* stream);
 
 /* The same SYRK step on the tensor cores (csrc/syrk_i8.cu): Cmat[Dpad,Dpad] -= Zt^T Zt for Zt double [Kpad,Dpad]
  * (Dpad a multiple of 128), FP64-equivalent through `slices` (3..7; 7 = 54 fractional bits) int8
- * Ozaki slices on tcgen05.mma kind::i8 with exact int32 accumulation in TMEM.  Both triangles are written.
+ * Ozaki slices on tcgen05.mma kind::i8 with exact int32 accumulation in TMEM.  The row-major LOWER triangle is written.
  * Selected inside vgg_ba_solve by VGG_SYRK=ozaki[:slices]; exposed for the parity tests and profiling. */
 int vgg_syrk_ozaki_workspace_bytes(int Kpad, int Dpad, int slices, size_t* bytes);
 int vgg_syrk_ozaki(int Kpad, int Dpad, const double* Zt, double* Cmat, int slices, void* workspace, size_t ws_bytes,

@@ -379,7 +379,10 @@ def lm_solve(poses, intr, points, uv, mask, model, mode, param_const=None, point
         Hc, gc = _assemble_camera_system(blk, S, dc, ns)
         return blk, Hc, gc
 
+    import time as _time
+    _t0 = _time.perf_counter()
     blk, Hc, gc = evaluate(poses, intr, points)
+    _t_init = _time.perf_counter() - _t0        # initial evaluation (not an LM iteration): bench.py subtracts it
     cost = float(ar(np.array([blk["cost"]]))[0])
     Hc_diag = ar(np.diag(Hc).copy())
     gc_glob = ar(gc.copy())
@@ -398,7 +401,8 @@ def lm_solve(poses, intr, points, uv, mask, model, mode, param_const=None, point
 
     radius = opt.initial_trust_region_radius
     decrease_factor = 2.0
-    summary = {"iterations": 0, "successful": 0, "initial_cost": cost, "termination": "NO_CONVERGENCE"}
+    summary = {"iterations": 0, "successful": 0, "initial_cost": cost, "termination": "NO_CONVERGENCE",
+               "initial_eval_s": _t_init}
     gmax = grad_max_norm(gc_glob, blk["g_p"])
     if gmax <= opt.gradient_tolerance:
         summary.update(termination="CONVERGENCE_GRADIENT", final_cost=cost)

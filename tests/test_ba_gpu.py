@@ -228,9 +228,10 @@ def test_c2_full_size_properties(cuda_dev):
     assert 0.25 < rms < 0.5, rms            # 0.3 px noise per coordinate -> ~0.42 px per observation
 
 
-@pytest.mark.parametrize("n", [64, 100, 343, 2402])
+@pytest.mark.parametrize("n", [64, 100, 343, 512, 2403])
 def test_cholesky_matches_lapack(cuda_dev, n):
-    """csrc/chol.cu against numpy.linalg.cholesky (float64; 1e-10 of the factor's scale), plus failure reporting."""
+    """csrc/chol.cu -- the factorisation of the default LM path -- against numpy.linalg.cholesky (float64; 1e-10 of the
+    factor's scale; L in the lower triangle, L^T mirrored into the upper one), plus failure reporting."""
     import ctypes
     import torch
     from vggsfm_b200 import _lib
@@ -240,15 +241,17 @@ def test_cholesky_matches_lapack(cuda_dev, n):
     lda = (n + 127) // 128 * 128
     buf = torch.zeros(n, lda, dtype=torch.float64, device=cuda_dev)
     buf[:, :n] = torch.from_numpy(np.tril(A)).to(cuda_dev)
-    ws = torch.empty(((n + 63) // 64) * 32768 + 256, dtype=torch.uint8, device=cuda_dev)
+    ws = torch.empty(((n + 127) // 128) * 131072 + 256, dtype=torch.uint8, device=cuda_dev)
     info = ctypes.c_int(-1)
     L = _lib.lib()
     _lib.check(L.vgg_cholesky_lower(n, lda, buf.data_ptr(), ws.data_ptr(), ws.numel(), ctypes.byref(info),
                                     torch.cuda.current_stream().cuda_stream), "vgg_cholesky_lower")
     assert info.value == 0
     ref = np.linalg.cholesky(A)
-    got = np.tril(buf.cpu().numpy()[:, :n])
+    full = buf.cpu().numpy()[:, :n]
+    got = np.tril(full)
     assert np.abs(got - ref).max() <= 1e-10 * np.abs(ref).max()
+    assert np.array_equal(np.triu(full, 1), np.tril(full, -1).T)       # the mirror the backward substitution streams
     # not positive definite -> info reports the failing pivot (1-based)
     A2 = A.copy()
     A2[70 % n, 70 % n] = -1.0

@@ -24,7 +24,10 @@ def _run(Z, s, dev):
         _lib.check(L.vgg_syrk_ozaki(Kpad, Dpad, Zt.data_ptr(), C.data_ptr(), s, ws.data_ptr(), ws.numel(),
                                     torch.cuda.current_stream().cuda_stream), "vgg_syrk_ozaki")
         torch.cuda.synchronize()
-    return C.cpu().numpy()
+    full = C.cpu().numpy()
+    assert not np.triu(full, 1).any()                  # only the row-major LOWER triangle is written (csrc/chol.cu factors it)
+    low = np.tril(full)
+    return low + np.tril(low, -1).T
 
 
 def _case(Dpad, Kpad, seed):
@@ -44,7 +47,6 @@ def test_matches_float64(cuda_dev, Dpad, Kpad, s, tol):
     bound = np.abs(Z).T @ np.abs(Z)
     err = np.abs(got - ref)
     assert np.all(err <= tol * bound + 1e-300), (err / (bound + 1e-300)).max()
-    assert np.all(np.abs(got - got.T) <= 2.0 ** -50 * bound)      # mirrored entries differ only by the RED arrival order
     assert not got[:, -5:].any()
 
 

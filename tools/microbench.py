@@ -78,7 +78,7 @@ if mode in ("pose", "pipeline"):
     sys.exit(0)
 
 if mode == "chol":
-    n = int(sys.argv[2]) if len(sys.argv) > 2 else 2402
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 2403
     rng = np.random.default_rng(0)
     B = rng.normal(size=(n, n + 8))
     A = np.tril(B @ B.T + n * 1e-3 * np.eye(n))
@@ -86,7 +86,7 @@ if mode == "chol":
     src = torch.zeros(n, lda, dtype=torch.float64, device=dev)
     src[:, :n] = torch.from_numpy(A).to(dev)
     buf = src.clone()
-    ws = torch.empty(((n + 63) // 64) * 32768 + 256, dtype=torch.uint8, device=dev)
+    ws = torch.empty(((n + 127) // 128) * 131072 + 256, dtype=torch.uint8, device=dev)
     L = _lib.lib()
     st = torch.cuda.current_stream().cuda_stream
 
@@ -97,7 +97,11 @@ if mode == "chol":
     t_copy = timeit(lambda: buf.copy_(src))
     Afull = src[:, :n] + torch.tril(src[:, :n], -1).T
     t_torch = timeit(lambda: torch.linalg.cholesky(Afull))
-    print(f"[{tag}] cholesky n={n}: own {t_all - t_copy:.3f} ms   torch.linalg.cholesky {t_torch:.3f} ms")
+    run()
+    torch.cuda.synchronize()
+    got = torch.tril(buf[:, :n])
+    err = (got @ got.T - Afull).abs().max().item() / Afull.abs().max().item()
+    print(f"[{tag}] cholesky n={n}: own {t_all - t_copy:.3f} ms   torch.linalg.cholesky {t_torch:.3f} ms   |LL^T-A|/|A| = {err:.2e}")
 else:
     S = 400
     N = int(sys.argv[2]) if len(sys.argv) > 2 else 4096

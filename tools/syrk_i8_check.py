@@ -44,11 +44,13 @@ ws = torch.empty(nb.value, dtype=torch.uint8, device=dev)
 st = torch.cuda.current_stream().cuda_stream
 _lib.check(L.vgg_syrk_ozaki(Kpad, Dpad, Zt.data_ptr(), C.data_ptr(), s, ws.data_ptr(), ws.numel(), st), "syrk")
 torch.cuda.synchronize()
-got = C.cpu().numpy()
+got = np.tril(C.cpu().numpy())                      # the kernel writes the row-major LOWER triangle
+upper_untouched = not np.triu(C.cpu().numpy(), 1).any()
+got = got + np.tril(got, -1).T
 ref = -(Z.T @ Z)
 bound = np.abs(Z).T @ np.abs(Z) + 1e-300
 err = np.abs(got - ref) / bound
-print(f"Dpad={Dpad} Kpad={Kpad} slices={s}: max |err| / (|Z|^T|Z|) = {err.max():.3e}   symmetric: {np.array_equal(got, got.T)}  "
+print(f"Dpad={Dpad} Kpad={Kpad} slices={s}: max |err| / (|Z|^T|Z|) = {err.max():.3e}   symmetric: {upper_untouched}  "
       f"nonzero frac {np.mean(got != 0):.3f}")
 if err.max() > 1e-6:
     i, j = np.unravel_index(np.argmax(err), err.shape)

@@ -209,7 +209,7 @@ constexpr int SY_BM = 128, SY_BK = 16, SY_THREADS = 256, SY_STAGES = 3;
 
 __global__ void __launch_bounds__(SY_THREADS) syrk_kernel(int Kpad, int Dpad, int k_per_split,
                                                           const double* __restrict__ Zt, double* __restrict__ Cmat,
-                                                          ptrdiff_t mc_off) {
+                                                          ptrdiff_t mc_off, int fill_upper) {
   extern __shared__ __align__(16) double sy_smem[];
   // tile decode: blockIdx.x -> (bi >= bj)
   int t = blockIdx.x;
@@ -291,13 +291,13 @@ __global__ void __launch_bounds__(SY_THREADS) syrk_kernel(int Kpad, int Dpad, in
     for (int j = 0; j < 8; ++j) {
       const int c = bj * SY_BM + tx * 2 + (j & 1) + 32 * (j >> 1);
       if (acc[i][j] != 0.0) {
-        // both triangles: row-major lower (own Cholesky) == column-major upper, and its mirror (cuSOLVER LOWER)
-        // fabric mode: only the triangle the library factorisation reads (column-major lower), one multimem op each
-        if (!mc_off && (!diag || c <= r)) atomicAdd(&Cmat[(size_t)r * Dpad + c], -acc[i][j]);
-        if (!diag || c < r || (mc_off && c == r)) {
-          double* q = &Cmat[(size_t)c * Dpad + r];
+        // row-major LOWER triangle (what csrc/chol.cu factors; in fabric mode one multimem op per element); the mirror
+        // only for the library factorisation A/B (fill_upper: cuSOLVER's fast path reads the column-major lower view)
+        if (!diag || c <= r) {
+          double* q = &Cmat[(size_t)r * Dpad + c];
           ar_add(q, mc_off ? q + mc_off : nullptr, -acc[i][j]);
         }
+        if (fill_upper && (!diag || c < r)) atomicAdd(&Cmat[(size_t)c * Dpad + r], -acc[i][j]);
       }
     }
   }
@@ -317,7 +317,8 @@ __device__ __forceinline__ void dmma_m8n8k4(double& d0, double& d1, double a, do
 
 __global__ void __launch_bounds__(SY_THREADS) syrk_dmma_kernel(int Kpad, int Dpad, int k_per_split,
                                                                const double* __restrict__ Zt,
-                                                               double* __restrict__ Cmat, ptrdiff_t mc_off) {
+                                                               double* __restrict__ Cmat, ptrdiff_t mc_off,
+                                                               int fill_upper) {
   extern __shared__ __align__(16) double sd_smem[];
   int t = blockIdx.x;
   int bi = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
@@ -398,11 +399,11 @@ __global__ void __launch_bounds__(SY_THREADS) syrk_dmma_kernel(int Kpad, int Dpa
         const double v = c[i][j][h];
         const int col = cc + h;
         if (v != 0.0) {
-          if (!mc_off && (!diag || col <= r)) atomicAdd(&Cmat[(size_t)r * Dpad + col], -v);
-          if (!diag || col < r || (mc_off && col == r)) {                         // mirror / fabric triangle
-            double* q = &Cmat[(size_t)col * Dpad + r];
+          if (!diag || col <= r) {
+            double* q = &Cmat[(size_t)r * Dpad + col];
             ar_add(q, mc_off ? q + mc_off : nullptr, -v);
           }
+          if (fill_upper && (!diag || col < r)) atomicAdd(&Cmat[(size_t)col * Dpad + r], -v);   // library A/B only
         }
       }
     }
@@ -410,14 +411,15 @@ __global__ void __launch_bounds__(SY_THREADS) syrk_dmma_kernel(int Kpad, int Dpa
 }
 
 // ------------------------------------------------------------------------------------------------
-// A (both triangles, in place) = sc_i sc_j Sraw + diag; constant parameters pinned; b = sc * rhs
+// A (in place) = sc_i sc_j Sraw + diag; constant parameters pinned; b = sc * rhs.  Lower triangle only unless
+// fill_upper (library factorisation A/B, which reads the mirror).
 __global__ void scale_damp_kernel(int D, int Dpad, double* __restrict__ A, const double* __restrict__ rhs,
                                   const double* __restrict__ hdiag, const double* __restrict__ sc,
                                   const uint8_t* __restrict__ pconst, double radius, double min_diag, double max_diag,
-                                  double* __restrict__ bvec) {
+                                  double* __restrict__ bvec, int fill_upper) {
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const int i = blockIdx.y;
-  if (j >= D) return;            // both triangles (the factorisation may read either)
+  if (j >= D || (!fill_upper && j > i)) return;
   const bool ci = pconst[i] != 0, cj = pconst[j] != 0;
   double v;
   if (ci || cj) {
@@ -428,12 +430,14 @@ __global__ void scale_damp_kernel(int D, int Dpad, double* __restrict__ A, const
   }
   A[(size_t)i * Dpad + j] = v;
   if (i == j) {
-    // The scaled right-hand side also goes into column D of the buffer (row D of its column-major view): the
-    // factorisation of the bordered matrix [[A, b], [b^T, c]] = [[L, 0], [y^T, .]] leaves y = L^-1 b there, i.e.
-    // the forward substitution comes out of potrf for free (csrc/ba_solve.cu).  c only has to exceed y^T y.
+    // The scaled right-hand side also becomes row D of the matrix (in the workspace rhs IS row D, so this scales it in
+    // place; the library A/B wants it as column D = row D of its column-major view): the factorisation of the bordered
+    // matrix [[A, b], [b^T, c]] = [[L, 0], [y^T, .]] leaves y = L^-1 b there, i.e. the forward substitution comes out
+    // of the factorisation for free (csrc/ba_solve.cu).  c only has to exceed y^T y.
     const double b = ci ? 0.0 : rhs[i] * sc[i];
     bvec[i] = b;
-    A[(size_t)i * Dpad + D] = b;
+    if (fill_upper) A[(size_t)i * Dpad + D] = b;
+    else A[(size_t)D * Dpad + i] = b;
     if (i == 0) A[(size_t)D * Dpad + D] = 1e300;
   }
 }
@@ -628,6 +632,10 @@ int launch_z_transpose(int D, int N, int Dpad, const double* W, const double* M,
   VGG_LAUNCH_CHECK();
   return VGG_OK;
 }
+// 0 (default): the reduced system is kept as a row-major LOWER triangle (csrc/chol.cu); 1: both triangles, for the
+// library factorisation A/B (set by csrc/ba_solve.cu from VGG_CHOL)
+int g_fill_upper = 0;
+
 int launch_syrk(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t mc_off, cudaStream_t st) {
   const int nb = Dpad / SY_BM;
   const int ntiles = nb * (nb + 1) / 2;
@@ -650,8 +658,8 @@ int launch_syrk(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t mc
     attr_set = true;
   }
   dim3 grid(ntiles, splits);
-  if (use_dmma) syrk_dmma_kernel<<<grid, SY_THREADS, smem_d, st>>>(Kpad, Dpad, slabs_per * SY_BK, Zt, Cmat, mc_off);
-  else syrk_kernel<<<grid, SY_THREADS, smem, st>>>(Kpad, Dpad, slabs_per * SY_BK, Zt, Cmat, mc_off);
+  if (use_dmma) syrk_dmma_kernel<<<grid, SY_THREADS, smem_d, st>>>(Kpad, Dpad, slabs_per * SY_BK, Zt, Cmat, mc_off, g_fill_upper);
+  else syrk_kernel<<<grid, SY_THREADS, smem, st>>>(Kpad, Dpad, slabs_per * SY_BK, Zt, Cmat, mc_off, g_fill_upper);
   VGG_LAUNCH_CHECK();
   return VGG_OK;
 }
@@ -659,7 +667,7 @@ int launch_scale_damp(int D, int Dpad, double* A, const double* rhs, const doubl
                       const uint8_t* pconst, double radius, double min_diag, double max_diag, double* bvec,
                       cudaStream_t st) {
   dim3 grid((D + 255) / 256, D);
-  scale_damp_kernel<<<grid, 256, 0, st>>>(D, Dpad, A, rhs, hdiag, sc, pconst, radius, min_diag, max_diag, bvec);
+  scale_damp_kernel<<<grid, 256, 0, st>>>(D, Dpad, A, rhs, hdiag, sc, pconst, radius, min_diag, max_diag, bvec, g_fill_upper);
   VGG_LAUNCH_CHECK();
   return VGG_OK;
 }

@@ -60,6 +60,7 @@ int launch_trsv_upper(int n, int lda, const double* A, const double* y, size_t y
                       cudaStream_t st);
 size_t chol_workspace_doubles(int n);
 int chol_lower_inplace(int n, int lda, double* A, double* Ldiag, int* info, cudaStream_t st);
+extern int g_fill_upper;       // csrc/ba_schur.cu: 1 = also write the mirror triangle (library factorisation A/B)
 
 // gathers the accept/reject scalars into one 24-double record so the host reads them with ONE copy:
 // [0..7] = scal[0..7], [8..15] = small[0..7], [16] = potrf info, [17] = potrs info, [18] = |x|^2
@@ -226,7 +227,7 @@ static int make_layout(int S, int N, int model, int mode, void* base, size_t cap
   L->packed = c.take<double>(32);
   L->potrf_lwork = potrf_lwork;
   L->potrf_work = c.take<double>(potrf_lwork);
-  L->chol_diag = c.take<double>(chol_workspace_doubles(L->D));
+  L->chol_diag = c.take<double>(chol_workspace_doubles(L->D + 1));
   L->dev_info = c.take<int>(4);
   L->trsv_flags = c.take<int>(trsv_workspace_ints(L->D));
   L->oz_bytes = syrk_i8_workspace_bytes(L->Kpad, L->Dpad, 7);
@@ -479,6 +480,14 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
   double* rhs = L.AR + (size_t)D * L.Dpad;
   double* hdiag = rhs + L.Dpad;
   double* gvec = hdiag + L.Dpad;
+  // factorisation: 2 = csrc/chol.cu (default), 0 = cuSOLVER Xpotrf (VGG_CHOL=lib), 1 = cuSOLVER Dpotrf (VGG_CHOL=legacy)
+  static const int chol_mode = [] {
+    const char* e = getenv("VGG_CHOL");
+    if (!e || !e[0] || e[0] == 'o') return 2;
+    return (e[0] == 'l' && e[1] == 'e') ? 1 : 0;
+  }();
+  const int cm = mc_off ? 2 : chol_mode;           // fabric mode reduces the lower triangle only
+  g_fill_upper = cm != 2;
 
   EventPair evs;
   VGG_CUDA_CHECK(cudaEventCreate(&evs.a));
@@ -569,28 +578,23 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
     if ((rc = launch_scale_damp(D, L.Dpad, Sraw, rhs, hdiag, L.sc_c, prob->param_const, radius, opt.min_lm_diagonal,
                                 opt.max_lm_diagonal, L.bvec, st)))
       return rc;
-    // Factor the reduced system.  The buffer holds both triangles.  Default: cuSOLVER's 64-bit potrf on the
-    // column-major LOWER view (1.1 ms at n = 2402; its UPPER path takes 3.7 ms, r01 A/B).  VGG_CHOL=own selects the
-    // in-repo blocked Cholesky (csrc/chol.cu, row-major lower == column-major upper, 2.0 ms), VGG_CHOL=legacy the
-    // 32-bit cusolverDnDpotrf.
-    static const int chol_mode = [] {
-      const char* e = getenv("VGG_CHOL");
-      return !e ? 0 : (e[0] == 'o' ? 2 : (e[0] == 'l' ? 1 : 0));
-    }();
-    const int cm = (mc_off && chol_mode == 2) ? 0 : chol_mode;      // fabric mode reduces one triangle only
-    const cublasFillMode_t uplo = (cm == 2) ? CUBLAS_FILL_MODE_UPPER : CUBLAS_FILL_MODE_LOWER;
-    // Library paths factor the BORDERED matrix of order D+1 (scale_damp put the right-hand side in column D of the
-    // buffer = row D of the column-major view): potrf then leaves y = L^-1 b in that row, and only the backward
-    // substitution L^T x = y remains (one cublasDtrsv on the strided row instead of potrs' two: -0.17 ms at C3).
+    // Factor the reduced system.  Default: the in-repo blocked Cholesky (csrc/chol.cu) on the row-major LOWER triangle,
+    // of the BORDERED matrix of order D+1 -- scale_damp put the scaled right-hand side into row D, so the factorisation
+    // leaves y = L^-1 b there (and, mirrored like every panel, in column D): the forward substitution costs nothing and
+    // only the backward substitution L^T x = y remains.  VGG_CHOL=lib (cuSOLVER 64-bit potrf on the column-major LOWER
+    // view, r01 default, 1.05 ms at n = 2403) and VGG_CHOL=legacy (32-bit potrf) are kept for A/B; they need the mirror
+    // triangle (g_fill_upper) and are not available in fabric mode.
     const int nfac = D + 1;
-    if (cm == 0) {
+    if (cm == 2) {
+      if ((rc = chol_lower_inplace(nfac, L.Dpad, Sraw, L.chol_diag, L.dev_info, st))) return rc;
+    } else if (cm == 0) {
       static thread_local cusolverDnParams_t xp = nullptr;
       static thread_local void* xdev_fallback = nullptr;
       static thread_local void* xhost = nullptr;
       static thread_local size_t xdev_b = 0, xhost_b = 0;
       if (!xp) cusolverDnCreateParams(&xp);
       size_t db = 0, hb = 0;
-      if (cusolverDnXpotrf_bufferSize(cs, xp, uplo, nfac, CUDA_R_64F, Sraw, L.Dpad, CUDA_R_64F, &db, &hb) !=
+      if (cusolverDnXpotrf_bufferSize(cs, xp, CUBLAS_FILL_MODE_LOWER, nfac, CUDA_R_64F, Sraw, L.Dpad, CUDA_R_64F, &db, &hb) !=
           CUSOLVER_STATUS_SUCCESS) {
         set_error("cusolverDnXpotrf_bufferSize failed");
         return VGG_ESOLVER;
@@ -603,28 +607,24 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
         xdev = xdev_fallback;
       }
       if (hb > xhost_b) { free(xhost); xhost = malloc(hb); xhost_b = hb; }
-      if (cusolverDnXpotrf(cs, xp, uplo, nfac, CUDA_R_64F, Sraw, L.Dpad, CUDA_R_64F, xdev, db, xhost, hb, L.dev_info) !=
-          CUSOLVER_STATUS_SUCCESS) {
+      if (cusolverDnXpotrf(cs, xp, CUBLAS_FILL_MODE_LOWER, nfac, CUDA_R_64F, Sraw, L.Dpad, CUDA_R_64F, xdev, db, xhost, hb,
+                           L.dev_info) != CUSOLVER_STATUS_SUCCESS) {
         set_error("cusolverDnXpotrf failed to launch");
         return VGG_ESOLVER;
       }
-    } else if (cm == 1) {
-      if (cusolverDnDpotrf(cs, uplo, nfac, Sraw, L.Dpad, L.potrf_work, (int)L.potrf_lwork, L.dev_info) !=
+      g_launch_count += 1;
+    } else {
+      if (cusolverDnDpotrf(cs, CUBLAS_FILL_MODE_LOWER, nfac, Sraw, L.Dpad, L.potrf_work, (int)L.potrf_lwork, L.dev_info) !=
           CUSOLVER_STATUS_SUCCESS) {
         set_error("cusolverDnDpotrf failed to launch");
         return VGG_ESOLVER;
       }
-    } else if ((rc = chol_lower_inplace(D, L.Dpad, Sraw, L.chol_diag, L.dev_info, st))) {
-      return rc;
+      g_launch_count += 1;
     }
+    // Backward substitution on U = L^T (the row-major upper triangle in every mode), y = column D of the buffer.
     const double* dcs = L.bvec;
     size_t dcs_stride = 1;
-    if (cm == 2) {
-      if (cusolverDnDpotrs(cs, uplo, D, 1, Sraw, L.Dpad, L.bvec, L.Dpad, L.dev_info + 1) != CUSOLVER_STATUS_SUCCESS) {
-        set_error("cusolverDnDpotrs failed to launch");
-        return VGG_ESOLVER;
-      }
-    } else {
+    {
       static const bool lib_trsv = [] {
         const char* e = getenv("VGG_TRSV");
         return e && e[0] == 'c';                     // VGG_TRSV=cublas keeps the library call for A/B
@@ -641,6 +641,7 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
           set_error("cublasDtrsv failed to launch");
           return VGG_ESOLVER;
         }
+        g_launch_count += 1;
         dcs = Sraw + D;
         dcs_stride = (size_t)L.Dpad;
       } else {
@@ -648,7 +649,6 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
         if ((rc = launch_trsv_upper(D, L.Dpad, Sraw, Sraw + D, (size_t)L.Dpad, L.bvec, L.trsv_flags, 1, st))) return rc;
       }
     }
-    g_launch_count += 1;
     if ((rc = launch_cam_step(D, dcs, dcs_stride, L.sc_c, hdiag, gvec, prob->param_const, radius, opt.min_lm_diagonal,
                               opt.max_lm_diagonal, L.d_c, L.scal, st)))
       return rc;

@@ -1,39 +1,47 @@
-// Blocked right-looking Cholesky of the reduced camera system (row-major, lower triangle, in place).
-//
-// The reduced system of configuration C3 is 2402 x 2402 float64: cuSOLVER's potrf spends ~3.4 ms in ~250
-// tiny launches on it, more than the Schur build once the tracks are sharded over GPUs.  This
-// factorisation uses two launches per 64-column panel:
-//   chol_panel_kernel     every CTA re-factors the 64x64 diagonal block in shared memory in 8-column
-//                         micro-panels (8x8 leaf in registers with shuffles + rsqrt, 3 CTA barriers per
-//                         micro-panel), then a right-looking triangular solve, 4 threads per row, turns its 64
-//                         panel rows into L_ik.  CTA 0 parks the factored diagonal block in a side buffer.
-//   chol_trailing_kernel  A22 -= P P^T on 64x64 tiles with the whole K=64 panel resident in shared memory.
-// and one copy-back of the diagonal blocks at the end.  Ceres' counterpart: DENSE_SCHUR's LLT / LAPACK potrf
-// inside SchurComplementSolver (reached from pycolmap.bundle_adjustment).
+// Blocked right-looking Cholesky of the reduced camera system (row-major, lower triangle, in place) -- the
+// factorisation inside Ceres' DENSE_SCHUR (LAPACK potrf reached from pycolmap.bundle_adjustment), and the largest
+// serial piece of a bundle-adjustment iteration: n = 2403 at 400 frames (bordered with the right-hand side), 4.6 GFLOP
+// of float64 whose cost is a dependency chain, not arithmetic.  128-column panels; per panel
+//   chol_panel_kernel   EVERY CTA re-factors the 128x128 diagonal block in shared memory (8-column micro-panels: 8x8
+//                       leaf in registers with shuffles + rsqrt, one thread per row below it, 4x4 register tiles for the
+//                       rank-8 update), so no CTA waits for another one; it then solves its own 16 panel rows against
+//                       the block (16 threads per row, right-looking) and writes them back together with their
+//                       transpose: the upper triangle ends up holding L^T, which is what the backward substitution
+//                       kernel (csrc/trsv.cu) streams row by row.  <= 143 CTAs: one wave.
+//   chol_update_kernel  A22 -= P P^T on 64x64 tiles with mma.sync.m8n8k4.f64 (SASS DMMA), the K=128 panel rows of both
+//                       operands resident in shared memory (row stride 132 doubles: conflict-free fragment loads
+//                       straight from the row-major panel, no transpose), loaded in two cp.async halves so the second
+//                       half lands under the first half's math.
+// One-panel lookahead: the update of panel b first refreshes the next panel's 128 columns (mode 1, ~70 tiles); panel
+// b+1 is then factored on a high-priority side stream while the main stream finishes the rest of the update (mode 2).
+// The whole launch sequence (3 kernels + 2 events per panel) is captured once per (matrix, order) into a CUDA graph.
 #include <stdlib.h>
+#include <map>
+#include <tuple>
 #include "common.cuh"
 
 namespace vgg {
 
-constexpr int CH_NB = 64;
-constexpr int CH_LD = 66;     // shared-memory row stride (even: 16-byte aligned pairs; 66*2 mod 32 = 4: conflict-free)
+constexpr int CB = 128;       // panel width
+constexpr int CLD = 132;      // shared-memory row stride (doubles): rows 16-byte aligned, DMMA fragment loads conflict-free
+constexpr int C_RPC = 16;     // panel rows per CTA in the triangular solve
+constexpr int CT = 64;        // trailing-update tile
+constexpr int C_THREADS = 256;
 
-// Cholesky of the 64x64 block in shared memory Ls (row stride CH_LD) by the whole CTA (256 threads), in
-// 8-column micro-panels: (a) warp 0 factors the 8x8 diagonal micro-block in registers (one row per lane,
-// shuffles for the pivot column, rsqrt instead of sqrt+divide), (b) one thread per row below solves its 8
-// entries against it, (c) all threads apply the rank-8 update to the rest of the block.  Three CTA barriers per
-// micro-panel instead of three per column.  dinv[j] = 1 / L[j][j].  Returns 0 or 1 + first bad pivot (all threads).
-__device__ __forceinline__ int cta_chol64(double* Ls, double* dinv, int* fail_sm, int tid) {
+// Cholesky of the 128x128 block in shared memory Ls (row stride CLD) by the whole CTA (256 threads).  Lower triangle
+// in, L out (entries above the diagonal are left undefined).  dinv[j] = 1 / L[j][j].  Returns 0 or 1 + first bad pivot.
+__device__ __forceinline__ int cta_chol128(double* Ls, double* dinv, int* fail_sm, int tid) {
   const int lane = tid & 31, warp = tid >> 5;
   if (tid == 0) *fail_sm = 0;
   __syncthreads();
-  for (int p = 0; p < 8; ++p) {
+  for (int p = 0; p < CB / 8; ++p) {
     const int c0 = p * 8;
     if (warp == 0) {
+      // (a) 8x8 leaf: one row per lane (lanes 8..31 mirror lanes 0..7), pivot column through shuffles
       double a[8];
       const int r = c0 + (lane & 7);
 #pragma unroll
-      for (int c = 0; c < 8; ++c) a[c] = Ls[r * CH_LD + c0 + c];
+      for (int c = 0; c < 8; ++c) a[c] = Ls[r * CLD + c0 + c];
       int fail = 0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -50,42 +58,66 @@ __device__ __forceinline__ int cta_chol64(double* Ls, double* dinv, int* fail_sm
       }
       if (lane < 8) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) Ls[r * CH_LD + c0 + c] = (c <= lane) ? a[c] : 0.0;
+        for (int c = 0; c < 8; ++c) Ls[r * CLD + c0 + c] = (c <= lane) ? a[c] : 0.0;
       }
       if (lane == 0 && fail && *fail_sm == 0) *fail_sm = fail;
     }
     __syncthreads();
-    // (b) rows below the micro-block: x L^T = a  (one thread per row)
+    // (b) rows below the micro-block: x L^T = a, one thread per row
     {
       const int r = c0 + 8 + tid;
-      if (r < CH_NB) {
+      if (r < CB) {
         double x[8];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) x[c] = Ls[r * CH_LD + c0 + c];
+        for (int c = 0; c < 8; c += 2) {
+          const double2 v = *reinterpret_cast<const double2*>(Ls + r * CLD + c0 + c);
+          x[c] = v.x;
+          x[c + 1] = v.y;
+        }
 #pragma unroll
         for (int m = 0; m < 8; ++m) {
           x[m] *= dinv[c0 + m];
 #pragma unroll
-          for (int j = m + 1; j < 8; ++j) x[j] = fma(-x[m], Ls[(c0 + j) * CH_LD + c0 + m], x[j]);
+          for (int j = m + 1; j < 8; ++j) x[j] = fma(-x[m], Ls[(c0 + j) * CLD + c0 + m], x[j]);
         }
 #pragma unroll
-        for (int c = 0; c < 8; ++c) Ls[r * CH_LD + c0 + c] = x[c];
+        for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2*>(Ls + r * CLD + c0 + c) = make_double2(x[c], x[c + 1]);
       }
     }
     __syncthreads();
-    // (c) rank-8 update of the remaining lower triangle: rows/cols >= c0+8
+    // (c) rank-8 update of the remaining lower triangle (rows/cols >= c0+8) in 4x4 register tiles
     {
-      const int m = CH_NB - (c0 + 8);           // remaining dimension
-      for (int e = tid; e < m * m; e += 256) {
-        const int i = e / m, c = e - i * m;
-        if (c <= i) {
-          const double* li = Ls + (c0 + 8 + i) * CH_LD + c0;
-          const double* lc = Ls + (c0 + 8 + c) * CH_LD + c0;
-          double s = Ls[(c0 + 8 + i) * CH_LD + c0 + 8 + c];
+      const int base = c0 + 8;
+      const int tm = (CB - base) >> 2;                 // tiles per side
+      const int count = tm * (tm + 1) / 2;
+      for (int e = tid; e < count; e += C_THREADS) {
+        int ti = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
+        while ((ti + 1) * (ti + 2) / 2 <= e) ++ti;
+        while (ti * (ti + 1) / 2 > e) --ti;
+        const int tj = e - ti * (ti + 1) / 2;
+        const int i0 = base + 4 * ti, j0 = base + 4 * tj;
+        double li[4][8], lj[4][8];
 #pragma unroll
-          for (int k = 0; k < 8; ++k) s = fma(-li[k], lc[k], s);
-          Ls[(c0 + 8 + i) * CH_LD + c0 + 8 + c] = s;
-        }
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int k = 0; k < 8; k += 2) {
+            const double2 u = *reinterpret_cast<const double2*>(Ls + (i0 + a) * CLD + c0 + k);
+            li[a][k] = u.x;
+            li[a][k + 1] = u.y;
+            const double2 w = *reinterpret_cast<const double2*>(Ls + (j0 + a) * CLD + c0 + k);
+            lj[a][k] = w.x;
+            lj[a][k + 1] = w.y;
+          }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) {
+            if (ti == tj && b > a) continue;
+            double s = Ls[(i0 + a) * CLD + j0 + b];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s = fma(-li[a][k], lj[b][k], s);
+            Ls[(i0 + a) * CLD + j0 + b] = s;
+          }
       }
     }
     __syncthreads();
@@ -93,204 +125,346 @@ __device__ __forceinline__ int cta_chol64(double* Ls, double* dinv, int* fail_sm
   return *fail_sm;
 }
 
-// grid.x = 1 + number of 64-row chunks below the diagonal block; block 256
-__global__ void __launch_bounds__(256) chol_panel_kernel(int n, int lda, int k0, double* __restrict__ A,
-                                                         double* __restrict__ Ldiag /*[nblk][64*64]*/,
-                                                         int* __restrict__ info) {
-  extern __shared__ __align__(16) double panel_smem[];
-  double* Ls = panel_smem;
-  double* Ts = panel_smem + CH_NB * CH_LD;
-  __shared__ double dinv[CH_NB];
+// grid.x = 1 + number of 16-row chunks below the diagonal block; block 256.  CTA 0 stores the factored block: L^T into
+// the strict upper triangle in place (nobody reads it), L itself into the side buffer Ldiag -- the other CTAs of this
+// launch may still be loading the unfactored block, so it is copied into place by chol_copy_diag_kernel at the end.
+__global__ void __launch_bounds__(C_THREADS, 1) chol_panel_kernel(int n, int lda, int k0, double* __restrict__ A,
+                                                                   double* __restrict__ Ldiag /*[nblk][128*128]*/,
+                                                                   int* __restrict__ info) {
+  extern __shared__ __align__(16) double cp_smem[];
+  double* Ls = cp_smem;                        // [128][CLD]
+  double* Ts = cp_smem + CB * CLD;             // [16][CLD]
+  __shared__ double dinv[CB];
   __shared__ int fail_sm;
   const int tid = threadIdx.x, lane = tid & 31;
-  const int nb = min(CH_NB, n - k0);
-  const int r0 = k0 + CH_NB + ((int)blockIdx.x - 1) * CH_NB;
-  // diagonal block (lower part, identity padding) and this CTA's 64 panel rows: a warp reads one 512 B row
-  for (int e = tid; e < CH_NB * CH_NB; e += 256) {
-    const int i = e >> 6, j = e & 63;
-    double v = (i == j) ? 1.0 : 0.0;
-    if (i < nb && j < nb && j <= i) v = A[(size_t)(k0 + i) * lda + k0 + j];
-    Ls[i * CH_LD + j] = v;
-    if (blockIdx.x > 0) Ts[i * CH_LD + j] = (r0 + i < n && j < nb) ? A[(size_t)(r0 + i) * lda + k0 + j] : 0.0;
+  const int nb = min(CB, n - k0);
+  const bool solver = blockIdx.x > 0;
+  const int r0 = k0 + CB + ((int)blockIdx.x - 1) * C_RPC;
+  // diagonal block: lower part, identity padding beyond nb (entries above the diagonal are never read)
+  for (int e = tid; e < CB * (CB / 2); e += C_THREADS) {
+    const int i = e >> 6, j = (e & 63) * 2;
+    double2 v = make_double2(0.0, 0.0);
+    if (i < nb && j <= i) {
+      v = *reinterpret_cast<const double2*>(A + (size_t)(k0 + i) * lda + k0 + j);
+      if (j + 1 > i) v.y = 0.0;
+    }
+    if (i >= nb) {
+      if (j == i) v.x = 1.0;
+      if (j + 1 == i) v.y = 1.0;
+    }
+    *reinterpret_cast<double2*>(Ls + i * CLD + j) = v;
   }
-  const int fail = cta_chol64(Ls, dinv, &fail_sm, tid);
+  if (solver) {
+    for (int e = tid; e < C_RPC * (CB / 2); e += C_THREADS) {
+      const int r = e >> 6, j = (e & 63) * 2;
+      double2 v = make_double2(0.0, 0.0);
+      if (r0 + r < n && j < nb) {
+        v = *reinterpret_cast<const double2*>(A + (size_t)(r0 + r) * lda + k0 + j);
+        if (j + 1 >= nb) v.y = 0.0;
+      }
+      *reinterpret_cast<double2*>(Ts + r * CLD + j) = v;
+    }
+  }
+  const int fail = cta_chol128(Ls, dinv, &fail_sm, tid);
   if (fail && blockIdx.x == 0 && tid == 0) atomicCAS(info, 0, k0 + fail);
-  if (blockIdx.x == 0) {
-    double* dst = Ldiag + (size_t)(k0 / CH_NB) * CH_NB * CH_NB;
-    for (int e = tid; e < CH_NB * CH_NB; e += 256) dst[e] = Ls[(e >> 6) * CH_LD + (e & 63)];
+  // mirror: Ls[m][j] = L[j][m] for j > m (the solve below reads column m of L as a contiguous row; CTA 0 stores it as L^T)
+  for (int e = tid; e < CB * CB; e += C_THREADS) {
+    const int i = e >> 7, j = e & 127;
+    if (j > i) Ls[i * CLD + j] = Ls[j * CLD + i];
+  }
+  __syncthreads();
+  if (!solver) {
+    double* dst = Ldiag + (size_t)(k0 / CB) * CB * CB;
+    for (int e = tid; e < CB * CB; e += C_THREADS) {
+      const int i = e >> 7, j = e & 127;
+      if (i < nb && j < nb) {
+        if (j > i) A[(size_t)(k0 + i) * lda + k0 + j] = Ls[i * CLD + j];
+        else dst[e] = Ls[i * CLD + j];
+      }
+    }
     return;
   }
-  // X L^T = A_ik, right-looking: 4 threads per row, thread q owns columns j = q + 4*jj
+  // X L^T = A_ik, right-looking: 16 threads per row, thread q owns columns j = q + 16*jj
   {
-    const int r = tid >> 2, q = tid & 3;
-    double a[16];
+    const int r = tid >> 4, q = tid & 15;
+    double a[8];
 #pragma unroll
-    for (int jj = 0; jj < 16; ++jj) a[jj] = Ts[r * CH_LD + q + 4 * jj];
+    for (int jj = 0; jj < 8; ++jj) a[jj] = Ts[r * CLD + q + 16 * jj];
 #pragma unroll
-    for (int m = 0; m < CH_NB; ++m) {
-      const int qm = m & 3, jm = m >> 2;
+    for (int m = 0; m < CB; ++m) {
+      const int qm = m & 15, jm = m >> 4;
       double x = a[jm] * dinv[m];
-      x = __shfl_sync(0xffffffffu, x, (lane & ~3) | qm);
+      x = __shfl_sync(0xffffffffu, x, qm, 16);
       if (q == qm) a[jm] = x;
+      const double* lrow = Ls + m * CLD;
 #pragma unroll
-      for (int jj = 0; jj < 16; ++jj) {
-        if (4 * jj + 3 > m) {                       // compile-time prune; exact test below
-          const int j = q + 4 * jj;
-          if (j > m) a[jj] = fma(-x, Ls[j * CH_LD + m], a[jj]);
+      for (int jj = 0; jj < 8; ++jj) {
+        if (16 * jj + 15 > m) {                      // compile-time prune; exact test below
+          const int j = q + 16 * jj;
+          if (j > m) a[jj] = fma(-x, lrow[j], a[jj]);
         }
       }
     }
 #pragma unroll
-    for (int jj = 0; jj < 16; ++jj) Ts[r * CH_LD + q + 4 * jj] = a[jj];
+    for (int jj = 0; jj < 8; ++jj) Ts[r * CLD + q + 16 * jj] = a[jj];
   }
   __syncthreads();
-  for (int e = tid; e < CH_NB * CH_NB; e += 256) {
-    const int r = e >> 6, c = e & 63;
-    if (r0 + r < n && c < nb) A[(size_t)(r0 + r) * lda + k0 + c] = Ts[r * CH_LD + c];
+  (void)lane;
+  // row-major store of the solved rows ...
+  for (int e = tid; e < C_RPC * CB; e += C_THREADS) {
+    const int r = e >> 7, c = e & 127;
+    if (r0 + r < n && c < nb) A[(size_t)(r0 + r) * lda + k0 + c] = Ts[r * CLD + c];
+  }
+  // ... and their transpose into the upper triangle (16 consecutive doubles = one 128-byte segment per column c)
+  for (int e = tid; e < C_RPC * CB; e += C_THREADS) {
+    const int c = e >> 4, r = e & 15;
+    if (r0 + r < n && c < nb) A[(size_t)(k0 + c) * lda + r0 + r] = Ts[r * CLD + c];
   }
 }
 
-// A[t0.., t0..] -= P P^T, P = A[t0.., k0..k0+63]; 64x64 tiles (lower), 256 threads, 4x4 outputs per thread
-// mode 0: all lower tiles; mode 1: first tile column only (the next panel's columns); mode 2: the tiles right of it
-__global__ void __launch_bounds__(256) chol_trailing_kernel(int n, int lda, int k0, int t0, int mode,
-                                                            double* __restrict__ A) {
-  extern __shared__ __align__(16) double ch_smem[];
-  double* As = ch_smem;                         // [64 rows][CH_LD]
-  double* Bs = ch_smem + CH_NB * CH_LD;
+__device__ __forceinline__ void chol_dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// A[t0.., t0..] -= P P^T (lower tiles), P = A[t0.., k0..k0+127].  64x64 tiles, 8 warps as 2x4, warp tile 32x16.
+// mode 0: all lower tiles; 1: tile columns 0 and 1 (the next panel's 128 columns); 2: tile columns >= 2.
+__global__ void __launch_bounds__(C_THREADS, 1) chol_update_kernel(int n, int lda, int k0, int t0, int mode,
+                                                                    double* __restrict__ A) {
+  extern __shared__ __align__(16) double cu_smem[];
+  double* As = cu_smem;                         // [64][CLD]
+  double* Bs = cu_smem + CT * CLD;
+  const int T = (n - t0 + CT - 1) / CT;
   int bi, bj;
-  if (mode == 1) {
-    bi = blockIdx.x; bj = 0;
-  } else {
-    const int t = blockIdx.x;
-    bi = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-    while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
-    while (bi * (bi + 1) / 2 > t) --bi;
-    bj = t - bi * (bi + 1) / 2;
-    if (mode == 2) { ++bi; ++bj; }
-  }
-  const bool diag = bi == bj;
-  const int tid = threadIdx.x;
-  const int ri = t0 + bi * 64, rj = t0 + bj * 64;
-  // panel rows, row-major (k contiguous): a warp loads one 512 B row per step as 32 double2
-  for (int e = tid; e < 64 * 32; e += 256) {
-    const int row = e >> 5, kp = e & 31;
-    double2 va = make_double2(0.0, 0.0);
-    if (ri + row < n) va = *reinterpret_cast<const double2*>(A + (size_t)(ri + row) * lda + k0 + 2 * kp);
-    *reinterpret_cast<double2*>(As + row * CH_LD + 2 * kp) = va;
-    if (!diag) {
-      double2 vb = make_double2(0.0, 0.0);
-      if (rj + row < n) vb = *reinterpret_cast<const double2*>(A + (size_t)(rj + row) * lda + k0 + 2 * kp);
-      *reinterpret_cast<double2*>(Bs + row * CH_LD + 2 * kp) = vb;
+  {
+    int t = blockIdx.x;
+    if (mode == 1) {
+      if (t < T) { bi = t; bj = 0; }
+      else { bi = t - T + 1; bj = 1; }
+    } else {
+      bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
+      while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+      while (bi * (bi + 1) / 2 > t) --bi;
+      bj = t - bi * (bi + 1) / 2;
+      if (mode == 2) { bi += 2; bj += 2; }
     }
   }
-  __syncthreads();
+  const bool diag = bi == bj;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ri = t0 + bi * CT, rj = t0 + bj * CT;
+  // panel rows, row-major (k contiguous), two K halves as two cp.async groups
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    for (int e = tid; e < CT * 16; e += C_THREADS) {
+      const int row = e >> 4, ch = (e & 15) * 4 + half * 64;     // 16-byte chunk = 2 doubles; 4 doubles per thread-step
+      double* da = As + row * CLD + ch;
+      if (ri + row < n) {
+        const double* src = A + (size_t)(ri + row) * lda + k0 + ch;
+        cp_async16(da, src);
+        cp_async16(da + 2, src + 2);
+      } else {
+        *reinterpret_cast<double2*>(da) = make_double2(0.0, 0.0);
+        *reinterpret_cast<double2*>(da + 2) = make_double2(0.0, 0.0);
+      }
+      if (!diag) {
+        double* db = Bs + row * CLD + ch;
+        if (rj + row < n) {
+          const double* src = A + (size_t)(rj + row) * lda + k0 + ch;
+          cp_async16(db, src);
+          cp_async16(db + 2, src + 2);
+        } else {
+          *reinterpret_cast<double2*>(db) = make_double2(0.0, 0.0);
+          *reinterpret_cast<double2*>(db + 2) = make_double2(0.0, 0.0);
+        }
+      }
+    }
+    cp_async_commit();
+  }
   const double* bs = diag ? As : Bs;
-  const int ty = tid >> 4, tx = tid & 15;         // rows ty + 16 i, cols tx + 16 j
-  double acc[4][4];
+  const int wm = warp >> 2, wn = warp & 3;
+  const int g = lane >> 2, q = lane & 3;
+  double c[4][2][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-#pragma unroll 8
-  for (int kk = 0; kk < CH_NB; kk += 2) {
-    double2 a[4], b[4];
+    for (int j = 0; j < 2; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+  const double* arow = As + (wm * 32 + g) * CLD + q;
+  const double* brow = bs + (wn * 16 + g) * CLD + q;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      a[i] = *reinterpret_cast<const double2*>(As + (ty + 16 * i) * CH_LD + kk);
-      b[i] = *reinterpret_cast<const double2*>(bs + (tx + 16 * i) * CH_LD + kk);
+  for (int half = 0; half < 2; ++half) {
+    if (half == 0) cp_async_wait<1>();
+    else cp_async_wait<0>();
+    __syncthreads();
+#pragma unroll 4
+    for (int k4 = half * 16; k4 < half * 16 + 16; ++k4) {
+      double a[4], b[2];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = arow[i * 8 * CLD + k4 * 4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) b[j] = brow[j * 8 * CLD + k4 * 4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) chol_dmma(c[i][j][0], c[i][j][1], a[i], b[j]);
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        acc[i][j] = fma(a[i].x, b[j].x, acc[i][j]);
-        acc[i][j] = fma(a[i].y, b[j].y, acc[i][j]);
-      }
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int r = ri + ty + 16 * i;
+    const int r = ri + wm * 32 + i * 8 + g;
     if (r >= n) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = rj + tx + 16 * j;
-      if (c > r || c >= n) continue;              // lower triangle only
-      A[(size_t)r * lda + c] -= acc[i][j];
+    for (int j = 0; j < 2; ++j) {
+      const int col = rj + wn * 16 + j * 8 + 2 * q;
+      if (col > r) continue;                         // lower triangle only (col <= r < n)
+      double* p = A + (size_t)r * lda + col;
+      if (col + 1 <= r) {
+        double2 v = *reinterpret_cast<double2*>(p);
+        v.x -= c[i][j][0];
+        v.y -= c[i][j][1];
+        *reinterpret_cast<double2*>(p) = v;
+      } else {
+        *p -= c[i][j][0];
+      }
     }
   }
 }
 
 __global__ void chol_copy_diag_kernel(int n, int lda, const double* __restrict__ Ldiag, double* __restrict__ A) {
   const int blk = blockIdx.x;
-  const int k0 = blk * CH_NB;
-  for (int e = threadIdx.x; e < CH_NB * CH_NB; e += blockDim.x) {
-    const int i = e / CH_NB, j = e % CH_NB;
-    if (k0 + i < n && j <= i) A[(size_t)(k0 + i) * lda + k0 + j] = Ldiag[(size_t)blk * CH_NB * CH_NB + e];
+  const int k0 = blk * CB;
+  for (int e = threadIdx.x; e < CB * CB; e += blockDim.x) {
+    const int i = e >> 7, j = e & 127;
+    if (k0 + i < n && j <= i) A[(size_t)(k0 + i) * lda + k0 + j] = Ldiag[(size_t)blk * CB * CB + e];
   }
 }
 
 size_t chol_workspace_doubles(int n) {
-  const int nblk = (n + CH_NB - 1) / CH_NB;
-  return (size_t)nblk * CH_NB * CH_NB;
+  const int nblk = (n + CB - 1) / CB;
+  return (size_t)nblk * CB * CB;          // factored diagonal blocks, parked until the end of the factorisation
 }
 
-// In-place Cholesky of the row-major lower triangle of A[n x n] (lda even, A 16-byte aligned).
-// info (device int): 0 on success, else 1-based index of the first non-positive pivot.
-// One-panel lookahead: the trailing update of panel b first refreshes the next panel's 64 columns; panel b+1 is
-// then factored on a side stream while the main stream finishes the rest of the update (the panel kernel is a
-// latency chain on ~40 CTAs, the update is throughput work on the whole chip).
-int chol_lower_inplace(int n, int lda, double* A, double* Ldiag, int* info, cudaStream_t st) {
-  VGG_REQUIRE((lda % 2) == 0, "lda must be even");
-  VGG_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int), st));
-  const int nblk = (n + CH_NB - 1) / CH_NB;
-  const size_t smem = sizeof(double) * 2 * CH_NB * CH_LD;
-  static bool attr_set = false;
-  if (!attr_set) {
-    VGG_CUDA_CHECK(cudaFuncSetAttribute(chol_trailing_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VGG_CUDA_CHECK(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+namespace {
+
+struct CholStreams {
+  cudaStream_t side = nullptr, cap = nullptr;
+  cudaEvent_t ev_col = nullptr, ev_panel = nullptr;
+  bool ready = false;
+};
+
+int chol_streams(CholStreams** out) {
+  static thread_local CholStreams s;
+  if (!s.ready) {
+    int lo = 0, hi = 0;
+    VGG_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    VGG_CUDA_CHECK(cudaStreamCreateWithPriority(&s.side, cudaStreamNonBlocking, hi));
+    VGG_CUDA_CHECK(cudaStreamCreateWithFlags(&s.cap, cudaStreamNonBlocking));
+    VGG_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_col, cudaEventDisableTiming));
+    VGG_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_panel, cudaEventDisableTiming));
+    s.ready = true;
   }
-  static thread_local cudaStream_t side = nullptr;
-  static thread_local cudaEvent_t ev_col = nullptr, ev_panel = nullptr;
-  static const bool lookahead = [] { const char* e = getenv("VGG_CHOL_LOOKAHEAD"); return !(e && e[0] == '0'); }();
-  if (lookahead && !side) {
-    VGG_CUDA_CHECK(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));
-    VGG_CUDA_CHECK(cudaEventCreateWithFlags(&ev_col, cudaEventDisableTiming));
-    VGG_CUDA_CHECK(cudaEventCreateWithFlags(&ev_panel, cudaEventDisableTiming));
-  }
+  *out = &s;
+  return VGG_OK;
+}
+
+int chol_set_attrs() {
+  static bool done = false;
+  if (done) return VGG_OK;
+  VGG_CUDA_CHECK(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(sizeof(double) * (CB + C_RPC) * CLD)));
+  VGG_CUDA_CHECK(cudaFuncSetAttribute(chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(sizeof(double) * 2 * CT * CLD)));
+  done = true;
+  return VGG_OK;
+}
+
+// the launch sequence on (st, side); with lookahead == false everything goes to st in program order
+int chol_enqueue(int n, int lda, double* A, double* Ldiag, int* info, cudaStream_t st, CholStreams* cs, bool lookahead) {
+  const int nblk = (n + CB - 1) / CB;
+  const size_t smem_p = sizeof(double) * (CB + C_RPC) * CLD;
+  const size_t smem_u = sizeof(double) * 2 * CT * CLD;
   auto panel = [&](int b, cudaStream_t s2) -> int {
-    const int k0 = b * CH_NB;
-    const int below = n - (k0 + CH_NB);
-    const int chunks = below > 0 ? (below + CH_NB - 1) / CH_NB : 0;
-    chol_panel_kernel<<<1 + chunks, 256, smem, s2>>>(n, lda, k0, A, Ldiag, info);
+    const int k0 = b * CB;
+    const int below = n - (k0 + CB);
+    const int chunks = below > 0 ? (below + C_RPC - 1) / C_RPC : 0;
+    chol_panel_kernel<<<1 + chunks, C_THREADS, smem_p, s2>>>(n, lda, k0, A, Ldiag, info);
     VGG_LAUNCH_CHECK();
     return VGG_OK;
   };
   int rc;
   if ((rc = panel(0, st))) return rc;
   for (int b = 0; b + 1 < nblk; ++b) {
-    const int k0 = b * CH_NB, t0 = k0 + CH_NB;
-    const int nt = (n - t0 + 63) / 64;
+    const int k0 = b * CB, t0 = k0 + CB;
+    const int T = (n - t0 + CT - 1) / CT;
+    const int n_col = T >= 2 ? 2 * T - 1 : 1;
+    const int n_rest = T > 2 ? (T - 2) * (T - 1) / 2 : 0;
     if (!lookahead) {
-      chol_trailing_kernel<<<nt * (nt + 1) / 2, 256, smem, st>>>(n, lda, k0, t0, 0, A);
+      chol_update_kernel<<<T * (T + 1) / 2, C_THREADS, smem_u, st>>>(n, lda, k0, t0, 0, A);
       VGG_LAUNCH_CHECK();
       if ((rc = panel(b + 1, st))) return rc;
       continue;
     }
-    chol_trailing_kernel<<<nt, 256, smem, st>>>(n, lda, k0, t0, 1, A);
+    chol_update_kernel<<<n_col, C_THREADS, smem_u, st>>>(n, lda, k0, t0, 1, A);
     VGG_LAUNCH_CHECK();
-    VGG_CUDA_CHECK(cudaEventRecord(ev_col, st));
-    VGG_CUDA_CHECK(cudaStreamWaitEvent(side, ev_col, 0));
-    if ((rc = panel(b + 1, side))) return rc;
-    VGG_CUDA_CHECK(cudaEventRecord(ev_panel, side));
-    if (nt > 1) {
-      chol_trailing_kernel<<<(nt - 1) * nt / 2, 256, smem, st>>>(n, lda, k0, t0, 2, A);
+    VGG_CUDA_CHECK(cudaEventRecord(cs->ev_col, st));
+    VGG_CUDA_CHECK(cudaStreamWaitEvent(cs->side, cs->ev_col, 0));
+    if ((rc = panel(b + 1, cs->side))) return rc;
+    VGG_CUDA_CHECK(cudaEventRecord(cs->ev_panel, cs->side));
+    if (n_rest > 0) {
+      chol_update_kernel<<<n_rest, C_THREADS, smem_u, st>>>(n, lda, k0, t0, 2, A);
       VGG_LAUNCH_CHECK();
     }
-    VGG_CUDA_CHECK(cudaStreamWaitEvent(st, ev_panel, 0));
+    VGG_CUDA_CHECK(cudaStreamWaitEvent(st, cs->ev_panel, 0));
   }
   chol_copy_diag_kernel<<<nblk, 256, 0, st>>>(n, lda, Ldiag, A);
   VGG_LAUNCH_CHECK();
+  return VGG_OK;
+}
+
+}  // namespace
+
+// In-place Cholesky of the row-major lower triangle of A[n x n] (lda even, A 16-byte aligned): on return the lower
+// triangle holds L and the strict upper triangle L^T.  info (device int): 0 or the 1-based index of the first
+// non-positive pivot.  VGG_CHOL_LOOKAHEAD=0 / VGG_CHOL_GRAPH=0 switch the side stream / the CUDA graph off (A/B).
+int chol_lower_inplace(int n, int lda, double* A, double* Ldiag, int* info, cudaStream_t st) {
+  VGG_REQUIRE((lda % 2) == 0, "lda must be even");
+  int rc;
+  if ((rc = chol_set_attrs())) return rc;
+  VGG_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int), st));
+  static const bool lookahead = [] { const char* e = getenv("VGG_CHOL_LOOKAHEAD"); return !(e && e[0] == '0'); }();
+  static const bool use_graph = [] { const char* e = getenv("VGG_CHOL_GRAPH"); return !(e && e[0] == '0'); }();
+  const int nblk = (n + CB - 1) / CB;
+  CholStreams* cs = nullptr;
+  if ((rc = chol_streams(&cs))) return rc;
+  if (nblk < 3 || !use_graph) return chol_enqueue(n, lda, A, Ldiag, info, st, cs, lookahead && nblk >= 3);
+  // one captured graph per (matrix, order): ~60 launches + events become a single cudaGraphLaunch
+  typedef std::tuple<double*, int, int, int*, double*, bool> Key;
+  static thread_local std::map<Key, cudaGraphExec_t> cache;
+  const Key key(A, n, lda, info, Ldiag, lookahead);
+  auto it = cache.find(key);
+  if (it == cache.end()) {
+    const long long launches_before = g_launch_count;
+    cudaGraph_t graph = nullptr;
+    VGG_CUDA_CHECK(cudaStreamBeginCapture(cs->cap, cudaStreamCaptureModeThreadLocal));
+    rc = chol_enqueue(n, lda, A, Ldiag, info, cs->cap, cs, lookahead);
+    const cudaError_t ce = cudaStreamEndCapture(cs->cap, &graph);
+    g_launch_count = launches_before;
+    if (rc) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    VGG_CUDA_CHECK(ce);
+    cudaGraphExec_t exec = nullptr;
+    VGG_CUDA_CHECK(cudaGraphInstantiate(&exec, graph, 0));
+    cudaGraphDestroy(graph);
+    if (cache.size() > 8) {
+      for (auto& kv : cache) cudaGraphExecDestroy(kv.second);
+      cache.clear();
+    }
+    it = cache.emplace(key, exec).first;
+  }
+  VGG_CUDA_CHECK(cudaGraphLaunch(it->second, st));
+  g_launch_count += 2 + 3 * (nblk - 1);          // kernels inside the graph
   return VGG_OK;
 }
 

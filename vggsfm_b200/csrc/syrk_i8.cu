@@ -196,7 +196,8 @@ constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) 
 __global__ void __launch_bounds__(OZ_THREADS, 1)
     oz_syrk_kernel(const __grid_constant__ OzPlan plan, const OzWork* __restrict__ work, int nwork, int KB,
                    const int8_t* __restrict__ slices, size_t slice_stride, const int* __restrict__ expo,
-                   const double* __restrict__ pow2, int Dpad, double* __restrict__ Cmat, ptrdiff_t mc_off) {
+                   const double* __restrict__ pow2, int Dpad, double* __restrict__ Cmat, ptrdiff_t mc_off,
+                   int fill_upper) {
   extern __shared__ __align__(1024) uint8_t oz_smem[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(oz_smem), 1024));
   uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (size_t)OZ_STAGES * OZ_STAGE_BYTES);
@@ -332,8 +333,11 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
         else if (tame && ec > -400 && ec < 400) v = v * sr * pow2[col];
         else v = ldexp(v, er + ec + g.exp_base);
         if (v != 0.0) {
-          if (!mc_off && (!diag || col <= r)) atomicAdd(&Cmat[(size_t)r * Dpad + col], -v);
-          if (!diag || col < r || (mc_off && col == r)) {
+          // The work list holds UPPER tiles (bi <= bj): TMEM lane = r, so the 32 lanes of one RED instruction hit 32
+          // consecutive addresses of row `col` -- the mirrored element (col, r) of the row-major LOWER triangle, which is
+          // what csrc/chol.cu factors (fabric mode: one multimem op per element).  The direct element (r, col) is only
+          // written for the library factorisation A/B.
+          if (!diag || col >= r) {
             double* q = &Cmat[(size_t)col * Dpad + r];
             if (mc_off) {
               asm volatile("multimem.red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(q + mc_off), "d"(-v) : "memory");
@@ -341,6 +345,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
               atomicAdd(q, -v);
             }
           }
+          if (fill_upper && (!diag || col > r)) atomicAdd(&Cmat[(size_t)r * Dpad + col], -v);
         }
       }
     }
@@ -429,7 +434,8 @@ __device__ __forceinline__ void umma_commit_2cta(uint64_t* bar) {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZ_THREADS, 1)
     oz_syrk_pair_kernel(const __grid_constant__ OzPlan plan, const OzWork2* __restrict__ work, int nwork, int KB,
                         const int8_t* __restrict__ slices, size_t slice_stride, const int* __restrict__ expo,
-                        const double* __restrict__ pow2, int Dpad, double* __restrict__ Cmat, ptrdiff_t mc_off) {
+                        const double* __restrict__ pow2, int Dpad, double* __restrict__ Cmat, ptrdiff_t mc_off,
+                   int fill_upper) {
   extern __shared__ __align__(1024) uint8_t oz_smem[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(oz_smem), 1024));
   uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (size_t)OZ2_STAGES * OZ2_STAGE_BYTES);
@@ -582,15 +588,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(OZ_THREADS, 1)
         else if (tame && ec > -400 && ec < 400) v = v * sr * pow2[col];
         else v = ldexp(v, er + ec + g.exp_base);
         if (v != 0.0) {
-          if (!mc_off && (!diag || col <= r)) atomicAdd(&Cmat[(size_t)r * Dpad + col], -v);
-          if (!diag || col < r || (mc_off && col == r)) {
-            double* q = &Cmat[(size_t)col * Dpad + r];
+          // row-major LOWER triangle (csrc/chol.cu factors it; fabric mode: one multimem op per element); the mirror only
+          // for the library factorisation A/B
+          if (!diag || col <= r) {
+            double* q = &Cmat[(size_t)r * Dpad + col];
             if (mc_off) {
               asm volatile("multimem.red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(q + mc_off), "d"(-v) : "memory");
             } else {
               atomicAdd(q, -v);
             }
           }
+          if (fill_upper && (!diag || col < r)) atomicAdd(&Cmat[(size_t)col * Dpad + r], -v);
         }
       }
     }
@@ -842,8 +850,10 @@ int syrk_i8_reset_amax(void* ws, int Dpad, cudaStream_t st) {
   return VGG_OK;
 }
 
-// Sraw -= Zt^T Zt with s int8 slices.  Zt [Kpad][Dpad] (Dpad % 128 == 0), Cmat [Dpad][Dpad] row-major, both
-// triangles written (mirror only in fabric mode), same contract as launch_syrk.
+// Sraw -= Zt^T Zt with s int8 slices.  Zt [Kpad][Dpad] (Dpad % 128 == 0), Cmat [Dpad][Dpad] row-major, LOWER triangle
+// written (plus the mirror when g_fill_upper), same contract as launch_syrk.
+extern int g_fill_upper;      // csrc/ba_schur.cu
+
 int launch_syrk_i8(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t mc_off, int s, void* ws,
                    size_t ws_bytes, cudaStream_t st, bool amax_ready) {
   VGG_REQUIRE(Dpad % OZ_BM == 0, "syrk_i8: Dpad must be a multiple of 128");
@@ -861,7 +871,7 @@ int launch_syrk_i8(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t
     {
       std::vector<OzTileJob> jobs;
       for (int bi = 0; bi < nb; ++bi)
-        for (int bj = 0; bj <= bi; ++bj) jobs.push_back({bi, bi, bj, 0});
+        for (int bj = 0; bj <= bi; ++bj) jobs.push_back({bj, bj, bi, 0});     // upper tile (row block bj <= column block bi)
       build_work_list<OzWork>(hs.plan, jobs, KB, hs.sms,
                               [](const OzTileJob& j, int g, int k0, int k1) { return OzWork{j.bi0, j.bj, g, k0, k1}; }, &hs.work);
     }
@@ -922,11 +932,11 @@ int launch_syrk_i8(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t
     const int nwork2 = (int)hs.work2.size();
     const int nclusters = std::min(std::max(1, hs.sms / 2), nwork2);
     oz_syrk_pair_kernel<<<2 * nclusters, OZ_THREADS, OZ2_SMEM_BYTES, st>>>(hs.plan, work_raw, nwork2, KB, slices, slice_stride,
-                                                                         expo, pow2, Dpad, Cmat, mc_off);
+                                                                         expo, pow2, Dpad, Cmat, mc_off, g_fill_upper);
   } else {
     const int grid = std::min(hs.sms, nwork);
     oz_syrk_kernel<<<grid, OZ_THREADS, OZ_SMEM_BYTES, st>>>(hs.plan, work_d, nwork, KB, slices, slice_stride, expo, pow2,
-                                                          Dpad, Cmat, mc_off);
+                                                          Dpad, Cmat, mc_off, g_fill_upper);
   }
   VGG_LAUNCH_CHECK();
   return VGG_OK;
