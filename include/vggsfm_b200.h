@@ -230,6 +230,22 @@ int vgg_undistort_simple_radial(int S, int N, const double* tracks_normalized, c
                                 int max_iterations, double max_step_norm, double rel_step_size, double* out,
                                 int* iterations_run, void* workspace, size_t ws_bytes, void* stream);
 
+/* pycolmap.absolute_pose_estimation for the frames refine_pose cannot refine (vggsfm/utils/triangulation.py:404-433:
+ * estimate_focal_length = True, ransac.max_error = 12) and for the video runner's PnP alignment
+ * (vggsfm/runners/video_runner.py:985-998): P3P + LO-RANSAC, batched over frames AND over COLMAP's 31 focal-length
+ * factors (0.2 + 4.8 (i/30)^2) in one launch, on caller-drawn minimal samples (u_samples double [num_trials,3], uniform
+ * in [0,1), mapped to the frame's usable points).  uv float [S,P,2] pixels, mask uint8 [S,P] usable observations,
+ * frame_flags uint8 [S] (0 = skip the frame), points double [P,3], intr double [S,4] = f,cx,cy,k.
+ * Out: pose_out double [S,12] (R|t, written for successful frames only), focal_out double [S] (prior focal x best
+ * factor), num_inliers_out int32 [S] (0 = no model: the reference's `None`), inlier_out uint8 [S,P].
+ * The non-linear refinement COLMAP runs afterwards is vgg_pose_refinement.  P <= ~9700 per call. */
+int vgg_pnp_workspace_bytes(int S, int estimate_focal_length, size_t* bytes);
+int vgg_absolute_pose_estimation(int S, int P, int camera_model, const float* uv, const uint8_t* mask,
+                                 const uint8_t* frame_flags, const double* points, const double* intr,
+                                 const double* u_samples, int num_trials, int estimate_focal_length, double max_error,
+                                 double* pose_out, double* focal_out, int* num_inliers_out, uint8_t* inlier_out,
+                                 void* workspace, size_t ws_bytes, void* stream);
+
 /* ------------------------------------------------------------------------------------------- */
 /* Tracker correlation inner loop (float32 math on float or half feature pyramids)             */
 /* ------------------------------------------------------------------------------------------- */

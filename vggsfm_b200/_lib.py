@@ -17,7 +17,7 @@ EXPORTS = [
     "vgg_ba_default_options", "vgg_ba_dims", "vgg_ba_workspace_bytes", "vgg_ba_camrec_len",
     "vgg_ba_build_blocks", "vgg_ba_schur", "vgg_cholesky_lower", "vgg_ba_solve",
     "vgg_ba_reduced_system_doubles", "vgg_ba_solve_fabric",
-    "vgg_pose_default_options", "vgg_pose_refinement", "vgg_syrk_ozaki_workspace_bytes", "vgg_syrk_ozaki",
+    "vgg_pose_default_options", "vgg_pose_refinement", "vgg_pnp_workspace_bytes", "vgg_absolute_pose_estimation", "vgg_syrk_ozaki_workspace_bytes", "vgg_syrk_ozaki",
     "vgg_tri_workspace_bytes", "vgg_triangulate_tracks", "vgg_triangulate_by_pair", "vgg_filter_points3d",
     "vgg_project_points", "vgg_normalize_tracks", "vgg_undistort_simple_radial",
     "vgg_corr_pyramid_bytes", "vgg_corr_build_pyramid", "vgg_corr_sample", "vgg_sample_features4d",
@@ -132,6 +132,8 @@ def lib() -> ctypes.CDLL:
     L.vgg_pose_default_options.argtypes = [ctypes.POINTER(PoseOptions)]
     L.vgg_pose_default_options.restype = None
     L.vgg_pose_refinement.argtypes = [ci, ci, ci, vp, vp, vp, vp, vp, vp, ctypes.POINTER(PoseOptions), vp, vp, vp, vp]
+    L.vgg_pnp_workspace_bytes.argtypes = [ci, ci, ctypes.POINTER(cs)]
+    L.vgg_absolute_pose_estimation.argtypes = [ci, ci, ci, vp, vp, vp, vp, vp, vp, ci, ci, cd, vp, vp, vp, vp, vp, cs, vp]
     L.vgg_syrk_ozaki_workspace_bytes.argtypes = [ci, ci, ci, ctypes.POINTER(cs)]
     L.vgg_syrk_ozaki_mma_rate.argtypes = [ci, ci, ctypes.POINTER(cd), vp]
     L.vgg_probe_remote_mbarrier.argtypes = [ctypes.POINTER(ctypes.c_int), vp]

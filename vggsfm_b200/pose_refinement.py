@@ -6,9 +6,11 @@ The reference walks the frames in Python and calls ``pycolmap.pose_refinement`` 
 csrc/pose_refine.cu) and nothing leaves the GPU.  PyTorch is used for device memory and index
 compaction only; there is no fallback path.
 
-Not built: ``pycolmap.absolute_pose_estimation`` (P3P LO-RANSAC with COLMAP's own RNG), the
-``force_estimate`` fall-back of refine_pose (triangulation.py:404-431).  Frames that would take it are
-reported in ``PoseReport.needs_absolute_pose`` and keep their current pose.
+``pycolmap.absolute_pose_estimation`` -- the ``force_estimate`` fall-back of refine_pose (triangulation.py:404-433)
+and the video runner's PnP alignment -- is ``absolute_pose_estimation_batched`` below: P3P + LO-RANSAC for all the
+frames that need it and all 31 focal-length factors in one launch (csrc/pnp.cu), followed by the same refinement
+kernel.  COLMAP draws its minimal samples from an internal generator no caller can seed; here they come from
+torch's CPU generator (``draw_pnp_samples``), like the triangulation pairs.
 """
 from __future__ import annotations
 
@@ -44,6 +46,7 @@ class PoseReport:
     num_inliers: torch.Tensor           # [S] int64 effective inliers per frame
     inlier_used: torch.Tensor           # [S,P] bool
     needs_absolute_pose: Optional[torch.Tensor] = None   # [S] bool (refine_pose only)
+    absolute_pose_ok: Optional[torch.Tensor] = None      # [S] bool: frames re-estimated by P3P LO-RANSAC
     kernel_launches: int = 0
 
 
@@ -78,6 +81,49 @@ def pose_refinement_batched(poses, intr4, points3D, tracks2D, inlier, frame_flag
                                      sd.data_ptr(), si.data_ptr(), stream), "vgg_pose_refinement")
     return PoseReport(si[:, 0], si[:, 1], si[:, 2], sd[:, 0], sd[:, 1], sd[:, 3].round().long(), used.bool(),
                       kernel_launches=1 if S > 0 else 0)
+
+
+def draw_pnp_samples(num_trials: int = 128) -> torch.Tensor:
+    """Minimal-sample draws of the absolute-pose RANSAC: [num_trials,3] uniform numbers from torch's CPU generator
+    (``torch.manual_seed`` makes a run reproducible); the kernel maps them to the frame's usable points."""
+    return torch.rand(num_trials, 3, dtype=torch.float64)
+
+
+def absolute_pose_estimation_batched(tracks2D, points3D, masks, intr4, model: int, frames=None, estimate_focal_length=False,
+                                     max_error=12.0, u_samples=None, num_trials=128):
+    """``pycolmap.absolute_pose_estimation`` (estimation part) for many frames at once: ``vgg_absolute_pose_estimation``.
+
+    tracks2D [S,P,2], points3D [P,3], masks [S,P] usable observations, intr4 [S,4] f64 (f,cx,cy,k), frames [S] bool
+    (default: all).  Returns (poses [S,3,4] f64 -- rows of failed / skipped frames are zero, focal [S] f64,
+    num_inliers [S] int32 -- 0 where the reference would get ``None``, inliers [S,P] bool)."""
+    if not tracks2D.is_cuda:
+        raise RuntimeError("vggsfm_b200.absolute_pose_estimation needs CUDA tensors (no CPU fallback)")
+    L = _lib.lib()
+    dev = tracks2D.device
+    S, P = masks.shape
+    poses = torch.zeros(S, 3, 4, dtype=torch.float64, device=dev)
+    focal = intr4[:, 0].clone().double()
+    ninl = torch.zeros(S, dtype=torch.int32, device=dev)
+    inl = torch.zeros(S, P, dtype=torch.uint8, device=dev)
+    if S == 0 or P < 3:
+        return poses, focal, ninl, inl.bool()
+    uv = tracks2D.float().contiguous()
+    mk = masks.to(torch.uint8).contiguous()
+    fl = (torch.ones(S, dtype=torch.uint8, device=dev) if frames is None else frames.to(torch.uint8)).contiguous()
+    pts = points3D.double().contiguous()
+    it4 = intr4.double().contiguous()
+    us = (draw_pnp_samples(num_trials) if u_samples is None else u_samples).to(torch.float64).to(dev).contiguous()
+    nb = ctypes.c_size_t()
+    _lib.check(L.vgg_pnp_workspace_bytes(S, 1 if estimate_focal_length else 0, ctypes.byref(nb)), "vgg_pnp_workspace_bytes")
+    ws = torch.empty(max(nb.value, 256), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(L.vgg_absolute_pose_estimation(S, P, model, uv.data_ptr(), mk.data_ptr(), fl.data_ptr(), pts.data_ptr(),
+                                                  it4.data_ptr(), us.data_ptr(), us.shape[0], 1 if estimate_focal_length else 0,
+                                                  float(max_error), poses.data_ptr(), focal.data_ptr(), ninl.data_ptr(),
+                                                  inl.data_ptr(), ws.data_ptr(), ws.numel(), stream),
+                   "vgg_absolute_pose_estimation")
+    return poses, focal, ninl, inl.bool()
 
 
 def _intr4(intrinsics, extra_params, model):
@@ -185,10 +231,46 @@ def refine_pose(extrinsics, intrinsics, extra_params, inlier, points3D, tracks, 
     refined = rep.termination < 6
     rep.needs_absolute_pose = (~refined) | (focal < 0.1 * scale) | (focal > 30 * scale)   # :396-402
     if force_estimate and bool(rep.needs_absolute_pose.any()):
-        print(f"vggsfm_b200.refine_pose: {int(rep.needs_absolute_pose.sum())} frame(s) would take "
-              "pycolmap.absolute_pose_estimation in the reference; not built -- poses kept")
+        _estimate_absolute_poses(rep.needs_absolute_pose, poses, intr4, points3D, tracks2D, inl, model, shared_camera,
+                                 float(max_reproj_error), rep)
     last_report = rep
     return _finish(poses, intr4, extrinsics, intrinsics, extra_params, model, scale)
+
+
+def _estimate_absolute_poses(need, poses, intr4, points3D, tracks2D, inl_nongeo, model, shared_camera, max_error, rep):
+    """triangulation.py:404-433 for the frames in ``need`` (in place on poses / intr4): P3P LO-RANSAC with the focal
+    ladder on the visible matches when a frame has more than 50 of them (retried on all matches when that fails), on
+    all matches otherwise; a found model replaces the pose and is refined with the RANSAC inliers, like
+    pycolmap.absolute_pose_estimation's own refinement step.  With a shared camera the estimated focal length is used
+    for the pose only (COLMAP would write it into the single shared Camera in the middle of the frame loop)."""
+    S, P = inl_nongeo.shape
+    dev = poses.device
+    vis = inl_nongeo.bool()
+    enough = vis.sum(dim=1) > 50
+    all_pts = torch.ones_like(vis)
+    first = torch.where(enough[:, None], vis, all_pts)
+    us = draw_pnp_samples()
+    p1, f1, n1, i1 = absolute_pose_estimation_batched(tracks2D, points3D, first, intr4, model, need, True, max_error, us)
+    retry = need & enough & (n1 == 0)
+    if bool(retry.any()):
+        p2, f2, n2, i2 = absolute_pose_estimation_batched(tracks2D, points3D, all_pts, intr4, model, retry, True, max_error, us)
+        p1 = torch.where(retry[:, None, None], p2, p1)
+        f1 = torch.where(retry, f2, f1)
+        n1 = torch.where(retry, n2, n1)
+        i1 = torch.where(retry[:, None], i2, i1)
+    ok = need & (n1 > 0)
+    rep.absolute_pose_ok = ok
+    if not bool(ok.any()):
+        return
+    poses[ok] = p1[ok]
+    if not shared_camera:
+        intr4[ok, 0] = f1[ok]
+    flags = ok.to(torch.uint8) * FLAG_ACTIVE
+    if not shared_camera:
+        flags = flags | (FLAG_FOCAL | FLAG_EXTRA)
+    opt = default_pose_options()
+    r2 = pose_refinement_batched(poses, intr4, points3D, tracks2D, i1, flags, model, opt)
+    rep.kernel_launches += r2.kernel_launches + 2
 
 
 def init_refine_pose(extrinsics, intrinsics, extra_params, inlier, points3D, tracks, valid_track_mask_init, image_size,

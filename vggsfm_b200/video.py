@@ -28,10 +28,11 @@ def filter_points_and_compute_masks(points, tracks, extrinsics, intrinsics, extr
 
 
 def align_next_window(extrinsics, tracks, inlier, points3D, intrinsics, extra_params=None, camera_type="SIMPLE_PINHOLE",
-                      min_vis_num=50):
-    """video_runner.py:941-1017 (use_pnp=False): every frame but the first is refined against the carried 3D
-    points with the shared camera held constant; a frame with <= min_vis_num inliers uses all points.
-    Returns refined_extrinsics [S,3,4] f64."""
+                      min_vis_num=50, use_pnp=False):
+    """video_runner.py:941-1017: every frame but the first is refined against the carried 3D points with the shared
+    camera held constant; a frame with <= min_vis_num inliers uses all points.  ``use_pnp`` first re-estimates each of
+    those frames by P3P LO-RANSAC at 12 px on its inlier points (:985-998, default estimation options: no focal
+    ladder); a frame without a model keeps its incoming pose.  Returns refined_extrinsics [S,3,4] f64."""
     model = ba.camera_model_id(camera_type)
     S = extrinsics.shape[0]
     dev = extrinsics.device
@@ -44,6 +45,11 @@ def align_next_window(extrinsics, tracks, inlier, points3D, intrinsics, extra_pa
     intr4 = pr._intr4(K, ex, model)
     flags = torch.full((S,), pr.FLAG_ACTIVE, dtype=torch.uint8, device=dev)
     flags[0] = 0
+    if use_pnp:
+        p_est, _, n_est, _ = pr.absolute_pose_estimation_batched(tracks, points3D, inl, intr4, model, frames=flags.bool(),
+                                                                 estimate_focal_length=False, max_error=12.0)
+        ok = n_est > 0
+        poses[ok] = p_est[ok]
     pr.last_report = pr.pose_refinement_batched(poses, intr4, points3D, tracks, inl, flags, model, pr.default_pose_options())
     return poses
 
