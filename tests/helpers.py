@@ -53,3 +53,28 @@ def rotation_angle_deg(R1, R2):
     2*asin(|R1-R2|_F / (2*sqrt(2))) so that it stays accurate near zero (acos((tr-1)/2) bottoms out at ~1e-6 deg)."""
     d = np.linalg.norm((R1 - R2).reshape(R1.shape[0], -1), axis=1)
     return np.degrees(2.0 * np.arcsin(np.clip(d / (2.0 * np.sqrt(2.0)), 0.0, 1.0)))
+
+
+def tiny_former(in_dim, out_dim, seed):
+    """Deterministic stand-in for the tracker's EfficientUpdateFormer (a learned module outside the hot path) used by
+    the tracker host-loop goldens: token-wise + time-mixed + track-mixed linear maps, so that a wrong permutation of the
+    (track, frame) axes or a wrong input layout changes the output."""
+    import torch
+    import torch.nn as nn
+
+    class TinyFormer(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.a = nn.Linear(in_dim, out_dim)
+            self.b = nn.Linear(in_dim, out_dim)
+
+        def forward(self, x):                       # [B, N, S, D] -> [B, N, S, out]
+            return (0.3 * torch.tanh(self.a(x)) + 0.2 * torch.tanh(self.b(x.mean(dim=2, keepdim=True)))
+                    + 0.1 * torch.tanh(self.b(x.mean(dim=1, keepdim=True))))
+
+    g = torch.Generator().manual_seed(seed)
+    m = TinyFormer()
+    with torch.no_grad():
+        for p in m.parameters():
+            p.copy_(torch.randn(p.shape, generator=g) * 0.05)
+    return m
