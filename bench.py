@@ -247,6 +247,73 @@ def syrk_roofline(D, K3, dev, clocks):
             "note": "time includes the column-max and slicing kernels; in the LM loop the column max is fused into z_build"}
 
 
+def corr_section(dev, hbm_peak):
+    """C4 (BASELINE.json configs[3]): one correlation + sampling pass of the tracker's refinement loop, fused CUDA kernel
+    vs the reference's GPU path restated with stock PyTorch ops (oracle.corr_oracle.TorchCorrBlock: fp16 matmul of the
+    full volume + grid_sample) on the same device.  Coarse: fmaps [1,128,128,128,128], one 1024-query chunk, 5 levels,
+    r = 4.  Fine: [1024,128,32,31,31] patches, one query each, 3 levels, r = 3.  Algorithmic bytes of the fused kernel =
+    the (2r+2)^2 footprint positions x C x 2 B per level + the target vector + coordinates + outputs."""
+    import torch
+    from vggsfm_b200.corr import CorrBlock
+    from oracle.corr_oracle import TorchCorrBlock
+    out = {}
+
+    def timeit(fn, reps, warm=2):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    for name, (B, S, C, H, W, N, L, r) in {"coarse": (1, 128, 128, 128, 128, 1024, 5, 4), "fine": (1024, 128, 32, 31, 31, 1, 3, 3)}.items():
+        try:
+            g = torch.Generator(device=dev).manual_seed(0)
+            fm = torch.randn(B, S, C, H, W, device=dev, dtype=torch.float16, generator=g)
+            tg = torch.randn(B, S, N, C, device=dev, dtype=torch.float32, generator=g)
+            co = torch.rand(B, S, N, 2, device=dev, generator=g) * torch.tensor([W - 9.0, H - 9.0], device=dev) + 4.0
+            K = 2 * r + 1
+            ours = CorrBlock(fm, num_levels=L, radius=r, half=True)
+            torch.cuda.synchronize()
+
+            def run_ours():
+                ours.corr(tg)
+                return ours.sample(co)
+            ms = timeit(run_ours, 5)
+            foot = sum(min((2 * r + 2), H >> l) * min((2 * r + 2), W >> l) for l in range(L)) * C * 2
+            ab = B * S * N * (foot + C * 4 + 8 + L * K * K * 4)
+            rec = {"shape": [B, S, C, H, W], "queries": N, "levels": L, "radius": r, "ms_fused": ms,
+                   "algorithmic_bytes": ab, "achieved_gbs": ab / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": ab / (ms * 1e-3) / 1e9 / hbm_peak,
+                   "pairs_per_s": B * S * N / (ms * 1e-3)}
+            res = run_ours()
+            del ours
+            try:
+                with torch.autocast("cuda", dtype=torch.float16):
+                    base = TorchCorrBlock(fm, num_levels=L, radius=r)
+
+                    def run_base():
+                        base.corr(tg)
+                        return base.sample(co)
+                    rec["ms_torch_reference_path"] = timeit(run_base, 2, warm=1)
+                    ref = run_base().float()
+                rec["speedup_vs_torch_path"] = rec["ms_torch_reference_path"] / ms
+                rec["max_abs_diff_vs_torch_path"] = float((res - ref).abs().max())
+                rec["flops_torch_path"] = 2.0 * B * S * N * C * sum((H >> l) * (W >> l) for l in range(L))
+                del base, ref
+            except Exception as e:      # the full volume does not fit next to the bench tensors: report ours only
+                rec["torch_reference_path_error"] = str(e)[:160]
+            out[name] = rec
+            del fm, tg, co, res
+            torch.cuda.empty_cache()
+        except Exception as e:
+            out[name] = {"error": str(e)[:200]}
+    return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -406,6 +473,7 @@ def run_gpu(args):
     roof = None
     roof_syrk = None
     cpu_base = None
+    corr = None
     if rank == 0:
         peak, peak_src = load_peaks()
         dc, ns = ba.dims(model, mode)
@@ -462,6 +530,9 @@ def run_gpu(args):
             roof_syrk = syrk_roofline(S_FRAMES * dc + ns, 3 * n_loc, dev, clocks)
         except Exception as e:
             roof_syrk = {"error": str(e)[:200]}
+        if world == 1 and not args.no_corr:
+            torch.cuda.empty_cache()
+            corr = corr_section(dev, peak)
         if world == 1:
             v, dt = cpu_ba_sample(sc, extr, K, extra, pts, 3)
             tv, tdt, tkind = cpu_tri_sample(sc, 16)
@@ -482,7 +553,7 @@ def run_gpu(args):
             "tracks_per_s": tracks_per_s, "tri_ms_per_pass": tri_ms / args.steps, "tri_median_point_error": tri_median_err,
             "e2e": {"value": e2e_value, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_syrk": roof_syrk,
-            "cpu_baseline": cpu_base,
+            "cpu_baseline": cpu_base, "corr": corr,
         }
         line["config"]["syrk"] = os.environ.get("VGG_SYRK", "ozaki:7") + " (default: tcgen05 kind::i8, 7 Ozaki slices, FP64-equivalent)"
         if hook is not None:
@@ -501,6 +572,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-corr", action="store_true", help="skip the C4 correlation section (rank 0, N=1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -99,6 +99,15 @@ typedef struct vgg_ba_fabric {
   double* ar_local;
   double* ar_multicast;
   size_t ar_doubles;     /* >= vgg_ba_reduced_system_doubles() */
+  /* v2 (optional; world = 0 keeps v1): reduce-scatter of the lower triangle's 128-row blocks onto their owners
+   * (block b -> rank b mod world) with system-scope REDs over NVLink, gather by peer loads, barriers and the small
+   * cost/gradient all-reduces as kernels on the same allocation -- no NCCL call, no host callback inside the LM loop,
+   * inbound traffic per GPU independent of the number of ranks, bit-identical systems on all ranks.
+   * peer_base[r] = rank r's base address of the SAME symmetric allocation (ar_local == peer_base[rank]), which must
+   * hold total_doubles >= vgg_ba_fabric_doubles() and be zero-filled once when it is created. */
+  int32_t world, rank;
+  double* peer_base[8];
+  size_t total_doubles;
 } vgg_ba_fabric;
 
 void vgg_ba_default_options(vgg_ba_options* opt);
@@ -143,6 +152,7 @@ int vgg_ba_solve(const vgg_ba_problem* prob, const vgg_ba_options* opt, void* wo
                  size_t ws_bytes, vgg_allreduce_fn allreduce, void* allreduce_user,
                  vgg_ba_summary* summary, double* trace, void* stream);
 int vgg_ba_reduced_system_doubles(int S, int camera_model, int intr_mode, size_t* doubles);
+int vgg_ba_fabric_doubles(int S, int camera_model, int intr_mode, size_t* doubles);
 int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt, void* workspace,
                         size_t ws_bytes, vgg_allreduce_fn allreduce, void* allreduce_user,
                         const vgg_ba_fabric* fabric, vgg_ba_summary* summary, double* trace, void* stream);

@@ -67,3 +67,43 @@ def corr_sample(fmaps, targets, coords, num_levels, radius, border=False):
         y = (c[:, 1:2, None] + d[None, None, :]).expand(-1, K, K).reshape(-1, K * K)
         outs.append(_bilinear_gather(vol.reshape(B * S * N, H, W), x, y, border).reshape(B, S, N, K * K))
     return torch.cat(outs, dim=-1)
+
+
+class TorchCorrBlock:
+    """Stock-PyTorch statement of CorrBlock on ANY device (blocks.py:338-416): per level one torch.matmul of the targets
+    with every spatial position (fp16 under autocast on a GPU, as the reference runs it, runners/runner.py:418), the
+    [B,S,N,H,W] volume in memory, then F.grid_sample (align_corners=True, zeros padding) at the (2r+1)^2 taps.  This is
+    what the reference executes on a GPU; bench.py times it as the C4 baseline (kind "port": written from the reference's
+    description, not imported -- /root/reference does not exist on the GPU box)."""
+
+    def __init__(self, fmaps, num_levels=4, radius=4, padding_mode="zeros"):
+        B, S, C, H, W = fmaps.shape
+        self.S, self.C, self.num_levels, self.radius, self.padding_mode = S, C, num_levels, radius, padding_mode
+        self.pyr = [fmaps]
+        for _ in range(num_levels - 1):
+            f = F.avg_pool2d(fmaps.reshape(B * S, C, H, W), 2, stride=2)
+            _, _, H, W = f.shape
+            fmaps = f.reshape(B, S, C, H, W)
+            self.pyr.append(fmaps)
+
+    def corr(self, targets):
+        B, S, N, C = targets.shape
+        self.vols = []
+        for fm in self.pyr:
+            H, W = fm.shape[-2:]
+            v = torch.matmul(targets, fm.reshape(B, S, C, H * W)).reshape(B, S, N, H, W)
+            self.vols.append(v / torch.sqrt(torch.tensor(float(C))))
+
+    def sample(self, coords):
+        r = self.radius
+        B, S, N, _ = coords.shape
+        d = torch.linspace(-r, r, 2 * r + 1, device=coords.device)
+        delta = torch.stack(torch.meshgrid(d, d, indexing="ij"), dim=-1)           # (..., 0) = row-varying -> added to x
+        out = []
+        for i, v in enumerate(self.vols):
+            H, W = v.shape[-2:]
+            c = coords.reshape(B * S * N, 1, 1, 2) / 2 ** i + delta[None]
+            g = torch.stack([c[..., 0] * (2.0 / max(W - 1, 1)) - 1.0, c[..., 1] * (2.0 / max(H - 1, 1)) - 1.0], dim=-1)
+            s = F.grid_sample(v.reshape(B * S * N, 1, H, W), g.to(v.dtype), align_corners=True, padding_mode=self.padding_mode)
+            out.append(s.reshape(B, S, N, -1))
+        return torch.cat(out, dim=-1).contiguous()

@@ -21,6 +21,8 @@ def _free_port():
 
 
 def _worker(rank, world, port, q, use_fabric=False):
+    if use_fabric == 1:
+        os.environ["VGG_FABRIC"] = "1"           # v1: multimem all-reduce + hook barriers (read once by the library)
     import torch
     import torch.distributed as dist
     from vggsfm_b200 import bundle_adjustment as ba
@@ -44,12 +46,13 @@ def _worker(rank, world, port, q, use_fabric=False):
     s = ba.lm_solve(t(c["uv"][:, lo:hi], torch.float32), t(c["mask"][:, lo:hi].astype(np.uint8)), poses, intr, pts,
                     c["model"], c["mode"], options=opt, allreduce=hook, want_trace=True)
     q.put((rank, poses.cpu().numpy(), intr.cpu().numpy(), pts.cpu().numpy(), s.iterations, s.final_cost,
-           s.trace.numpy().copy(), hook.calls, hook.barriers, bool(fabric is not None and fabric.ok)))
+           s.trace.numpy().copy(), hook.calls, hook.barriers, bool(fabric is not None and fabric.ok),
+           bool(fabric is not None and fabric.v2 and use_fabric == 2)))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("use_fabric", [False, True], ids=["nccl_allreduce", "multimem_fused"])
+@pytest.mark.parametrize("use_fabric", [0, 1, 2], ids=["nccl_allreduce", "fabric_v1_multimem", "fabric_v2_reduce_scatter"])
 def test_two_gpu_sharded_lm_matches_single_gpu(use_fabric):
     import torch
     import torch.multiprocessing as mp
@@ -75,10 +78,14 @@ def test_two_gpu_sharded_lm_matches_single_gpu(use_fabric):
     opt.max_num_iterations = 8
     s = ba.lm_solve(t(c["uv"], torch.float32), t(c["mask"].astype(np.uint8)), poses, intr, pts, c["model"], c["mode"],
                     options=opt, want_trace=True)
-    for rank, p, i, x, its, cost, tr, calls, barriers, fabric_ok in res:
+    for rank, p, i, x, its, cost, tr, calls, barriers, fabric_ok, v2 in res:
         lo, hi = (0, 256) if rank == 0 else (256, 512)
-        assert its == s.iterations and calls >= 2 * its
-        if use_fabric and fabric_ok:
+        assert its == s.iterations
+        if v2:
+            assert calls == 0 and barriers == 0      # no NCCL call, no host callback: everything is csrc/fabric.cu kernels
+        else:
+            assert calls >= 2 * its
+        if use_fabric == 1 and fabric_ok:
             assert barriers == 2 * its         # zeroed-before / landed-after, once per Schur build
         if use_fabric and not fabric_ok:
             pytest.skip("no NVSwitch multicast on this box")

@@ -16,7 +16,7 @@ EXPORTS = [
     "vgg_last_error", "vgg_version",
     "vgg_ba_default_options", "vgg_ba_dims", "vgg_ba_workspace_bytes", "vgg_ba_camrec_len",
     "vgg_ba_build_blocks", "vgg_ba_schur", "vgg_cholesky_lower", "vgg_ba_solve",
-    "vgg_ba_reduced_system_doubles", "vgg_ba_solve_fabric",
+    "vgg_ba_reduced_system_doubles", "vgg_ba_fabric_doubles", "vgg_ba_solve_fabric",
     "vgg_pose_default_options", "vgg_pose_refinement", "vgg_pnp_workspace_bytes", "vgg_absolute_pose_estimation", "vgg_syrk_ozaki_workspace_bytes", "vgg_syrk_ozaki",
     "vgg_tri_workspace_bytes", "vgg_triangulate_tracks", "vgg_triangulate_by_pair", "vgg_filter_points3d",
     "vgg_project_points", "vgg_normalize_tracks", "vgg_undistort_simple_radial",
@@ -67,7 +67,9 @@ class BASummary(ctypes.Structure):
 
 
 class BAFabric(ctypes.Structure):
-    _fields_ = [("ar_local", ctypes.c_void_p), ("ar_multicast", ctypes.c_void_p), ("ar_doubles", ctypes.c_size_t)]
+    _fields_ = [("ar_local", ctypes.c_void_p), ("ar_multicast", ctypes.c_void_p), ("ar_doubles", ctypes.c_size_t),
+                ("world", ctypes.c_int32), ("rank", ctypes.c_int32), ("peer_base", ctypes.c_void_p * 8),
+                ("total_doubles", ctypes.c_size_t)]
 
 
 class PoseOptions(ctypes.Structure):
@@ -127,6 +129,7 @@ def lib() -> ctypes.CDLL:
                                ctypes.c_void_p]
     vp, ci, cd, cs = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_size_t
     L.vgg_ba_reduced_system_doubles.argtypes = [ci, ci, ci, ctypes.POINTER(cs)]
+    L.vgg_ba_fabric_doubles.argtypes = [ci, ci, ci, ctypes.POINTER(cs)]
     L.vgg_ba_solve_fabric.argtypes = [ctypes.POINTER(BAProblem), ctypes.POINTER(BAOptions), vp, cs, ALLREDUCE_FN, vp,
                                       ctypes.POINTER(BAFabric), ctypes.POINTER(BASummary), vp, vp]
     L.vgg_pose_default_options.argtypes = [ctypes.POINTER(PoseOptions)]

@@ -635,6 +635,8 @@ int launch_z_transpose(int D, int N, int Dpad, const double* W, const double* M,
 // 0 (default): the reduced system is kept as a row-major LOWER triangle (csrc/chol.cu); 1: both triangles, for the
 // library factorisation A/B (set by csrc/ba_solve.cu from VGG_CHOL)
 int g_fill_upper = 0;
+// reduce-scatter destinations of the running multi-GPU solve (set per iteration by csrc/ba_solve.cu; world <= 1: off)
+FabricDev g_fabric_dev = {0, 0, {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}};
 
 int launch_syrk(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t mc_off, cudaStream_t st) {
   const int nb = Dpad / SY_BM;

@@ -7,6 +7,8 @@
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
+#include <functional>
+#include <map>
 #include <vector>
 #include "common.cuh"
 
@@ -61,6 +63,11 @@ int launch_trsv_upper(int n, int lda, const double* A, const double* y, size_t y
 size_t chol_workspace_doubles(int n);
 int chol_lower_inplace(int n, int lda, double* A, double* Ldiag, int* info, cudaStream_t st);
 extern int g_fill_upper;       // csrc/ba_schur.cu: 1 = also write the mirror triangle (library factorisation A/B)
+extern FabricDev g_fabric_dev; // csrc/ba_schur.cu: reduce-scatter destinations read by the SYRK epilogue
+int launch_fabric_barrier(const FabricDev& fd, size_t flags_off, unsigned long long epoch, int* err, cudaStream_t st);
+int launch_fabric_gather(const FabricDev& fd, int nrows, int nmat, int ncols_vec, int lda, cudaStream_t st);
+int launch_fabric_allreduce(const FabricDev& fd, size_t flags_off, size_t mail_off, int mail_len, int parity,
+                            unsigned long long epoch, double* vec, int count, int max_slot, int* err, cudaStream_t st);
 
 // gathers the accept/reject scalars into one 24-double record so the host reads them with ONE copy:
 // [0..7] = scal[0..7], [8..15] = small[0..7], [16] = potrf info, [17] = potrs info, [18] = |x|^2
@@ -71,6 +78,7 @@ __global__ void pack_scalars_kernel(const double* __restrict__ scal, const doubl
   else if (i < 16) out[i] = small[i - 8];
   else if (i < 18) out[i] = (double)info[i - 16];
   else if (i == 18) out[i] = scal[8];              // |x|^2 (xnorm_kernel), 0 unless parameter_tolerance > 0
+  else if (i == 19) out[i] = (double)info[2];      // a cross-rank barrier of csrc/fabric.cu timed out
 }
 
 // |x|^2 of Ceres' reduced program in ambient coordinates (ParameterToleranceReached: step_norm <= tol * (|x| + tol)):
@@ -281,10 +289,57 @@ static int potrf_lwork(int D, int Dpad, size_t* lwork) {
   return VGG_OK;
 }
 
+// Layout of the symmetric allocation of fabric v2 (doubles): two copies of the reduced system (iteration parity, so a
+// rank may zero the next copy while a slow peer still pulls from the previous one), the mailboxes of the small
+// all-reduce (2 parities x 8 source ranks), one row of 64-bit barrier flags.
+struct FabricLayout {
+  size_t arc, mail_off, flags_off, total;
+  int mail_len;
+};
+static FabricLayout fabric_layout(int D, int Dpad) {
+  FabricLayout f;
+  f.arc = align_up((size_t)D * Dpad + 3 * (size_t)Dpad, 256);
+  f.mail_len = Dpad + 64;
+  f.mail_off = 2 * f.arc;
+  f.flags_off = align_up(f.mail_off + (size_t)2 * 8 * f.mail_len, 32);
+  f.total = f.flags_off + 64;
+  return f;
+}
+
+// Run-time state of fabric v2 (csrc/fabric.cu): reduce-scatter + gather of the reduced system, in-kernel barriers and
+// small all-reduces -- no NCCL call and no host callback inside the LM loop.
+struct Fabric2 {
+  bool on = false;
+  FabricDev base{};                 // peer[r] = base of rank r's symmetric allocation
+  FabricLayout lay{};
+  unsigned long long* epoch = nullptr;
+  int small_parity = 0;
+  int* err = nullptr;
+  FabricDev at(size_t off) const {
+    FabricDev f = base;
+    for (int r = 0; r < f.world; ++r) f.peer[r] += off;
+    return f;
+  }
+  int barrier(cudaStream_t st) { return launch_fabric_barrier(base, lay.flags_off, ++*epoch, err, st); }
+  int allreduce(double* vec, int count, int max_slot, cudaStream_t st) {
+    small_parity ^= 1;
+    return launch_fabric_allreduce(base, lay.flags_off, lay.mail_off, lay.mail_len, small_parity, ++*epoch, vec, count,
+                                   max_slot, err, st);
+  }
+};
+
+// resets the process-wide kernel switches when a solve ends, on every exit path
+struct SolveGuard {
+  ~SolveGuard() {
+    g_fabric_dev.world = 0;
+    g_fill_upper = 0;
+  }
+};
+
 // Schur complement of blk onto AR (Sraw, rhs, hdiag, gvec) at the given radius
 static int schur_build(const Layout& L, const BlockSet& b, const uint8_t* point_const, double radius, double min_diag,
-                       double max_diag, cudaStream_t st, ptrdiff_t mc_off = 0, vgg_allreduce_fn barrier = nullptr,
-                       void* barrier_user = nullptr) {
+                       double max_diag, cudaStream_t st, ptrdiff_t mc_off = 0,
+                       const std::function<int()>* barrier = nullptr) {
   int rc;
   double* Sraw = L.AR;
   double* rhs = L.AR + (size_t)L.D * L.Dpad;
@@ -295,7 +350,7 @@ static int schur_build(const Layout& L, const BlockSet& b, const uint8_t* point_
     return rc;
   VGG_CUDA_CHECK(cudaMemsetAsync(L.AR, 0, sizeof(double) * ((size_t)L.D * L.Dpad + 3 * (size_t)L.Dpad), st));
   // fabric mode: every rank's copy must be zero before anyone's multimem reductions land in it
-  if (mc_off && barrier && (rc = barrier(barrier_user, nullptr, 0, 2, st))) return rc;
+  if (mc_off && barrier && (rc = (*barrier)())) return rc;
   if ((rc = launch_assemble_hc(L.S, L.dc, L.ns, L.KR, L.Dpad, b.camrec, b.shared, Sraw, rhs, hdiag, gvec, mc_off, st))) return rc;
   const int oz = L.oz_bytes ? syrk_i8_slices() : 0;
   if (oz && (rc = syrk_i8_reset_amax(L.oz_ws, L.Dpad, st))) return rc;
@@ -305,7 +360,7 @@ static int schur_build(const Layout& L, const BlockSet& b, const uint8_t* point_
   else rc = launch_syrk(L.Kpad, L.Dpad, L.Zt, Sraw, mc_off, st);
   if (rc) return rc;
   // ... and all reductions must have landed before anyone reads its copy
-  if (mc_off && barrier && (rc = barrier(barrier_user, nullptr, 0, 2, st))) return rc;
+  if (mc_off && barrier && (rc = (*barrier)())) return rc;
   return VGG_OK;
 }
 
@@ -433,6 +488,17 @@ int vgg_ba_reduced_system_doubles(int S, int camera_model, int intr_mode, size_t
   return VGG_OK;
 }
 
+int vgg_ba_fabric_doubles(int S, int camera_model, int intr_mode, size_t* doubles) {
+  int dc, ns;
+  if (!doubles || dims_of(camera_model, intr_mode, &dc, &ns, nullptr) != VGG_OK) {
+    set_error("bad camera_model/intr_mode");
+    return VGG_EINVAL;
+  }
+  const int D = S * dc + ns;
+  *doubles = fabric_layout(D, (int)align_up((size_t)D + 2, 128)).total;
+  return VGG_OK;
+}
+
 int vgg_ba_solve(const vgg_ba_problem* prob, const vgg_ba_options* opt_in, void* workspace, size_t ws_bytes,
                  vgg_allreduce_fn allreduce, void* ar_user, vgg_ba_summary* summary, double* trace, void* stream) {
   return vgg_ba_solve_fabric(prob, opt_in, workspace, ws_bytes, allreduce, ar_user, nullptr, summary, trace, stream);
@@ -470,16 +536,44 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
   // fabric mode: the reduced system lives in symmetric (peer-mapped) memory and is reduced by multimem operations
   // issued from the producing kernels; mc_off is the distance from a local address to its multicast twin
   ptrdiff_t mc_off = 0;
+  Fabric2 fab2;
+  SolveGuard guard;
+  static thread_local std::map<const double*, unsigned long long> fabric_epochs;
   if (fabric && fabric->ar_local && fabric->ar_multicast) {
-    VGG_REQUIRE(allreduce, "fabric mode needs the hook for its barrier (op 2)");
     VGG_REQUIRE(fabric->ar_doubles >= ar_count, "fabric buffer too small (vgg_ba_reduced_system_doubles)");
     L.AR = fabric->ar_local;
     mc_off = fabric->ar_multicast - fabric->ar_local;
+    // v2 (default when the caller passed the peer table): VGG_FABRIC=1 keeps v1 (multimem all-reduce into every copy,
+    // barriers and small all-reduces through the host hook) for A/B
+    static const bool want_v2 = [] { const char* e = getenv("VGG_FABRIC"); return !(e && e[0] == '1'); }();
+    const FabricLayout lay = fabric_layout(D, L.Dpad);
+    if (want_v2 && fabric->world > 1 && fabric->world <= 8 && fabric->peer_base[0] && fabric->total_doubles >= lay.total &&
+        L.oz_bytes && syrk_i8_slices() > 0) {
+      fab2.on = true;
+      fab2.lay = lay;
+      fab2.base.world = fabric->world;
+      fab2.base.rank = fabric->rank;
+      for (int r = 0; r < fabric->world; ++r) fab2.base.peer[r] = fabric->peer_base[r];
+      fab2.epoch = &fabric_epochs[fabric->peer_base[fabric->rank]];
+      fab2.err = L.dev_info + 2;
+    } else {
+      VGG_REQUIRE(allreduce, "fabric v1 needs the hook for its barrier (op 2)");
+    }
   }
   double* Sraw = L.AR;
   double* rhs = L.AR + (size_t)D * L.Dpad;
   double* hdiag = rhs + L.Dpad;
   double* gvec = hdiag + L.Dpad;
+  const std::function<int()> barrier_fn = [&]() -> int {
+    if (fab2.on) return fab2.barrier(st);
+    return allreduce(ar_user, nullptr, 0, 2, st);
+  };
+  // sum (and one max slot) of a small vector over the ranks: in-kernel over the fabric, else through the host hook
+  auto reduce_small = [&](double* vec, size_t count, int op) -> int {
+    if (fab2.on) return fab2.allreduce(vec, (int)count, op == 1 ? 0 : -1, st);
+    if (allreduce) return allreduce(ar_user, vec, count, op, st);
+    return VGG_OK;
+  };
   // factorisation: 2 = csrc/chol.cu (default), 0 = cuSOLVER Xpotrf (VGG_CHOL=lib), 1 = cuSOLVER Dpotrf (VGG_CHOL=legacy)
   static const int chol_mode = [] {
     const char* e = getenv("VGG_CHOL");
@@ -523,7 +617,7 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
   auto read_scalars = [&]() -> int {
     pack_scalars_kernel<<<1, 32, 0, st>>>(L.scal, L.small, L.dev_info, L.packed);
     VGG_LAUNCH_CHECK();
-    VGG_CUDA_CHECK(cudaMemcpyAsync(h_scal, L.packed, sizeof(double) * 24, cudaMemcpyDeviceToHost, st));
+    VGG_CUDA_CHECK(cudaMemcpyAsync(h_scal, L.packed, sizeof(double) * 24, cudaMemcpyDeviceToHost, st));   // [0..19] used
     VGG_CUDA_CHECK(cudaStreamSynchronize(st));
     return VGG_OK;
   };
@@ -533,11 +627,15 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
     VGG_CUDA_CHECK(cudaMemsetAsync(L.small, 0, sizeof(double) * (8 + (size_t)L.Dpad), st));
     VGG_CUDA_CHECK(cudaMemcpyAsync(L.small, b.cost, sizeof(double), cudaMemcpyDeviceToDevice, st));
     if ((r = launch_extract_gvec(S, dc, ns, L.KR, b.camrec, b.shared, L.small + 8, st))) return r;
-    if (allreduce && (r = allreduce(ar_user, L.small, 8 + (size_t)L.Dpad, 0, st))) return r;
+    if ((r = reduce_small(L.small, 8 + (size_t)L.Dpad, 0))) return r;
     VGG_CUDA_CHECK(cudaMemsetAsync(L.scal + 4, 0, sizeof(double) * 2, st));
     if ((r = launch_gradmax(D, N, L.small + 8, prob->param_const, b.g_p, prob->point_const, L.scal, st))) return r;
-    if (allreduce && (r = allreduce(ar_user, L.scal + 5, 1, 1, st))) return r;
+    if ((r = reduce_small(L.scal + 5, 1, 1))) return r;
     if ((r = read_scalars())) return r;
+    if (h_scal[19] != 0.0) {
+      set_error("fabric barrier timed out: a peer rank did not arrive");
+      return VGG_ECUDA;
+    }
     *cost_out = h_scal[8];
     *gmax_out = fmax(h_scal[4], h_scal[5]);
     return VGG_OK;
@@ -567,9 +665,24 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
     ++it;
     const int cand = cur ^ 1;
     VGG_CUDA_CHECK(cudaMemsetAsync(L.scal, 0, sizeof(double) * 16, st));
+    if (fab2.on) {
+      // this iteration's copy of the reduced system (parity) and where the SYRK epilogue sends each row block
+      const size_t off = (size_t)(it & 1) * fab2.lay.arc;
+      L.AR = fabric->ar_local + off;
+      Sraw = L.AR;
+      rhs = L.AR + (size_t)D * L.Dpad;
+      hdiag = rhs + L.Dpad;
+      gvec = hdiag + L.Dpad;
+      g_fabric_dev = fab2.at(off);
+    }
     if ((rc = schur_build(L, L.blk[cur], prob->point_const, radius, opt.min_lm_diagonal, opt.max_lm_diagonal, st, mc_off,
-                          allreduce, ar_user)))
+                          (fab2.on || allreduce) ? &barrier_fn : nullptr)))
       return rc;
+    if (fab2.on) {
+      // every row block is complete on its owner: pull the others (matrix rows 0..D incl. the rhs row, then hdiag, gvec)
+      if ((rc = launch_fabric_gather(g_fabric_dev, D + 3, D + 1, D, L.Dpad, st))) return rc;
+      g_fabric_dev.world = 0;
+    }
     if (allreduce && !mc_off && (rc = allreduce(ar_user, L.AR, ar_count, 0, st))) return rc;
     if (!have_scale_c) {
       if ((rc = launch_jacobi_scale_cams(D, hdiag, L.sc_c, opt.jacobi_scaling, st))) return rc;
@@ -652,8 +765,8 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
     if ((rc = launch_cam_step(D, dcs, dcs_stride, L.sc_c, hdiag, gvec, prob->param_const, radius, opt.min_lm_diagonal,
                               opt.max_lm_diagonal, L.d_c, L.scal, st)))
       return rc;
-    if (mc_off) {
-      // Fabric mode: the multimem reductions reach each rank's copy in a different order, so the copies (and with
+    if (mc_off && !fab2.on) {
+      // Fabric v1: the multimem reductions reach each rank's copy in a different order, so the copies (and with
       // them the factorisation and the camera step) differ in the last bits.  Keep the replicated camera state
       // and the accept/reject scalars bit-identical on every rank: element-wise MAX over ranks of
       // [d_c | quad_c | |d_c|^2] (one 19 KB collective; any rank-consistent choice within rounding would do).
@@ -675,9 +788,19 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
     VGG_CUDA_CHECK(cudaMemcpyAsync(L.small + 1, L.scal + 2, sizeof(double) * 2, cudaMemcpyDeviceToDevice, st));
     VGG_CUDA_CHECK(cudaMemcpyAsync(L.small + 3, L.scal + 6, sizeof(double), cudaMemcpyDeviceToDevice, st));
     if ((rc = launch_extract_gvec(S, dc, ns, L.KR, L.blk[cand].camrec, L.blk[cand].shared, L.small + 8, st))) return rc;
-    if (allreduce && (rc = allreduce(ar_user, L.small, 8 + (size_t)L.Dpad, 0, st))) return rc;
-    if ((rc = launch_gradmax(D, N, L.small + 8, prob->param_const, L.blk[cand].g_p, prob->point_const, L.scal, st))) return rc;
-    if (allreduce && (rc = allreduce(ar_user, L.scal + 5, 1, 1, st))) return rc;
+    if (fab2.on) {
+      // one in-kernel all-reduce for everything: the point-gradient max rides in slot 4 (max), the rest is summed
+      if ((rc = launch_gradmax(D, N, L.small + 8, prob->param_const, L.blk[cand].g_p, prob->point_const, L.scal, st))) return rc;
+      VGG_CUDA_CHECK(cudaMemcpyAsync(L.small + 4, L.scal + 5, sizeof(double), cudaMemcpyDeviceToDevice, st));
+      if ((rc = fab2.allreduce(L.small, 8 + L.Dpad, 4, st))) return rc;
+      VGG_CUDA_CHECK(cudaMemsetAsync(L.scal + 4, 0, sizeof(double) * 2, st));
+      if ((rc = launch_gradmax(D, N, L.small + 8, prob->param_const, L.blk[cand].g_p, prob->point_const, L.scal, st))) return rc;
+      VGG_CUDA_CHECK(cudaMemcpyAsync(L.scal + 5, L.small + 4, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    } else {
+      if (allreduce && (rc = allreduce(ar_user, L.small, 8 + (size_t)L.Dpad, 0, st))) return rc;
+      if ((rc = launch_gradmax(D, N, L.small + 8, prob->param_const, L.blk[cand].g_p, prob->point_const, L.scal, st))) return rc;
+      if (allreduce && (rc = allreduce(ar_user, L.scal + 5, 1, 1, st))) return rc;
+    }
     if (opt.parameter_tolerance > 0.0) {
       // |x| of THIS rank's points + the replicated cameras; with track shards the point part is a partial sum, which
       // only makes the test stricter by under-estimating |x| (parameter_tolerance is 0 in every COLMAP preset)
@@ -692,6 +815,10 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
     const double quad = h_scal[0] + h_scal[9];
     const double step_norm = sqrt(h_scal[1] + h_scal[10]);
     const double model_change = 0.5 * quad;
+    if (h_scal[19] != 0.0) {
+      set_error("fabric barrier timed out: a peer rank did not arrive");
+      return VGG_ECUDA;
+    }
     const bool solver_bad = h_info[0] != 0 || h_info[1] != 0 || h_scal[7] > 0 || h_scal[11] > 0;
     double* tr = trace ? trace + (size_t)(it - 1) * 8 : nullptr;
     if (tr) {

@@ -51,6 +51,12 @@ struct Carver {
   bool ok() const { return base == nullptr || off <= cap; }
 };
 
+// Destination table of the fused multi-GPU reduction (csrc/fabric.cu): world <= 1 means "not in use".
+struct FabricDev {
+  int world, rank;
+  double* peer[8];     // rank r's copy of the buffer being addressed (same layout on every rank, peer-mapped)
+};
+
 #ifdef __CUDACC__
 // ---------------------------------------------------------------------------------------------
 // TMA 1-D bulk copies + mbarrier (PTX ISA 8.x, sm_90+; SASS: UBLKCP / SYNCS)

@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     oz_syrk_kernel(const __grid_constant__ OzPlan plan, const OzWork* __restrict__ work, int nwork, int KB,
                    const int8_t* __restrict__ slices, size_t slice_stride, const int* __restrict__ expo,
                    const double* __restrict__ pow2, int Dpad, double* __restrict__ Cmat, ptrdiff_t mc_off,
-                   int fill_upper) {
+                   int fill_upper, const __grid_constant__ FabricDev fd) {
   extern __shared__ __align__(1024) uint8_t oz_smem[];
   uint8_t* tiles = reinterpret_cast<uint8_t*>(align_up(reinterpret_cast<size_t>(oz_smem), 1024));
   uint64_t* full = reinterpret_cast<uint64_t*>(tiles + (size_t)OZ_STAGES * OZ_STAGE_BYTES);
@@ -338,11 +338,15 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
           // what csrc/chol.cu factors (fabric mode: one multimem op per element).  The direct element (r, col) is only
           // written for the library factorisation A/B.
           if (!diag || col >= r) {
-            double* q = &Cmat[(size_t)col * Dpad + r];
-            if (mc_off) {
-              asm volatile("multimem.red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(q + mc_off), "d"(-v) : "memory");
+            const size_t off = (size_t)col * Dpad + r;
+            if (fd.world > 1) {
+              // reduce-scatter: row block wk.bj of the lower triangle lives on rank (wk.bj mod world) until the gather
+              // (csrc/fabric.cu); one system-scope RED over NVLink per element, only into the owner's copy
+              asm volatile("red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(fd.peer[wk.bj % fd.world] + off), "d"(-v) : "memory");
+            } else if (mc_off) {
+              asm volatile("multimem.red.relaxed.sys.global.add.f64 [%0], %1;" ::"l"(Cmat + off + mc_off), "d"(-v) : "memory");
             } else {
-              atomicAdd(q, -v);
+              atomicAdd(Cmat + off, -v);
             }
           }
           if (fill_upper && (!diag || col > r)) atomicAdd(&Cmat[(size_t)r * Dpad + col], -v);
@@ -853,6 +857,7 @@ int syrk_i8_reset_amax(void* ws, int Dpad, cudaStream_t st) {
 // Sraw -= Zt^T Zt with s int8 slices.  Zt [Kpad][Dpad] (Dpad % 128 == 0), Cmat [Dpad][Dpad] row-major, LOWER triangle
 // written (plus the mirror when g_fill_upper), same contract as launch_syrk.
 extern int g_fill_upper;      // csrc/ba_schur.cu
+extern FabricDev g_fabric_dev;  // csrc/ba_schur.cu: reduce-scatter destinations of the current multi-GPU solve (world <= 1: off)
 
 int launch_syrk_i8(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t mc_off, int s, void* ws,
                    size_t ws_bytes, cudaStream_t st, bool amax_ready) {
@@ -916,7 +921,7 @@ int launch_syrk_i8(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t
   const size_t slice_stride = (size_t)nb * KB * OZ_TILE_BYTES;
   const int nwork = (int)hs.work.size();
 
-  const bool pair = use_pair_kernel() && hs.sms >= 2;
+  const bool pair = use_pair_kernel() && hs.sms >= 2 && g_fabric_dev.world <= 1;   // the reduce-scatter epilogue lives in oz_syrk_kernel
   if (pair) VGG_CUDA_CHECK(cudaMemcpyAsync(work_raw, hs.pinned2, sizeof(OzWork2) * hs.work2.size(), cudaMemcpyHostToDevice, st));
   else VGG_CUDA_CHECK(cudaMemcpyAsync(work_d, hs.pinned, sizeof(OzWork) * nwork, cudaMemcpyHostToDevice, st));
   if (!amax_ready) {
@@ -936,7 +941,7 @@ int launch_syrk_i8(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t
   } else {
     const int grid = std::min(hs.sms, nwork);
     oz_syrk_kernel<<<grid, OZ_THREADS, OZ_SMEM_BYTES, st>>>(hs.plan, work_d, nwork, KB, slices, slice_stride, expo, pow2,
-                                                          Dpad, Cmat, mc_off, g_fill_upper);
+                                                          Dpad, Cmat, mc_off, g_fill_upper, g_fabric_dev);
   }
   VGG_LAUNCH_CHECK();
   return VGG_OK;

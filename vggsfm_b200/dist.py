@@ -29,25 +29,43 @@ def shard_range(N: int, rank: int, world: int, multiple: int = 16):
 
 
 class FabricBuffer:
-    """Reduced-system buffer in symmetric (peer-mapped, NVSwitch-multicast) memory for the fused reduction:
-    the Schur kernels of every rank add into all copies with multimem.red (csrc/ba_schur.cu: ar_add), so the
-    per-iteration all-reduce of [D x Dpad | rhs | diag | g] needs no separate collective -- only two barriers."""
+    """Reduced-system buffer in symmetric (peer-mapped, NVSwitch-multicast) memory for the fused reduction
+    (include/vggsfm_b200.h: vgg_ba_fabric).  v2 (default): the tcgen05 SYRK's epilogue REDs every 128-row block of the
+    lower triangle into its owner's copy over NVLink (reduce-scatter), every rank then pulls the blocks it does not own
+    (csrc/fabric.cu), and the barriers / small all-reduces of the LM loop are kernels on the same allocation -- no NCCL
+    call and no host callback inside the loop.  v1 (``VGG_FABRIC=1``): multimem.red into every copy + barriers and
+    small all-reduces through the AllReduceHook."""
 
     def __init__(self, S: int, model: int, mode: int, device, group=None):
         import torch.distributed._symmetric_memory as symm_mem
-        n = ctypes.c_size_t()
+        group = group if group is not None else dist.group.WORLD
+        n, n2 = ctypes.c_size_t(), ctypes.c_size_t()
         _lib.check(_lib.lib().vgg_ba_reduced_system_doubles(S, model, mode, ctypes.byref(n)), "vgg_ba_reduced_system_doubles")
-        self.count = n.value
-        self.tensor = symm_mem.empty(self.count, dtype=torch.float64, device=device)
-        self.handle = symm_mem.rendezvous(self.tensor, group if group is not None else dist.group.WORLD)
+        _lib.check(_lib.lib().vgg_ba_fabric_doubles(S, model, mode, ctypes.byref(n2)), "vgg_ba_fabric_doubles")
+        self.count, self.total = n.value, n2.value
+        self.tensor = symm_mem.empty(self.total, dtype=torch.float64, device=device)
+        self.handle = symm_mem.rendezvous(self.tensor, group)
+        self.tensor.zero_()                           # barrier flags and mailboxes start at zero on every rank
+        torch.cuda.synchronize(device)
+        dist.barrier(group=group)
         self.multicast_ptr = int(getattr(self.handle, "multicast_ptr", 0) or 0)
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        ptrs = getattr(self.handle, "buffer_ptrs", None)
+        self.peer_ptrs = [int(p) for p in ptrs] if ptrs is not None else []
         self.ok = self.multicast_ptr != 0
+        self.v2 = self.ok and len(self.peer_ptrs) == self.world and 1 < self.world <= 8
 
     def barrier(self):
         self.handle.barrier(channel=0)
 
     def struct(self):
-        return _lib.BAFabric(self.tensor.data_ptr(), self.multicast_ptr, self.count)
+        f = _lib.BAFabric()
+        f.ar_local, f.ar_multicast, f.ar_doubles = self.tensor.data_ptr(), self.multicast_ptr, self.count
+        if self.v2:
+            f.world, f.rank, f.total_doubles = self.world, self.rank, self.total
+            for r, p in enumerate(self.peer_ptrs):
+                f.peer_base[r] = p
+        return f
 
 
 class AllReduceHook:
