@@ -127,13 +127,22 @@ def build_blocks(uv, mask, poses, intr, points, model, mode, point_const=None, t
     dc, ns = dims(model, mode)
     KR = L.vgg_ba_camrec_len(model, mode)
     dev = uv.device
+    # the five accumulators carved back to back (cost | shared | camrec | g_p | H_pp, 32-double aligned) like the
+    # solver's own workspace, so the library zeroes them with ONE memset
+    al = lambda n: (n + 31) // 32 * 32
+    offs, tot = {}, 0
+    for name, n in (("cost", 8), ("shared", 8), ("camrec", S * KR), ("g_p", N * 3), ("H_pp", N * 6)):
+        offs[name] = (tot, n)
+        tot += al(n)
+    flat = torch.empty(tot, dtype=torch.float64, device=dev)
+    view = lambda name, shape: flat[offs[name][0]:offs[name][0] + offs[name][1]].view(*shape)
     out = {
-        "cost": torch.empty(1, dtype=torch.float64, device=dev),
-        "camrec": torch.empty(S, KR, dtype=torch.float64, device=dev),
-        "g_p": torch.empty(N, 3, dtype=torch.float64, device=dev),
-        "H_pp": torch.empty(N, 6, dtype=torch.float64, device=dev),
+        "cost": view("cost", (8,))[:1],
+        "camrec": view("camrec", (S, KR)),
+        "g_p": view("g_p", (N, 3)),
+        "H_pp": view("H_pp", (N, 6)),
         "W": torch.empty(N, (S * dc + ns + 1) // 2 * 2, 3, dtype=torch.float64, device=dev),
-        "shared": torch.empty(8, dtype=torch.float64, device=dev),
+        "shared": view("shared", (8,)),
     }
     p = _problem(uv, mask, poses, intr, points, model, mode, None, point_const)
     with torch.cuda.device(dev):
