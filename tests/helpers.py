@@ -69,8 +69,14 @@ def tiny_former(in_dim, out_dim, seed):
             self.b = nn.Linear(in_dim, out_dim)
 
         def forward(self, x):                       # [B, N, S, D] -> [B, N, S, out]
-            return (0.3 * torch.tanh(self.a(x)) + 0.2 * torch.tanh(self.b(x.mean(dim=2, keepdim=True)))
-                    + 0.1 * torch.tanh(self.b(x.mean(dim=1, keepdim=True))))
+            # coordinate outputs (first two channels) small, feature outputs O(1): the loop then stays a contraction
+            # (GroupNorm re-normalises the feature delta, so a tiny delta would amplify float32 rounding differences
+            # between two correct correlation implementations ~20x per iteration and the golden would pin nothing)
+            y = (torch.tanh(self.a(x)) + 0.5 * torch.tanh(self.b(x.mean(dim=2, keepdim=True)))
+                 + 0.25 * torch.tanh(self.b(x.mean(dim=1, keepdim=True))))
+            scale = torch.ones(y.shape[-1], device=y.device, dtype=y.dtype)
+            scale[:2] = 0.08
+            return y * scale
 
     g = torch.Generator().manual_seed(seed)
     m = TinyFormer()

@@ -54,7 +54,10 @@ def main():
                                       depth=1, fine=False, cfg=cfg)
         ref.updateformer = tiny_former(ref.transformer_dim, 34, seed=1)
         ref.eval()
-        fmaps = torch.randn(2, 5, 32, 32, 48)
+        # smooth feature maps (a coarse random field, bilinearly upsampled, + 5 % noise): the correlation landscape a
+        # trained encoder produces, not white noise
+        fmaps = torch.nn.functional.interpolate(torch.randn(10, 32, 5, 7), size=(32, 48), mode="bilinear", align_corners=True)
+        fmaps = (fmaps + 0.05 * torch.randn_like(fmaps)).reshape(2, 5, 32, 32, 48)
         qp = torch.rand(2, 20, 2) * torch.tensor([48 * 4 - 8.0, 32 * 4 - 8.0]) + 4.0
         preds, vis, feats, qfeat = ref(qp, fmaps, iters=4, return_feat=True)
         np.savez_compressed(os.path.join(out, "tracker_coarse.npz"), fmaps=fmaps.numpy(), qp=qp.numpy(),
@@ -71,7 +74,8 @@ def main():
         fine.updateformer = tiny_former(fine.transformer_dim, 34, seed=2)
         fine.eval()
         fnet = torch.nn.Conv2d(3, 32, 3, padding=1)
-        images = torch.rand(1, 4, 3, 72, 72)
+        images = torch.nn.functional.interpolate(torch.rand(4, 3, 9, 9), size=(72, 72), mode="bilinear", align_corners=True)[None]
+        images = images + 0.02 * torch.rand_like(images)
         coarse = torch.rand(1, 4, 7, 2) * 60 + 6
         coarse[0, :, 0] = torch.tensor([1.3, 70.2])          # a track whose patch is clamped at the border
         tracks, score = rt.refine_track(images, fnet, fine, coarse, compute_score=True, pradius=15, sradius=2, fine_iters=3)

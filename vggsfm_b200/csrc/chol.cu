@@ -28,99 +28,160 @@ constexpr int C_RPC = 16;     // panel rows per CTA in the triangular solve
 constexpr int CT = 64;        // trailing-update tile
 constexpr int C_THREADS = 256;
 
+__device__ __forceinline__ void chol_dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
 // Cholesky of the 128x128 block in shared memory Ls (row stride CLD) by the whole CTA (256 threads).  Lower triangle
 // in, L out (entries above the diagonal are left undefined).  dinv[j] = 1 / L[j][j].  Returns 0 or 1 + first bad pivot.
+// Two levels (r02 profile of the one-level version: 77 us per panel, the 4x4-tile rank-8 updates of the whole
+// trailing block ran into 8-way bank conflicts and 128 FMA instructions per 16 outputs):
+//   * four 32-column sub-panels; inside one, 8-column micro-panels: (a) 8x8 leaf by warp 0 (one row per lane, pivot
+//     column through shuffles, rsqrt), (b) one thread per row below solves its 8 entries, (c) rank-8 update of the
+//     REST OF THE SUB-PANEL only (<= 24 columns), two threads per row;
+//   * after each sub-panel ONE rank-32 update of everything to its right with mma.sync.m8n8k4.f64 (DMMA), 32x16 warp
+//     tiles straight from the row-major block (row stride 132: conflict-free fragments).
 __device__ __forceinline__ int cta_chol128(double* Ls, double* dinv, int* fail_sm, int tid) {
   const int lane = tid & 31, warp = tid >> 5;
   if (tid == 0) *fail_sm = 0;
   __syncthreads();
-  for (int p = 0; p < CB / 8; ++p) {
-    const int c0 = p * 8;
-    if (warp == 0) {
-      // (a) 8x8 leaf: one row per lane (lanes 8..31 mirror lanes 0..7), pivot column through shuffles
-      double a[8];
-      const int r = c0 + (lane & 7);
-#pragma unroll
-      for (int c = 0; c < 8; ++c) a[c] = Ls[r * CLD + c0 + c];
-      int fail = 0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const double pj = __shfl_sync(0xffffffffu, a[j], j);
-        if (!(pj > 0.0) && fail == 0) fail = c0 + j + 1;
-        const double inv = rsqrt(pj > 0.0 ? pj : 1.0);
-        a[j] = (lane == j) ? pj * inv : a[j] * inv;
-        if (lane == j) dinv[c0 + j] = inv;
-#pragma unroll
-        for (int c = j + 1; c < 8; ++c) {
-          const double lc = __shfl_sync(0xffffffffu, a[j], c);
-          if (lane >= c) a[c] = fma(-a[j], lc, a[c]);
-        }
-      }
-      if (lane < 8) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) Ls[r * CLD + c0 + c] = (c <= lane) ? a[c] : 0.0;
-      }
-      if (lane == 0 && fail && *fail_sm == 0) *fail_sm = fail;
-    }
-    __syncthreads();
-    // (b) rows below the micro-block: x L^T = a, one thread per row
-    {
-      const int r = c0 + 8 + tid;
-      if (r < CB) {
-        double x[8];
+  for (int sp = 0; sp < CB / 32; ++sp) {
+    const int c32 = sp * 32;
+    for (int mp = 0; mp < 4; ++mp) {
+      const int c0 = c32 + mp * 8;
+      if (warp == 0) {
+        // (a) 8x8 leaf: one row per lane (lanes 8..31 mirror lanes 0..7), pivot column through shuffles
+        double a[8];
+        const int r = c0 + (lane & 7);
 #pragma unroll
         for (int c = 0; c < 8; c += 2) {
           const double2 v = *reinterpret_cast<const double2*>(Ls + r * CLD + c0 + c);
-          x[c] = v.x;
-          x[c + 1] = v.y;
+          a[c] = v.x;
+          a[c + 1] = v.y;
         }
+        int fail = 0;
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-          x[m] *= dinv[c0 + m];
+        for (int j = 0; j < 8; ++j) {
+          const double pj = __shfl_sync(0xffffffffu, a[j], j);
+          if (!(pj > 0.0) && fail == 0) fail = c0 + j + 1;
+          const double inv = rsqrt(pj > 0.0 ? pj : 1.0);
+          a[j] = (lane == j) ? pj * inv : a[j] * inv;
+          if (lane == j) dinv[c0 + j] = inv;
 #pragma unroll
-          for (int j = m + 1; j < 8; ++j) x[j] = fma(-x[m], Ls[(c0 + j) * CLD + c0 + m], x[j]);
+          for (int c = j + 1; c < 8; ++c) {
+            const double lc = __shfl_sync(0xffffffffu, a[j], c);
+            if (lane >= c) a[c] = fma(-a[j], lc, a[c]);
+          }
         }
+        if (lane < 8) {
 #pragma unroll
-        for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2*>(Ls + r * CLD + c0 + c) = make_double2(x[c], x[c + 1]);
+          for (int c = 0; c < 8; ++c) Ls[r * CLD + c0 + c] = (c <= lane) ? a[c] : 0.0;
+        }
+        if (lane == 0 && fail && *fail_sm == 0) *fail_sm = fail;
       }
-    }
-    __syncthreads();
-    // (c) rank-8 update of the remaining lower triangle (rows/cols >= c0+8) in 4x4 register tiles
-    {
-      const int base = c0 + 8;
-      const int tm = (CB - base) >> 2;                 // tiles per side
-      const int count = tm * (tm + 1) / 2;
-      for (int e = tid; e < count; e += C_THREADS) {
-        int ti = (int)((sqrtf(8.0f * (float)e + 1.0f) - 1.0f) * 0.5f);
-        while ((ti + 1) * (ti + 2) / 2 <= e) ++ti;
-        while (ti * (ti + 1) / 2 > e) --ti;
-        const int tj = e - ti * (ti + 1) / 2;
-        const int i0 = base + 4 * ti, j0 = base + 4 * tj;
-        double li[4][8], lj[4][8];
+      __syncthreads();
+      // (b) rows below the micro-block: x L^T = a, one thread per row
+      {
+        const int r = c0 + 8 + tid;
+        if (r < CB) {
+          double x[8];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
+          for (int c = 0; c < 8; c += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(Ls + r * CLD + c0 + c);
+            x[c] = v.x;
+            x[c + 1] = v.y;
+          }
+#pragma unroll
+          for (int m = 0; m < 8; ++m) {
+            x[m] *= dinv[c0 + m];
+#pragma unroll
+            for (int j = m + 1; j < 8; ++j) x[j] = fma(-x[m], Ls[(c0 + j) * CLD + c0 + m], x[j]);
+          }
+#pragma unroll
+          for (int c = 0; c < 8; c += 2) *reinterpret_cast<double2*>(Ls + r * CLD + c0 + c) = make_double2(x[c], x[c + 1]);
+        }
+      }
+      __syncthreads();
+      // (c) rank-8 update of the remaining columns of THIS sub-panel (c0+8 .. c32+31), all rows below; two threads
+      //     per row, each takes every second column
+      if (mp < 3) {
+        const int r = c0 + 8 + (tid >> 1), half = tid & 1;
+        if (r < CB) {
+          double li[8];
 #pragma unroll
           for (int k = 0; k < 8; k += 2) {
-            const double2 u = *reinterpret_cast<const double2*>(Ls + (i0 + a) * CLD + c0 + k);
-            li[a][k] = u.x;
-            li[a][k + 1] = u.y;
-            const double2 w = *reinterpret_cast<const double2*>(Ls + (j0 + a) * CLD + c0 + k);
-            lj[a][k] = w.x;
-            lj[a][k + 1] = w.y;
+            const double2 v = *reinterpret_cast<const double2*>(Ls + r * CLD + c0 + k);
+            li[k] = v.x;
+            li[k + 1] = v.y;
           }
+          const int jend = min(r, c32 + 31);
+          for (int j = c0 + 8 + half; j <= jend; j += 2) {
+            const double* lj = Ls + j * CLD + c0;
+            double sacc = Ls[r * CLD + j];
 #pragma unroll
-        for (int a = 0; a < 4; ++a)
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            if (ti == tj && b > a) continue;
-            double s = Ls[(i0 + a) * CLD + j0 + b];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) s = fma(-li[a][k], lj[b][k], s);
-            Ls[(i0 + a) * CLD + j0 + b] = s;
+            for (int k = 0; k < 8; k += 2) {
+              const double2 v = *reinterpret_cast<const double2*>(lj + k);
+              sacc = fma(-li[k], v.x, sacc);
+              sacc = fma(-li[k + 1], v.y, sacc);
+            }
+            Ls[r * CLD + j] = sacc;
           }
+        }
+        __syncthreads();
       }
     }
-    __syncthreads();
+    // rank-32 update of the block to the right of the sub-panel: C[i][j] -= sum_k L[i][c32+k] L[j][c32+k], i >= j >= c32+32
+    const int t0 = c32 + 32;
+    const int nrb = (CB - t0) / 32;                  // 32-row blocks: 3, 2, 1, 0
+    if (nrb > 0) {
+      const int ntile = nrb * (nrb + 1);             // sum over rb of (2 rb + 2) 16-column tiles
+      const int g = lane >> 2, q = lane & 3;
+      for (int t = warp; t < ntile; t += C_THREADS / 32) {
+        int rb = 0, cb = t;
+        while (cb >= 2 * rb + 2) { cb -= 2 * rb + 2; ++rb; }
+        const int R0 = t0 + rb * 32, C0 = t0 + cb * 16;
+        double c[4][2][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+        const double* arow = Ls + (R0 + g) * CLD + c32 + q;
+        const double* brow = Ls + (C0 + g) * CLD + c32 + q;
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          double a[4], b[2];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a[i] = arow[i * 8 * CLD + k4 * 4];
+#pragma unroll
+          for (int j = 0; j < 2; ++j) b[j] = brow[j * 8 * CLD + k4 * 4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) chol_dmma(c[i][j][0], c[i][j][1], a[i], b[j]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int r = R0 + i * 8 + g;
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int col = C0 + j * 8 + 2 * q;
+            if (col > r) continue;
+            double* pp = Ls + r * CLD + col;
+            if (col + 1 <= r) {
+              double2 v = *reinterpret_cast<double2*>(pp);
+              v.x -= c[i][j][0];
+              v.y -= c[i][j][1];
+              *reinterpret_cast<double2*>(pp) = v;
+            } else {
+              *pp -= c[i][j][0];
+            }
+          }
+        }
+      }
+      __syncthreads();
+    }
   }
   return *fail_sm;
 }
@@ -222,26 +283,26 @@ __global__ void __launch_bounds__(C_THREADS, 1) chol_panel_kernel(int n, int lda
   }
 }
 
-__device__ __forceinline__ void chol_dmma(double& d0, double& d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(d0), "+d"(d1)
-               : "d"(a), "d"(b));
-}
-
-// A[t0.., t0..] -= P P^T (lower tiles), P = A[t0.., k0..k0+127].  64x64 tiles, 8 warps as 2x4, warp tile 32x16.
-// mode 0: all lower tiles; 1: tile columns 0 and 1 (the next panel's 128 columns); 2: tile columns >= 2.
+// A[t0.., t0..] -= P P^T (lower part), P = A[t0.., k0..k0+127].  Tiles of TM rows x 64 columns, 8 warps.
+//   TM = 64 (trailing update off the critical path): tile (bi, bj), bj <= bi, warps 2x4, warp tile 32x16; mode 2 = tile
+//            columns >= 2, mode 0 = all.
+//   TM = 32 (mode 1, the next panel's 128 columns = tile columns 0 and 1, ON the critical path): twice as many CTAs so
+//            the ~140 tiles of a 2400-row matrix fill the 148 SMs with one short tile each; warps 1x8, warp tile 32x8.
+template <int TM>
 __global__ void __launch_bounds__(C_THREADS, 1) chol_update_kernel(int n, int lda, int k0, int t0, int mode,
                                                                     double* __restrict__ A) {
+  constexpr int WN = TM == 64 ? 4 : 8;            // warps along the 64 tile columns
+  constexpr int NJ = 64 / WN / 8;                 // 8-column MMA tiles per warp: 2 or 1
   extern __shared__ __align__(16) double cu_smem[];
-  double* As = cu_smem;                         // [64][CLD]
-  double* Bs = cu_smem + CT * CLD;
-  const int T = (n - t0 + CT - 1) / CT;
+  double* As = cu_smem;                         // [TM][CLD]
+  double* Bs = cu_smem + TM * CLD;              // [64][CLD]
   int bi, bj;
   {
     int t = blockIdx.x;
-    if (mode == 1) {
+    if (TM == 32) {
+      const int T = (n - t0 + 31) / 32;           // 32-row tiles; tile column 1 starts at row tile 2
       if (t < T) { bi = t; bj = 0; }
-      else { bi = t - T + 1; bj = 1; }
+      else { bi = t - T + 2; bj = 1; }
     } else {
       bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
       while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
@@ -250,47 +311,39 @@ __global__ void __launch_bounds__(C_THREADS, 1) chol_update_kernel(int n, int ld
       if (mode == 2) { bi += 2; bj += 2; }
     }
   }
-  const bool diag = bi == bj;
+  const bool diag = TM == 64 && bi == bj;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ri = t0 + bi * CT, rj = t0 + bj * CT;
+  const int ri = t0 + bi * TM, rj = t0 + bj * 64;
   // panel rows, row-major (k contiguous), two K halves as two cp.async groups
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
-    for (int e = tid; e < CT * 16; e += C_THREADS) {
-      const int row = e >> 4, ch = (e & 15) * 4 + half * 64;     // 16-byte chunk = 2 doubles; 4 doubles per thread-step
-      double* da = As + row * CLD + ch;
-      if (ri + row < n) {
-        const double* src = A + (size_t)(ri + row) * lda + k0 + ch;
-        cp_async16(da, src);
-        cp_async16(da + 2, src + 2);
+    for (int e = tid; e < (TM + 64) * 16; e += C_THREADS) {
+      const int row = e >> 4, ch = (e & 15) * 4 + half * 64;     // 4 doubles (two 16-byte chunks) per thread-step
+      const bool isA = row < TM;
+      if (!isA && diag) continue;
+      const int grow = isA ? ri + row : rj + (row - TM);
+      double* dst = (isA ? As + row * CLD : Bs + (row - TM) * CLD) + ch;
+      if (grow < n) {
+        const double* src = A + (size_t)grow * lda + k0 + ch;
+        cp_async16(dst, src);
+        cp_async16(dst + 2, src + 2);
       } else {
-        *reinterpret_cast<double2*>(da) = make_double2(0.0, 0.0);
-        *reinterpret_cast<double2*>(da + 2) = make_double2(0.0, 0.0);
-      }
-      if (!diag) {
-        double* db = Bs + row * CLD + ch;
-        if (rj + row < n) {
-          const double* src = A + (size_t)(rj + row) * lda + k0 + ch;
-          cp_async16(db, src);
-          cp_async16(db + 2, src + 2);
-        } else {
-          *reinterpret_cast<double2*>(db) = make_double2(0.0, 0.0);
-          *reinterpret_cast<double2*>(db + 2) = make_double2(0.0, 0.0);
-        }
+        *reinterpret_cast<double2*>(dst) = make_double2(0.0, 0.0);
+        *reinterpret_cast<double2*>(dst + 2) = make_double2(0.0, 0.0);
       }
     }
     cp_async_commit();
   }
   const double* bs = diag ? As : Bs;
-  const int wm = warp >> 2, wn = warp & 3;
+  const int wm = warp / WN, wn = warp % WN;
   const int g = lane >> 2, q = lane & 3;
-  double c[4][2][2];
+  double c[4][NJ][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 2; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+    for (int j = 0; j < NJ; ++j) c[i][j][0] = c[i][j][1] = 0.0;
   const double* arow = As + (wm * 32 + g) * CLD + q;
-  const double* brow = bs + (wn * 16 + g) * CLD + q;
+  const double* brow = bs + (wn * (8 * NJ) + g) * CLD + q;
 #pragma unroll
   for (int half = 0; half < 2; ++half) {
     if (half == 0) cp_async_wait<1>();
@@ -298,15 +351,15 @@ __global__ void __launch_bounds__(C_THREADS, 1) chol_update_kernel(int n, int ld
     __syncthreads();
 #pragma unroll 4
     for (int k4 = half * 16; k4 < half * 16 + 16; ++k4) {
-      double a[4], b[2];
+      double a[4], b[NJ];
 #pragma unroll
       for (int i = 0; i < 4; ++i) a[i] = arow[i * 8 * CLD + k4 * 4];
 #pragma unroll
-      for (int j = 0; j < 2; ++j) b[j] = brow[j * 8 * CLD + k4 * 4];
+      for (int j = 0; j < NJ; ++j) b[j] = brow[j * 8 * CLD + k4 * 4];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 2; ++j) chol_dmma(c[i][j][0], c[i][j][1], a[i], b[j]);
+        for (int j = 0; j < NJ; ++j) chol_dmma(c[i][j][0], c[i][j][1], a[i], b[j]);
     }
   }
 #pragma unroll
@@ -314,8 +367,8 @@ __global__ void __launch_bounds__(C_THREADS, 1) chol_update_kernel(int n, int ld
     const int r = ri + wm * 32 + i * 8 + g;
     if (r >= n) continue;
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const int col = rj + wn * 16 + j * 8 + 2 * q;
+    for (int j = 0; j < NJ; ++j) {
+      const int col = rj + wn * (8 * NJ) + j * 8 + 2 * q;
       if (col > r) continue;                         // lower triangle only (col <= r < n)
       double* p = A + (size_t)r * lda + col;
       if (col + 1 <= r) {
@@ -372,8 +425,10 @@ int chol_set_attrs() {
   if (done) return VGG_OK;
   VGG_CUDA_CHECK(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(sizeof(double) * (CB + C_RPC) * CLD)));
-  VGG_CUDA_CHECK(cudaFuncSetAttribute(chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  VGG_CUDA_CHECK(cudaFuncSetAttribute(chol_update_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(sizeof(double) * 2 * CT * CLD)));
+  VGG_CUDA_CHECK(cudaFuncSetAttribute(chol_update_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(sizeof(double) * (32 + CT) * CLD)));
   done = true;
   return VGG_OK;
 }
@@ -396,22 +451,23 @@ int chol_enqueue(int n, int lda, double* A, double* Ldiag, int* info, cudaStream
   for (int b = 0; b + 1 < nblk; ++b) {
     const int k0 = b * CB, t0 = k0 + CB;
     const int T = (n - t0 + CT - 1) / CT;
-    const int n_col = T >= 2 ? 2 * T - 1 : 1;
+    const int T32 = (n - t0 + 31) / 32;
+    const int n_col = T32 + (T32 > 2 ? T32 - 2 : 0);       // 32-row tiles of tile columns 0 and 1
     const int n_rest = T > 2 ? (T - 2) * (T - 1) / 2 : 0;
     if (!lookahead) {
-      chol_update_kernel<<<T * (T + 1) / 2, C_THREADS, smem_u, st>>>(n, lda, k0, t0, 0, A);
+      chol_update_kernel<64><<<T * (T + 1) / 2, C_THREADS, smem_u, st>>>(n, lda, k0, t0, 0, A);
       VGG_LAUNCH_CHECK();
       if ((rc = panel(b + 1, st))) return rc;
       continue;
     }
-    chol_update_kernel<<<n_col, C_THREADS, smem_u, st>>>(n, lda, k0, t0, 1, A);
+    chol_update_kernel<32><<<n_col, C_THREADS, sizeof(double) * (32 + CT) * CLD, st>>>(n, lda, k0, t0, 1, A);
     VGG_LAUNCH_CHECK();
     VGG_CUDA_CHECK(cudaEventRecord(cs->ev_col, st));
     VGG_CUDA_CHECK(cudaStreamWaitEvent(cs->side, cs->ev_col, 0));
     if ((rc = panel(b + 1, cs->side))) return rc;
     VGG_CUDA_CHECK(cudaEventRecord(cs->ev_panel, cs->side));
     if (n_rest > 0) {
-      chol_update_kernel<<<n_rest, C_THREADS, smem_u, st>>>(n, lda, k0, t0, 2, A);
+      chol_update_kernel<64><<<n_rest, C_THREADS, smem_u, st>>>(n, lda, k0, t0, 2, A);
       VGG_LAUNCH_CHECK();
     }
     VGG_CUDA_CHECK(cudaStreamWaitEvent(st, cs->ev_panel, 0));
