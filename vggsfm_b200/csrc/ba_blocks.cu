@@ -188,12 +188,14 @@ __global__ void __launch_bounds__(BT, MINB) ba_blocks_kernel(
   const int D = S * DC + NS;
   const size_t pitch = w_pitch(D);
   // work item of this warp: frame group g (32 frames), track range [t_begin, t_end)
-  // The BW warps of a CTA share ONE frame group and take BW consecutive track chunks, so their camera records can be
-  // summed in shared memory and flushed with one set of REDs per CTA (r01: one set per warp; at 400 x 4096 that was
-  // 1.4 M f64 REDs on 15.6 K addresses, a tenth of the launch).
+  // Consecutive warps take consecutive FRAME GROUPS of the same track chunk: the 13 groups of a chunk then write the 13
+  // adjacent segments of the same tracks' W rows (57 KB contiguous per track) at about the same time, which keeps the
+  // DRAM pages open.  (r02 A/B: giving a CTA's warps one frame group and four chunks instead -- to merge their camera
+  // flushes -- cost 19 % at 400 x 131072: 4380 -> 3554 GB/s.)
   const int ngroups = (S + 31) / 32;
-  const int g = blockIdx.x % ngroups;
-  const int chunk = (blockIdx.x / ngroups) * BW + warp;
+  const int wid = blockIdx.x * BW + warp;
+  const int g = wid % ngroups;
+  const int chunk = wid / ngroups;
   const int t_begin = (int)min((long long)N, (long long)chunk * tracks_per_warp);
   const int t_end = min(N, t_begin + tracks_per_warp);
   const int s = g * 32 + lane;
@@ -351,21 +353,11 @@ __global__ void __launch_bounds__(BT, MINB) ba_blocks_kernel(
   }
   if (USE_TMA && lane == 0) tma_store_wait_all<0>();
 
-  // flush the camera records: the CTA's warps (same 32 frames, different tracks) meet in shared memory -- every
-  // staging buffer is free now -- and each (frame, entry) pair is committed with ONE RED per CTA
-  __syncthreads();
-  {
-    double* flat = reinterpret_cast<double*>(smem_raw);            // [BW][KR][32]
+  // flush this lane's camera record
+  if (frame_ok && t_begin < t_end) {
 #pragma unroll
-    for (int i = 0; i < KR; ++i) flat[((size_t)warp * KR + i) * 32 + lane] = acc[i];
-    __syncthreads();
-    for (int e = tid; e < KR * 32; e += BT) {
-      double v = 0.0;
-#pragma unroll
-      for (int w = 0; w < BW; ++w) v += flat[(size_t)w * KR * 32 + e];
-      const int fl = e & 31, i = e >> 5;
-      if (v != 0.0 && g * 32 + fl < S) atomicAdd(&camrec[(size_t)(g * 32 + fl) * KR + i], v);
-    }
+    for (int i = 0; i < KR; ++i)
+      if (acc[i] != 0.0) atomicAdd(&camrec[(size_t)s * KR + i], acc[i]);
   }
   // scalars: cost, g_s, H_ss
   {
@@ -417,7 +409,8 @@ static int launch_blocks(const vgg_ba_problem* p, double* cost, double* camrec, 
     tracks_per_warp = (int)best_tpw;
   }
   const int chunks = (N + tracks_per_warp - 1) / tracks_per_warp;
-  const unsigned grid = (unsigned)(((chunks + BW - 1) / BW) * ngroups);     // CTA = (frame group, BW consecutive chunks)
+  const long nwarps = (long)chunks * ngroups;
+  const unsigned grid = (unsigned)((nwarps + BW - 1) / BW);
   if (!outputs_zeroed) {
     // the five accumulators: ONE memset when the caller carved them back to back in the order of csrc/ba_solve.cu's
     // workspace (cost | shared | camrec | g_p | H_pp, gaps < 256 B) -- vggsfm_b200.bundle_adjustment.build_blocks does

@@ -43,45 +43,94 @@ __device__ __forceinline__ void chol_dmma(double& d0, double& d1, double a, doub
 //     REST OF THE SUB-PANEL only (<= 24 columns), two threads per row;
 //   * after each sub-panel ONE rank-32 update of everything to its right with mma.sync.m8n8k4.f64 (DMMA), 32x16 warp
 //     tiles straight from the row-major block (row stride 132: conflict-free fragments).
+// 1/sqrt(p) for p > 0: float seed + two Newton steps in double (full double accuracy from the 22-bit seed: 22 -> 44 ->
+// 88 bits); ~100 cycles of latency instead of ~150 for rsqrt(double) -- this sits on the 128-deep pivot chain of every panel.
+__device__ __forceinline__ double fast_rsqrt(double p) {
+  double r = (double)rsqrtf((float)p);
+  const double hp = 0.5 * p;
+  r = r * fma(-hp * r, r, 1.5);
+  r = r * fma(-hp * r, r, 1.5);
+  return r;
+}
+
 __device__ __forceinline__ int cta_chol128(double* Ls, double* dinv, int* fail_sm, int tid) {
   const int lane = tid & 31, warp = tid >> 5;
   if (tid == 0) *fail_sm = 0;
+  __syncthreads();
+  // 8x8 leaf by warp 0: one row per lane (lanes 8..31 mirror lanes 0..7), pivot column through shuffles
+  auto leaf = [&](int c0) {
+    double a[8];
+    const int r = c0 + (lane & 7);
+#pragma unroll
+    for (int c = 0; c < 8; c += 2) {
+      const double2 v = *reinterpret_cast<const double2*>(Ls + r * CLD + c0 + c);
+      a[c] = v.x;
+      a[c + 1] = v.y;
+    }
+    int fail = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const double pj = __shfl_sync(0xffffffffu, a[j], j);
+      if (!(pj > 0.0) && fail == 0) fail = c0 + j + 1;
+      const double inv = fast_rsqrt(pj > 0.0 ? pj : 1.0);
+      a[j] = (lane == j) ? pj * inv : a[j] * inv;
+      if (lane == j) dinv[c0 + j] = inv;
+#pragma unroll
+      for (int c = j + 1; c < 8; ++c) {
+        const double lc = __shfl_sync(0xffffffffu, a[j], c);
+        if (lane >= c) a[c] = fma(-a[j], lc, a[c]);
+      }
+    }
+    if (lane < 8) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) Ls[r * CLD + c0 + c] = (c <= lane) ? a[c] : 0.0;
+    }
+    if (lane == 0 && fail && *fail_sm == 0) *fail_sm = fail;
+  };
+  // C[r][j] -= sum_k L[r][c0+k] L[j][c0+k] for j = jb, jb+js, ... <= jend (two columns in flight)
+  auto row_update = [&](int r, int c0, int jb, int js, int jend) {
+    double li[8];
+#pragma unroll
+    for (int k = 0; k < 8; k += 2) {
+      const double2 v = *reinterpret_cast<const double2*>(Ls + r * CLD + c0 + k);
+      li[k] = v.x;
+      li[k + 1] = v.y;
+    }
+    int j = jb;
+    for (; j + js <= jend; j += 2 * js) {
+      const double* l0 = Ls + j * CLD + c0;
+      const double* l1 = Ls + (j + js) * CLD + c0;
+      double s0 = Ls[r * CLD + j], s1 = Ls[r * CLD + j + js];
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) {
+        const double2 u = *reinterpret_cast<const double2*>(l0 + k);
+        const double2 w = *reinterpret_cast<const double2*>(l1 + k);
+        s0 = fma(-li[k], u.x, s0);
+        s1 = fma(-li[k], w.x, s1);
+        s0 = fma(-li[k + 1], u.y, s0);
+        s1 = fma(-li[k + 1], w.y, s1);
+      }
+      Ls[r * CLD + j] = s0;
+      Ls[r * CLD + j + js] = s1;
+    }
+    if (j <= jend) {
+      const double* l0 = Ls + j * CLD + c0;
+      double s0 = Ls[r * CLD + j];
+#pragma unroll
+      for (int k = 0; k < 8; k += 2) {
+        const double2 u = *reinterpret_cast<const double2*>(l0 + k);
+        s0 = fma(-li[k], u.x, s0);
+        s0 = fma(-li[k + 1], u.y, s0);
+      }
+      Ls[r * CLD + j] = s0;
+    }
+  };
+  if (warp == 0) leaf(0);
   __syncthreads();
   for (int sp = 0; sp < CB / 32; ++sp) {
     const int c32 = sp * 32;
     for (int mp = 0; mp < 4; ++mp) {
       const int c0 = c32 + mp * 8;
-      if (warp == 0) {
-        // (a) 8x8 leaf: one row per lane (lanes 8..31 mirror lanes 0..7), pivot column through shuffles
-        double a[8];
-        const int r = c0 + (lane & 7);
-#pragma unroll
-        for (int c = 0; c < 8; c += 2) {
-          const double2 v = *reinterpret_cast<const double2*>(Ls + r * CLD + c0 + c);
-          a[c] = v.x;
-          a[c + 1] = v.y;
-        }
-        int fail = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const double pj = __shfl_sync(0xffffffffu, a[j], j);
-          if (!(pj > 0.0) && fail == 0) fail = c0 + j + 1;
-          const double inv = rsqrt(pj > 0.0 ? pj : 1.0);
-          a[j] = (lane == j) ? pj * inv : a[j] * inv;
-          if (lane == j) dinv[c0 + j] = inv;
-#pragma unroll
-          for (int c = j + 1; c < 8; ++c) {
-            const double lc = __shfl_sync(0xffffffffu, a[j], c);
-            if (lane >= c) a[c] = fma(-a[j], lc, a[c]);
-          }
-        }
-        if (lane < 8) {
-#pragma unroll
-          for (int c = 0; c < 8; ++c) Ls[r * CLD + c0 + c] = (c <= lane) ? a[c] : 0.0;
-        }
-        if (lane == 0 && fail && *fail_sm == 0) *fail_sm = fail;
-      }
-      __syncthreads();
       // (b) rows below the micro-block: x L^T = a, one thread per row
       {
         const int r = c0 + 8 + tid;
@@ -104,29 +153,24 @@ __device__ __forceinline__ int cta_chol128(double* Ls, double* dinv, int* fail_s
         }
       }
       __syncthreads();
-      // (c) rank-8 update of the remaining columns of THIS sub-panel (c0+8 .. c32+31), all rows below; two threads
-      //     per row, each takes every second column
+      // (c) rank-8 update of the remaining columns of THIS sub-panel (c0+8 .. c32+31), all rows below -- with one
+      //     micro-panel of lookahead: warp 0 first finishes the next 8x8 diagonal block and factors it (the pivot chain,
+      //     ~1.3k cycles) while warps 1..7 update everything else (two threads per row, alternate columns)
       if (mp < 3) {
-        const int r = c0 + 8 + (tid >> 1), half = tid & 1;
-        if (r < CB) {
-          double li[8];
-#pragma unroll
-          for (int k = 0; k < 8; k += 2) {
-            const double2 v = *reinterpret_cast<const double2*>(Ls + r * CLD + c0 + k);
-            li[k] = v.x;
-            li[k + 1] = v.y;
-          }
-          const int jend = min(r, c32 + 31);
-          for (int j = c0 + 8 + half; j <= jend; j += 2) {
-            const double* lj = Ls + j * CLD + c0;
-            double sacc = Ls[r * CLD + j];
-#pragma unroll
-            for (int k = 0; k < 8; k += 2) {
-              const double2 v = *reinterpret_cast<const double2*>(lj + k);
-              sacc = fma(-li[k], v.x, sacc);
-              sacc = fma(-li[k + 1], v.y, sacc);
-            }
-            Ls[r * CLD + j] = sacc;
+        const int n0 = c0 + 8;                                   // first row/column of the next micro-panel
+        if (warp == 0) {
+          if (lane < 8) row_update(n0 + lane, c0, n0, 1, n0 + lane);      // the next leaf's lower triangle
+          __syncwarp();
+          leaf(n0);
+        } else {
+          const int t = tid - 32;                                 // 224 threads: row = n0 + t/2 (skipping nothing), half
+          for (int rr = t >> 1; n0 + rr < CB; rr += 112) {
+            const int r = n0 + rr, half = t & 1;
+            const int jend = min(r, c32 + 31);
+            // rows of the next leaf block (r < n0+8) own only columns right of it?  no: their columns <= r all lie inside
+            // the leaf block, which warp 0 handles; other rows skip nothing
+            if (r < n0 + 8) continue;
+            row_update(r, c0, n0 + half, 2, jend);
           }
         }
         __syncthreads();
@@ -180,6 +224,9 @@ __device__ __forceinline__ int cta_chol128(double* Ls, double* dinv, int* fail_s
           }
         }
       }
+      __syncthreads();
+      // first leaf of the next sub-panel (its block is now complete)
+      if (warp == 0) leaf(t0);
       __syncthreads();
     }
   }
