@@ -20,11 +20,12 @@ namespace vgg {
 template <typename TOUT>
 __global__ void nchw_to_nhwc_kernel(int C, int H, int W, const float* __restrict__ in, float* __restrict__ out32,
                                     TOUT* __restrict__ outT) {
-  // grid: (ceil(HW/32), ceil(C/32), images); block (32, 8)
+  // grid: (ceil(HW/32) * images, ceil(C/32)); block (32, 8)   (images in x: the fine tracker has 131 072 of them)
   __shared__ float tile[32][33];
-  const size_t img = blockIdx.z;
   const int HW = H * W;
-  const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int tiles_hw = (HW + 31) / 32;
+  const size_t img = blockIdx.x / tiles_hw;
+  const int p0 = (int)(blockIdx.x % tiles_hw) * 32, c0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += 8) {
     const int c = c0 + j, p = p0 + threadIdx.x;
     tile[j][threadIdx.x] = (c < C && p < HW) ? in[(img * C + c) * HW + p] : 0.f;
@@ -282,7 +283,7 @@ int vgg_corr_build_pyramid(int BS, int C, int H, int W, int num_levels, const fl
     const size_t n = (size_t)BS * h * w * C;
     float* cur32 = (elem_size == 4) ? reinterpret_cast<float*>(pT) : reinterpret_cast<float*>(p32);
     if (l == 0) {
-      dim3 grid((h * w + 31) / 32, (C + 31) / 32, BS), block(32, 8);
+      dim3 grid((unsigned)((size_t)((h * w + 31) / 32) * BS), (C + 31) / 32), block(32, 8);
       if (elem_size == 4) nchw_to_nhwc_kernel<float><<<grid, block, 0, st>>>(C, h, w, fmaps_nchw, cur32, nullptr);
       else nchw_to_nhwc_kernel<__half><<<grid, block, 0, st>>>(C, h, w, fmaps_nchw, cur32, reinterpret_cast<__half*>(pT));
     } else {
