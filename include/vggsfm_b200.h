@@ -275,6 +275,18 @@ int vgg_corr_build_pyramid(int BS, int C, int H, int W, int num_levels, const fl
 int vgg_corr_sample(int BS, int N, int C, int H, int W, int num_levels, int radius, const void* pyramid, int elem_size,
                     const float* targets, const float* coords, int border_padding, float* out, void* stream);
 
+/* The same CorrBlock.corr + CorrBlock.sample for the coarse tracker's C = 128 maps ON THE TENSOR CORES
+ * (csrc/corr_tc.cu: tcgen05.mma kind::f16 M=128 x N=256 x K=128 into TMEM, footprint extraction from TMEM in the
+ * epilogue; the dense fp16 product of blocks.py:413 without ever storing the volume).  Zero padding only; map width a
+ * power of two.  vgg_corr_tc_build turns the HALF channels-last pyramid of vgg_corr_build_pyramid into operand tile
+ * images once per CorrBlock (tile_bytes from vgg_corr_tc_bytes); vgg_corr_tc_sample needs `target_bytes` of scratch for
+ * the fp16 target tiles of the call.  Same targets / coords / out layout as vgg_corr_sample. */
+int vgg_corr_tc_supported(int C, int H, int W, int num_levels, int radius);
+int vgg_corr_tc_bytes(int BS, int C, int H, int W, int num_levels, int N, size_t* tile_bytes, size_t* target_bytes);
+int vgg_corr_tc_build(int BS, int C, int H, int W, int num_levels, const void* pyramid_half, void* tiles, void* stream);
+int vgg_corr_tc_sample(int BS, int N, int C, int H, int W, int num_levels, int radius, const void* tiles, const float* targets,
+                       const float* coords, void* target_tiles, float* out, void* stream);
+
 /* sample_features4d (vggsfm/models/utils.py:415-447; colour read-back at models/triangulator.py:324, query
  * features in the tracker): bilinear sampling, align_corners=True, border padding.  input float [B,C,H,W],
  * coords float [B,R,2] (x,y) pixels, out float [B,R,C]. */

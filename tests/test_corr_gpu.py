@@ -69,3 +69,31 @@ def test_c4_shape_linearity(cuda_dev):
     cb.corr(t1)
     far = cb.sample(torch.full_like(c, -1000.0))
     assert far.abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("H,W,N,L,r", [(32, 32, 130, 3, 4), (24, 64, 256, 4, 3), (128, 128, 128, 5, 4)])
+def test_tensor_core_path_matches_cuda_core_path(cuda_dev, H, W, N, L, r):
+    """csrc/corr_tc.cu (tcgen05 kind::f16, footprint extraction from TMEM) against csrc/corr.cu on the same half
+    pyramid: both round targets and features to fp16 and accumulate in fp32, only the summation order differs (1e-3 of
+    the value range); queries on, near and beyond the border, a ragged last 128-query tile, non-square maps."""
+    import torch
+    from vggsfm_b200.corr import CorrBlock
+    g = torch.Generator(device=cuda_dev).manual_seed(H + N)
+    B, S, C = 1, 3, 128
+    fm = torch.randn(B, S, C, H, W, device=cuda_dev, generator=g)
+    tg = torch.randn(B, S, N, C, device=cuda_dev, generator=g)
+    co = torch.rand(B, S, N, 2, device=cuda_dev, generator=g) * torch.tensor([W + 10.0, H + 10.0], device=cuda_dev) - 5.0
+    co[0, 0, 0] = torch.tensor([0.0, 0.0], device=cuda_dev)
+    co[0, 0, 1] = torch.tensor([W - 1.0, H - 1.0], device=cuda_dev)
+    co[0, 1, 2] = torch.tensor([3.5, 7.25], device=cuda_dev)
+    a = CorrBlock(fm, num_levels=L, radius=r, half=True, tc=True)
+    assert a._pyr.tc_tiles is not None
+    b = CorrBlock(fm, num_levels=L, radius=r, half=True, tc=False)
+    assert b._pyr.tc_tiles is None
+    a.corr(tg)
+    b.corr(tg)
+    ya, yb = a.sample(co), b.sample(co)
+    torch.cuda.synchronize()
+    scale = yb.abs().max().item()
+    assert scale > 1.0
+    assert (ya - yb).abs().max().item() <= 1e-3 * scale, (ya - yb).abs().max().item() / scale

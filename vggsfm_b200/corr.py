@@ -17,7 +17,7 @@ def _stream(dev):
 
 
 class _Pyramid:
-    def __init__(self, fmaps, num_levels, radius, half=None):
+    def __init__(self, fmaps, num_levels, radius, half=None, tc=None):
         if not fmaps.is_cuda:
             raise RuntimeError("vggsfm_b200.CorrBlock needs CUDA tensors (no CPU fallback)")
         B, S, C, H, W = fmaps.shape
@@ -40,6 +40,19 @@ class _Pyramid:
                                                 scratch.data_ptr() if sb.value else None, _stream(dev)),
                        "vgg_corr_build_pyramid")
         self.dev = dev
+        # coarse tracker (C = 128, power-of-two maps, half pyramid): operand tile images for the tcgen05 kernel
+        # (csrc/corr_tc.cu); VGG_CORR_TC=0 keeps the CUDA-core footprint kernel for A/B
+        import os
+        self.tc_tiles = None
+        want_tc = (os.environ.get("VGG_CORR_TC", "1") != "0") if tc is None else bool(tc)
+        if self.elem == 2 and want_tc and L.vgg_corr_tc_supported(C, H, W, num_levels, radius):
+            tb = ctypes.c_size_t()
+            _lib.check(L.vgg_corr_tc_bytes(B * S, C, H, W, num_levels, 0, ctypes.byref(tb), None), "vgg_corr_tc_bytes")
+            self.tc_tiles = torch.empty(tb.value, dtype=torch.uint8, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(L.vgg_corr_tc_build(B * S, C, H, W, num_levels, self.pyr.data_ptr(), self.tc_tiles.data_ptr(),
+                                               _stream(dev)), "vgg_corr_tc_build")
+        self._tc_scratch = None
 
     def sample(self, coords, targets, border):
         B, S, N, D = coords.shape
@@ -51,6 +64,18 @@ class _Pyramid:
         out = torch.empty(B, S, N, self.num_levels * K * K, dtype=torch.float32, device=self.dev)
         tg = targets.float().contiguous()
         co = coords.float().contiguous()
+        if self.tc_tiles is not None and not border:
+            L = _lib.lib()
+            ab = ctypes.c_size_t()
+            _lib.check(L.vgg_corr_tc_bytes(B * S, self.C, self.H, self.W, self.num_levels, N, None, ctypes.byref(ab)),
+                       "vgg_corr_tc_bytes")
+            if self._tc_scratch is None or self._tc_scratch.numel() < ab.value:
+                self._tc_scratch = torch.empty(ab.value, dtype=torch.uint8, device=self.dev)
+            with torch.cuda.device(self.dev):
+                _lib.check(L.vgg_corr_tc_sample(B * S, N, self.C, self.H, self.W, self.num_levels, r, self.tc_tiles.data_ptr(),
+                                                tg.data_ptr(), co.data_ptr(), self._tc_scratch.data_ptr(), out.data_ptr(),
+                                                _stream(self.dev)), "vgg_corr_tc_sample")
+            return out
         with torch.cuda.device(self.dev):
             _lib.check(_lib.lib().vgg_corr_sample(B * S, N, self.C, self.H, self.W, self.num_levels, r, self.pyr.data_ptr(),
                                                   self.elem, tg.data_ptr(), co.data_ptr(), 1 if border else 0,
@@ -61,7 +86,7 @@ class _Pyramid:
 class CorrBlock:
     """blocks.py:338-416.  corr(targets) records the targets; sample(coords) runs the fused kernel."""
 
-    def __init__(self, fmaps, num_levels=4, radius=4, multiple_track_feats=False, padding_mode="zeros", half=None):
+    def __init__(self, fmaps, num_levels=4, radius=4, multiple_track_feats=False, padding_mode="zeros", half=None, tc=None):
         if multiple_track_feats:
             raise NotImplementedError("multiple_track_feats=True is not used by the reference configs")
         if padding_mode not in ("zeros", "border"):
@@ -70,7 +95,7 @@ class CorrBlock:
         self.num_levels, self.radius = num_levels, radius
         B, S, C, H, W = fmaps.shape
         self.S, self.C, self.H, self.W = S, C, H, W
-        self._pyr = _Pyramid(fmaps, num_levels, radius, half)
+        self._pyr = _Pyramid(fmaps, num_levels, radius, half, tc if padding_mode == "zeros" else False)
         self._targets = None
 
     def corr(self, targets):
