@@ -248,31 +248,27 @@ __global__ void __launch_bounds__(C_THREADS, 1) chol_panel_kernel(int n, int lda
   const int nb = min(CB, n - k0);
   const bool solver = blockIdx.x > 0;
   const int r0 = k0 + CB + ((int)blockIdx.x - 1) * C_RPC;
-  // diagonal block: lower part, identity padding beyond nb (entries above the diagonal are never read)
+  // diagonal block (rows < nb: whole 128-double rows, the part above the diagonal is never read; identity padding
+  // beyond nb) and this CTA's 16 panel rows: cp.async, all 16-byte chunks in flight at once (r02: the plain
+  // load -> store loop serialised 32 L2 round trips per thread, a third of the kernel)
   for (int e = tid; e < CB * (CB / 2); e += C_THREADS) {
     const int i = e >> 6, j = (e & 63) * 2;
-    double2 v = make_double2(0.0, 0.0);
-    if (i < nb && j <= i) {
-      v = *reinterpret_cast<const double2*>(A + (size_t)(k0 + i) * lda + k0 + j);
-      if (j + 1 > i) v.y = 0.0;
+    if (i < nb) {
+      cp_async16(Ls + i * CLD + j, A + (size_t)(k0 + i) * lda + k0 + j);
+    } else {
+      *reinterpret_cast<double2*>(Ls + i * CLD + j) = make_double2(j == i ? 1.0 : 0.0, j + 1 == i ? 1.0 : 0.0);
     }
-    if (i >= nb) {
-      if (j == i) v.x = 1.0;
-      if (j + 1 == i) v.y = 1.0;
-    }
-    *reinterpret_cast<double2*>(Ls + i * CLD + j) = v;
   }
   if (solver) {
     for (int e = tid; e < C_RPC * (CB / 2); e += C_THREADS) {
       const int r = e >> 6, j = (e & 63) * 2;
-      double2 v = make_double2(0.0, 0.0);
-      if (r0 + r < n && j < nb) {
-        v = *reinterpret_cast<const double2*>(A + (size_t)(r0 + r) * lda + k0 + j);
-        if (j + 1 >= nb) v.y = 0.0;
-      }
-      *reinterpret_cast<double2*>(Ts + r * CLD + j) = v;
+      if (r0 + r < n) cp_async16(Ts + r * CLD + j, A + (size_t)(r0 + r) * lda + k0 + j);
+      else *reinterpret_cast<double2*>(Ts + r * CLD + j) = make_double2(0.0, 0.0);
     }
   }
+  cp_async_commit();
+  cp_async_wait<0>();
+  __syncthreads();
   const int fail = cta_chol128(Ls, dinv, &fail_sm, tid);
   if (fail && blockIdx.x == 0 && tid == 0) atomicCAS(info, 0, k0 + fail);
   // mirror: Ls[m][j] = L[j][m] for j > m (the solve below reads column m of L as a contiguous row; CTA 0 stores it as L^T)

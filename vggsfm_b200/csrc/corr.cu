@@ -120,25 +120,27 @@ __global__ void __launch_bounds__(256) corr_sample_kernel(int BS, int N, int L, 
     const float cx = cx0 * scale, cy = cy0 * scale;
     const float fxf = floorf(cx), fyf = floorf(cy);
     const int fx = (int)fxf, fy = (int)fyf;
+    // Every footprint position is loaded UNCONDITIONALLY from a clamped address and masked afterwards: the loads of a
+    // level are then independent straight-line code the compiler issues back to back.  (r02 measurement of the guarded
+    // version, one `if (inside) load` per position: the 64-192 loads of a query serialised on their latency -- 4.2 ms
+    // for the fine tracker's 131 072 patches, 6 % of the HBM roofline.)
     float part[NF];
 #pragma unroll
     for (int iy = 0; iy < FP; ++iy) {
-      int Y = fy - R + iy;
-      bool yin = (Y >= 0 && Y < H);
-      if (border) { Y = min(max(Y, 0), H - 1); yin = true; }
+      const int Y = fy - R + iy;
+      const bool yin = border || (Y >= 0 && Y < H);
+      const int Yc = min(max(Y, 0), H - 1);
 #pragma unroll
       for (int ix = 0; ix < FP; ++ix) {
-        int X = fx - R + ix;
-        bool xin = (X >= 0 && X < W);
-        if (border) { X = min(max(X, 0), W - 1); xin = true; }
+        const int X = fx - R + ix;
+        const bool xin = border || (X >= 0 && X < W);
+        const int Xc = min(max(X, 0), W - 1);
+        float f[CPL];
+        VecLoad<T>::template load<CPL>(fm + ((size_t)Yc * W + Xc) * C + lane * CPL, f);
         float acc = 0.f;
-        if (yin && xin) {
-          float f[CPL];
-          VecLoad<T>::template load<CPL>(fm + ((size_t)Y * W + X) * C + lane * CPL, f);
 #pragma unroll
-          for (int i = 0; i < CPL; ++i) acc = fmaf(tg[i], f[i], acc);
-        }
-        part[iy * FP + ix] = acc;
+        for (int i = 0; i < CPL; ++i) acc = fmaf(tg[i], f[i], acc);
+        part[iy * FP + ix] = (yin && xin) ? acc : 0.f;
       }
     }
     // warp reduce-scatter in groups of 32 footprint positions
