@@ -119,3 +119,120 @@ def joint_BA(points3D, extrinsics, intrinsics, extra_params, tracks, masks, came
     if normalize:
         extr, out = ba.normalize(extr, out, 5.0, 0.1, 0.9, valid_points)                 # :513-514
     return out, extr, K_o[:1].clone(), (ex_o[:1].clone() if ex_o is not None else None), new_masks, valid_points
+
+
+class SceneStore:
+    """GPU-resident scene tables of the sliding-window pipeline -- what ``VideoRunner`` keeps in ``point_dict`` /
+    ``frame_dict`` (vggsfm/runners/video_runner.py:354-492, :543-638) and walks with O(points x frames) Python loops
+    before and after every bundle adjustment.
+
+    Points: ``xyz [P,3] float32`` (the runner stores ``.float()``, :620), ``rgb [P,3]``; point ids are row numbers, new
+    points are appended (``exist_max_point + index``, :395-399).  Observations: coordinate list ``(obs_point, obs_frame,
+    obs_uv, obs_vis)``.  Frames: ``extri [F,3,4] float64``.  ``dense(start, end)`` unrolls the tables into the [S,P]
+    grid the BA kernels take (the tensor form of ``dicts_to_reconstruction``, :543-604); ``replace_from_ba`` is
+    ``reconstruction_to_dicts`` (:606-638: surviving points renumbered 0..P'-1 in id order, visibilities reset to 1)."""
+
+    def __init__(self, device):
+        self.device = device
+        self.xyz = torch.zeros(0, 3, dtype=torch.float32, device=device)
+        self.rgb = torch.zeros(0, 3, dtype=torch.float32, device=device)
+        self.obs_point = torch.zeros(0, dtype=torch.int64, device=device)
+        self.obs_frame = torch.zeros(0, dtype=torch.int64, device=device)
+        self.obs_uv = torch.zeros(0, 2, dtype=torch.float32, device=device)
+        self.obs_vis = torch.zeros(0, dtype=torch.float32, device=device)
+        self.extri = torch.zeros(0, 3, 4, dtype=torch.float64, device=device)
+        self.has_extri = torch.zeros(0, dtype=torch.bool, device=device)
+
+    @property
+    def num_points(self):
+        return int(self.xyz.shape[0])
+
+    def set_extrinsics(self, start_idx, extrinsics):
+        end = start_idx + extrinsics.shape[0]
+        if end > self.extri.shape[0]:
+            grow = end - self.extri.shape[0]
+            self.extri = torch.cat([self.extri, torch.zeros(grow, 3, 4, dtype=torch.float64, device=self.device)])
+            self.has_extri = torch.cat([self.has_extri, torch.zeros(grow, dtype=torch.bool, device=self.device)])
+        self.extri[start_idx:end] = extrinsics.to(torch.float64)
+        self.has_extri[start_idx:end] = True
+
+    def _append_obs(self, point_ids, tracks, vis, valid, start_idx):
+        """tracks [S,P,2], vis/valid [S,P] for the points `point_ids` [P] in frames start_idx.."""
+        s_idx, p_idx = torch.nonzero(valid, as_tuple=True)
+        self.obs_point = torch.cat([self.obs_point, point_ids[p_idx]])
+        self.obs_frame = torch.cat([self.obs_frame, s_idx + start_idx])
+        self.obs_uv = torch.cat([self.obs_uv, tracks[s_idx, p_idx].float()])
+        self.obs_vis = torch.cat([self.obs_vis, vis[s_idx, p_idx].float()])
+
+    def add_points(self, points3D, points3D_rgb, tracks, vis, valid_2D_mask, start_idx):
+        """New points of a window (convert_pred_to_point_frame_dict + _update_points_to_dict, :354-470, for points not
+        yet in the store): appended, ids returned."""
+        P = points3D.shape[0]
+        ids = torch.arange(self.num_points, self.num_points + P, device=self.device)
+        self.xyz = torch.cat([self.xyz, points3D.float()])
+        rgb = points3D_rgb.float() if points3D_rgb is not None else torch.full((P, 3), float("nan"), device=self.device)
+        self.rgb = torch.cat([self.rgb, rgb])
+        self._append_obs(ids, tracks, vis, valid_2D_mask.bool(), start_idx)
+        return ids
+
+    def extend_tracks(self, point_ids, tracks, vis, valid_2D_mask, start_idx):
+        """Observations of EXISTING points in new frames (_update_points_to_dict with ids already in the dict)."""
+        self._append_obs(point_ids, tracks, vis, valid_2D_mask.bool(), start_idx)
+
+    def visible_points(self, frame_idx):
+        """frame_dict[frame]["visible_points"], ascending ids."""
+        return torch.sort(self.obs_point[self.obs_frame == frame_idx]).values
+
+    def dense(self, start_idx, end_idx):
+        """All points x frames [start, end): (xyz [P,3] f64, tracks [S,P,2] f32, masks [S,P] bool, extrinsics [S,3,4])."""
+        S, P = end_idx - start_idx, self.num_points
+        tracks = torch.zeros(S, P, 2, dtype=torch.float32, device=self.device)
+        masks = torch.zeros(S, P, dtype=torch.bool, device=self.device)
+        sel = (self.obs_frame >= start_idx) & (self.obs_frame < end_idx)
+        f, p = self.obs_frame[sel] - start_idx, self.obs_point[sel]
+        tracks[f, p] = self.obs_uv[sel]
+        masks[f, p] = True
+        return self.xyz.double(), tracks, masks, self.extri[start_idx:end_idx].clone()
+
+    def replace_from_ba(self, start_idx, points3D, extrinsics, tracks, masks, keep):
+        """reconstruction_to_dicts after a normalising joint BA (:532-536, :606-638): the store is rebuilt from the BA's
+        result -- points `keep` [P] bool survive and are renumbered in id order, their observations are the surviving
+        `masks` [S,P] of frames start_idx.., visibilities become 1, xyz is stored as float32."""
+        new_id = torch.cumsum(keep.long(), 0) - 1
+        self.xyz = points3D[keep].float()
+        self.rgb = self.rgb[keep]
+        m = masks & keep[None]
+        s_idx, p_idx = torch.nonzero(m, as_tuple=True)
+        self.obs_point = new_id[p_idx]
+        self.obs_frame = s_idx + start_idx
+        self.obs_uv = tracks[s_idx, p_idx].float()
+        self.obs_vis = torch.ones(s_idx.numel(), dtype=torch.float32, device=self.device)
+        self.has_extri[:] = False
+        self.set_extrinsics(start_idx, extrinsics)
+
+    def joint_bundle_adjustment(self, start_idx, end_idx, intrinsics, extra_params, camera_type="SIMPLE_PINHOLE",
+                                reproj_error=2.0, tri_angle=1.5, normalize=True):
+        """VideoRunner.joint_BA (:494-541) on the store: dense view -> joint_BA (CUDA) -> store rebuilt from the result.
+        Returns the refined shared (intrinsics [1,3,3], extra_params [1,1]|None)."""
+        xyz, tracks, masks, extr = self.dense(start_idx, end_idx)
+        pts, extr, K, ex, new_masks, valid = joint_BA(xyz, extr, intrinsics, extra_params, tracks, masks, camera_type=camera_type,
+                                                      reproj_error=reproj_error, tri_angle=tri_angle, normalize=normalize)
+        self.replace_from_ba(start_idx, pts, extr, tracks, new_masks, valid)
+        return K.float(), (ex.float() if ex is not None else None)
+
+
+def triangulate_window_points(extrinsics, intrinsics, extra_params, tracks, vis, score, max_reproj_error=4.0, min_inlier_num=3):
+    """VideoRunner.triangulate_window_points (video_runner.py:1189-1262) on tensors: LORANSAC triangulation of the
+    window's new tracks with the window's (already aligned) cameras, keep tracks with more than ``min_inlier_num`` inliers
+    (:1241 ``inlier_num > 3``-style test is the caller's), then the reprojection / cheirality filter.
+    extrinsics [S,3,4], intrinsics [1,3,3] shared, tracks [S,N,2].  Returns (points3D [N,3], inlier_mask [S,N], valid [N])."""
+    S = extrinsics.shape[0]
+    K = intrinsics.expand(S, -1, -1)
+    ex = extra_params.expand(S, -1) if extra_params is not None else None
+    tn = tri.cam_from_img(tracks, K, ex)
+    pts, num, mask = tri.triangulate_tracks(extrinsics, tn, track_vis=vis, track_score=score)
+    valid = num > min_inlier_num
+    ok, detail = tri.filter_all_points3D(pts, tracks, extrinsics, K, extra_params=ex, max_reproj_error=max_reproj_error,
+                                        return_detail=True, hard_max=-1)
+    valid = valid & ok
+    return pts, detail & valid[None], valid
