@@ -8,7 +8,7 @@
 // product is the right shape for this chip after all, as long as the 5.7 GB volume is never written: here one CTA per
 // SM walks work items (frame, 128 queries); per level and per tile of 256 positions it issues
 // tcgen05.mma M=128 x N=256 x K=128 (8 instructions of K=16) from shared memory into one of two 256-column TMEM
-// accumulators, while four epilogue warps (thread = query = TMEM lane) drain the other one with tcgen05.ld and keep
+// accumulators, while eight epilogue warps (thread = query = TMEM lane, two warps per lane quarter) drain the other one with tcgen05.ld and keep
 // only the (2r+2)^2 footprint values each query needs, in a shared-memory footprint table; after a level's last tile the
 // same warps interpolate the (2r+1)^2 taps and write them.  The correlation volume lives 2 us in TMEM.
 //   operands: K-major, 64-byte swizzle (k-blocks of 32 fp16 channels), stored in global memory as ready-made tile
@@ -31,7 +31,7 @@ constexpr int CT_KB = 4;                  // k-blocks of 32 channels (64 bytes)
 constexpr int CT_A_BYTES = CT_M * CT_C * 2;          // 32 KB
 constexpr int CT_B_BYTES = CT_N * CT_C * 2;          // 64 KB
 constexpr int CT_STAGES = 2;
-constexpr int CT_THREADS = 192;           // warp 0 producer, warp 1 MMA, warps 2..5 epilogue (TMEM quarter = warp & 3)
+constexpr int CT_THREADS = 320;           // warp 0 producer, warp 1 MMA, warps 2..9 epilogue (TMEM quarter = warp & 3, two per quarter)
 constexpr int CT_FB_LD = 101;             // footprint table row stride (floats): 10*10 (+1: conflict-free per-query rows)
 constexpr size_t CT_SMEM = 1024 + CT_A_BYTES + (size_t)CT_STAGES * CT_B_BYTES + (size_t)CT_M * CT_FB_LD * 4 + 256;
 
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1)
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
       mbar_init(&t_full[s], 1);
-      mbar_init(&t_empty[s], 4);
+      mbar_init(&t_empty[s], 8);
     }
     mbar_fence_init();
   }
@@ -222,8 +222,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1)
       }
     }
   } else {
-    // ===== epilogue: thread = query row = TMEM lane (quarter = warp & 3) =====
-    const int quarter = warp & 3;
+    // ===== epilogue: thread = query row = TMEM lane; two warps per lane quarter (quarter = warp & 3), warp `sub` of a
+    //       pair drains the 32-column chunks with (chunk & 1) == sub; the pair meets on a named barrier per level =====
+    const int quarter = warp & 3, sub = (warp - 2) >> 2;
     const int row = quarter * 32 + lane;                       // 0..127
     float* myfb = fb + row * CT_FB_LD;
     const float inv_sqrt_c = rsqrtf((float)CT_C);
@@ -237,19 +238,19 @@ __global__ void __launch_bounds__(CT_THREADS, 1)
         cy0 = coords[((size_t)img * N + n) * 2 + 1];
       }
       for (int l = 0; l < L; ++l) {
-        const int W = lv.W[l], H = lv.H[l], logW = lv.logW[l];
+        const int W = lv.W[l], logW = lv.logW[l];
         const float scale = 1.0f / (float)(1 << l);
         const float cx = cx0 * scale, cy = cy0 * scale;
         const float fxf = floorf(cx), fyf = floorf(cy);
         const int x0 = (int)fxf - R, y0 = (int)fyf - R;        // footprint origin
-        for (int i = 0; i < FP * FP; ++i) myfb[i] = 0.f;
-        __syncwarp();
+        for (int i = sub; i < FP * FP; i += 2) myfb[i] = 0.f;
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");       // table zeroed by both warps of the pair
         for (int t = 0; t < lv.ntiles[l]; ++t, ++tile_no) {
           const uint32_t buf = tile_no & 1u;
           mbar_wait(&t_full[buf], (uint32_t)((tile_no >> 1) & 1u));
           tcf_after();
 #pragma unroll 1
-          for (int ch = 0; ch < CT_N / 32; ++ch) {
+          for (int ch = sub; ch < CT_N / 32; ch += 2) {
             const int p0 = t * CT_N + ch * 32;
             bool need;
             int dy = 0, xc = 0;
@@ -287,10 +288,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1)
           __syncwarp();
           if (lane == 0) mbar_arrive1(&t_empty[buf]);
         }
-        (void)H;
-        // ---- interpolation of the K*K taps: each warp serves its own 32 queries, one query at a time (coalesced stores)
-        __syncwarp();
-        for (int qq = 0; qq < 32; ++qq) {
+        // ---- interpolation of the K*K taps: the pair shares its 32 queries (even / odd), one query at a time so that
+        //      the stores of a query are contiguous
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");       // both halves of every footprint are in
+        for (int qq = sub; qq < 32; qq += 2) {
           const int nq = m * CT_M + quarter * 32 + qq;
           if (nq >= N) break;
           const float qcx = __shfl_sync(0xffffffffu, cx, qq), qcy = __shfl_sync(0xffffffffu, cy, qq);
@@ -303,7 +304,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1)
             orow[o] = d00 * (1.f - wx) * (1.f - wy) + d01 * wx * (1.f - wy) + d10 * (1.f - wx) * wy + d11 * wx * wy;
           }
         }
-        __syncwarp();
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");       // tables are re-zeroed next level
       }
     }
   }
