@@ -390,6 +390,10 @@ static int launch_blocks(const vgg_ba_problem* p, double* cost, double* camrec, 
       int dev = 0, sms = 148, per_sm = minb;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      // the occupancy query needs the opt-in shared-memory limit in place (r02: without it the query returned 0, the
+      // grid was sized for ONE CTA per SM and the 400 x 4096 launch ran as a single wave of 147 CTAs, half the warps)
+      cudaFuncSetAttribute(ba_blocks_kernel<MODEL, MODE, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      cudaFuncSetAttribute(ba_blocks_kernel<MODEL, MODE, true, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (minb == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_blocks_kernel<MODEL, MODE, true, 3>, BT, smem);
       else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ba_blocks_kernel<MODEL, MODE, true, 2>, BT, smem);
       if (per_sm < 1) per_sm = 1;
