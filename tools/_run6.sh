@@ -1,0 +1,13 @@
+set -x
+timeout 300 python -m pytest tests/test_corr_gpu.py tests/test_ba_gpu.py -m gpu -q -k "tensor_core or blocks or c3" > gpurun_out/r02_t6.log 2>&1; tail -4 gpurun_out/r02_t6.log
+timeout 120 python tools/microbench.py blocks 4096 > gpurun_out/r02_blocks_bench.log 2>&1
+timeout 120 python tools/microbench.py blocks 131072 >> gpurun_out/r02_blocks_bench.log 2>&1
+timeout 120 python tools/microbench.py ba >> gpurun_out/r02_blocks_bench.log 2>&1
+cat gpurun_out/r02_blocks_bench.log
+timeout 300 python - > gpurun_out/r02_corr_tc.log 2>&1 <<'PY'
+import sys, json, torch
+sys.path.insert(0, '.')
+import bench
+print(json.dumps(bench.corr_section(torch.device('cuda:0'), 6540.5)))
+PY
+cat gpurun_out/r02_corr_tc.log | cut -c1-1500
