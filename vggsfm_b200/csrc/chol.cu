@@ -57,33 +57,41 @@ __device__ __forceinline__ int cta_chol128(double* Ls, double* dinv, int* fail_s
   const int lane = tid & 31, warp = tid >> 5;
   if (tid == 0) *fail_sm = 0;
   __syncthreads();
-  // 8x8 leaf by warp 0: one row per lane (lanes 8..31 mirror lanes 0..7), pivot column through shuffles
+  // 8x8 leaf by warp 0, shuffle-free: EVERY lane holds the whole lower triangle (36 doubles) and runs the same
+  // straight-line factorisation, so the pivot chain is rsqrt -> one multiply -> one FMA per column with the other
+  // updates in its shadow (r02 source-correlated profile of the one-row-per-lane version: ~300 cycles per pivot, half
+  // of them 64-bit shuffles; 45 % of the panel kernel's warp samples waited on barriers for this chain)
   auto leaf = [&](int c0) {
-    double a[8];
-    const int r = c0 + (lane & 7);
+    double a[36];
 #pragma unroll
-    for (int c = 0; c < 8; c += 2) {
-      const double2 v = *reinterpret_cast<const double2*>(Ls + r * CLD + c0 + c);
-      a[c] = v.x;
-      a[c + 1] = v.y;
-    }
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) a[i * (i + 1) / 2 + j] = Ls[(c0 + i) * CLD + c0 + j];
+    double dv[8];
     int fail = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const double pj = __shfl_sync(0xffffffffu, a[j], j);
+      const double pj = a[j * (j + 1) / 2 + j];
       if (!(pj > 0.0) && fail == 0) fail = c0 + j + 1;
       const double inv = fast_rsqrt(pj > 0.0 ? pj : 1.0);
-      a[j] = (lane == j) ? pj * inv : a[j] * inv;
-      if (lane == j) dinv[c0 + j] = inv;
+      dv[j] = inv;
+      a[j * (j + 1) / 2 + j] = pj * inv;
 #pragma unroll
-      for (int c = j + 1; c < 8; ++c) {
-        const double lc = __shfl_sync(0xffffffffu, a[j], c);
-        if (lane >= c) a[c] = fma(-a[j], lc, a[c]);
-      }
+      for (int i = j + 1; i < 8; ++i) a[i * (i + 1) / 2 + j] *= inv;
+#pragma unroll
+      for (int k = j + 1; k < 8; ++k)
+#pragma unroll
+        for (int i = k; i < 8; ++i)
+          a[i * (i + 1) / 2 + k] = fma(-a[i * (i + 1) / 2 + j], a[k * (k + 1) / 2 + j], a[i * (i + 1) / 2 + k]);
     }
-    if (lane < 8) {
+    // lane l stores row l (zeros above the diagonal) and dinv[l]
 #pragma unroll
-      for (int c = 0; c < 8; ++c) Ls[r * CLD + c0 + c] = (c <= lane) ? a[c] : 0.0;
+    for (int i = 0; i < 8; ++i) {
+      if (lane == i) {
+#pragma unroll
+        for (int c = 0; c < 8; ++c) Ls[(c0 + i) * CLD + c0 + c] = (c <= i) ? a[i * (i + 1) / 2 + c] : 0.0;
+        dinv[c0 + i] = dv[i];
+      }
     }
     if (lane == 0 && fail && *fail_sm == 0) *fail_sm = fail;
   };
