@@ -36,7 +36,7 @@ __device__ __forceinline__ void signal_and_wait(const FabricDev& fd, size_t flag
     const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(fd.peer[fd.rank] + flags_off) + tid;
     unsigned long long v = ld_acquire_sys(mine);
     long spins = 0;
-    while (v < epoch && ++spins < (1L << 27)) v = ld_acquire_sys(mine);      // bounded: a lost peer must not hang the GPU
+    while (v < epoch && ++spins < (1L << 22)) v = ld_acquire_sys(mine);      // bounded (~seconds): a lost peer must not hang the GPU
     if (v < epoch) *err = 1;
   }
 }
