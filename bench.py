@@ -314,6 +314,51 @@ def corr_section(dev, hbm_peak):
     return out
 
 
+def small_problem_section(dev):
+    """LM it/s at the sizes the real pipeline runs most: C1 (8 x 256, SIMPLE_PINHOLE), C2 (50 x 2048,
+    SIMPLE_PINHOLE), and the video runner's window BA (17 frames x 3072 points, first frame and the first 1024 points
+    constant, intrinsics constant; video_runner.py:813-829).  These are launch- and sync-bound, not bandwidth-bound."""
+    import torch
+    from vggsfm_b200 import bundle_adjustment as ba
+    from vggsfm_b200.synthetic import make_scene, perturb
+    out = {}
+    t = lambda a, dt=None: (torch.from_numpy(np.ascontiguousarray(a)).to(dt) if dt else torch.from_numpy(np.ascontiguousarray(a))).to(dev).contiguous()
+    for name, S, N, window in (("C1_8x256", 8, 256, False), ("C2_50x2048", 50, 2048, False), ("window_17x3072", 17, 3072, True)):
+        sc = make_scene(S, N, "SIMPLE_PINHOLE", seed=3, invisible_frac=0.2)
+        extr, K, _, pts = perturb(sc, seed=4)
+        intr = np.zeros((S, 4))
+        intr[:, 0], intr[:, 1], intr[:, 2] = K[:, 0, 0], K[:, 0, 2], K[:, 1, 2]
+        model = ba.SIMPLE_PINHOLE
+        mode = ba.INTR_CONST if window else ba.INTR_PER_FRAME
+        uv, mask = t(sc.tracks, torch.float32), t(sc.mask.astype(np.uint8))
+        p0, i0, x0 = t(extr), t(intr), t(pts)
+        pc = None
+        if window:
+            cp = torch.zeros(S, dtype=torch.bool, device=dev)
+            cp[0] = True
+            param_const = ba.default_param_const(S, model, mode, dev, False, False, gauge=False, const_pose=cp)
+            pc = (torch.arange(N, device=dev) < 1024).to(torch.uint8)
+        else:
+            param_const = ba.default_param_const(S, model, mode, dev)
+        opt = ba.default_options()
+        opt.max_num_iterations = 10
+        opt.gradient_tolerance = 0.0
+        run = lambda: ba.lm_solve(uv, mask, p0.clone(), i0.clone(), x0.clone(), model, mode, param_const, pc, opt)
+        for _ in range(3):
+            s_ = run()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps, its = 10, 0
+        a.record()
+        for _ in range(reps):
+            its += run().iterations
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        out[name] = {"it_per_s": its / (ms * 1e-3), "ms_per_iteration": ms / max(1, its), "launches_per_solve": s_.kernel_launches}
+    return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -474,6 +519,7 @@ def run_gpu(args):
     roof_syrk = None
     cpu_base = None
     corr = None
+    small = None
     if rank == 0:
         peak, peak_src = load_peaks()
         dc, ns = ba.dims(model, mode)
@@ -503,9 +549,12 @@ def run_gpu(args):
         ab = algo_bytes(S_FRAMES, n_loc)
         ach = ab / (ms * 1e-3) / 1e9
         roof = {"kernel": "ba_blocks_kernel<SIMPLE_RADIAL,INTR_SHARED,TMA>", "bound": "hbm", "achieved": ach,
-                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the ncu --set full capture
+                # profiles/r02_ncu_blocks_c3.txt (19.0 MB + 178.5 MB; part of W is still in the 126 MB L2 when the counters stop)
+                "traffic": 1.975e8 if n_loc == N_TRACKS else None,
                 "bytes_per_launch": ab, "ms_per_launch": ms, "observations": obs,
-                "note": "event time includes 6 cudaMemsetAsync of the accumulators"}
+                "note": "event time includes the accumulator memset, the W-tail memset2D and the 256 MB L2 flush is outside"}
         # scaled synthetic: 400 x 131072 tracks = 52 M observations, 8 GB of coupling blocks
         try:
             NS_ = 131072
@@ -530,6 +579,11 @@ def run_gpu(args):
             roof_syrk = syrk_roofline(S_FRAMES * dc + ns, 3 * n_loc, dev, clocks)
         except Exception as e:
             roof_syrk = {"error": str(e)[:200]}
+        if world == 1:
+            try:
+                small = small_problem_section(dev)
+            except Exception as e:
+                small = {"error": str(e)[:200]}
         if world == 1 and not args.no_corr:
             torch.cuda.empty_cache()
             corr = corr_section(dev, peak)
@@ -553,7 +607,7 @@ def run_gpu(args):
             "tracks_per_s": tracks_per_s, "tri_ms_per_pass": tri_ms / args.steps, "tri_median_point_error": tri_median_err,
             "e2e": {"value": e2e_value, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_syrk": roof_syrk,
-            "cpu_baseline": cpu_base, "corr": corr,
+            "cpu_baseline": cpu_base, "corr": corr, "small_problems": small,
         }
         line["config"]["syrk"] = os.environ.get("VGG_SYRK", "ozaki:7") + " (default: tcgen05 kind::i8, 7 Ozaki slices, FP64-equivalent)"
         if hook is not None:
