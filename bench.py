@@ -405,8 +405,14 @@ def run_gpu(args):
                     print(f"[bench] fabric reduction unavailable ({str(e)[:120]}); using NCCL all-reduce", file=sys.stderr)
                 fabric = None
         hook = AllReduceHook(fabric=fabric)
-        reduction = "multimem.red fused into the Schur kernels (NVSwitch multicast)" if hook.fabric is not None \
-            else "NCCL all-reduce of the reduced system"
+        if hook.fabric is None:
+            reduction = "NCCL all-reduce of the reduced system"
+        elif hook.fabric.v2 and os.environ.get("VGG_FABRIC", "2") != "1":
+            reduction = ("fabric v2: reduce-scatter of the lower triangle by red.add.f64 into the owning rank's rows from the "
+                         "SYRK epilogue, gather by peer loads, in-kernel barriers and mailbox all-reduce of the small vectors "
+                         "(csrc/fabric.cu; no NCCL call and no host callback inside the LM loop)")
+        else:
+            reduction = "fabric v1: multimem.red all-reduce fused into the Schur kernels (NVSwitch multicast) + host-hook barriers"
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
 
     def barrier():
@@ -530,22 +536,35 @@ def run_gpu(args):
             return S * N * (8 + 1) + S * (12 + 4) * 8 + N * 3 * 8 + S * KR * 8 + N * 9 * 8 + (S * dc + ns) * N * 3 * 8
 
         def time_blocks(uv_, mask_, poses_, intr_, X_, reps):
+            """(kernel ms, call ms): the kernel alone from the event pair the library records on its stream directly
+            around the ba_blocks_kernel launch (csrc/dev_probes.h), and the whole build_blocks call (accumulator memset,
+            W-tail memset2D, kernel) from torch events on the same stream.  L2 is flushed before every launch."""
+            import ctypes
+            L = _lib.lib()
             for _ in range(3):
                 ba.build_blocks(uv_, mask_, poses_, intr_, X_, model, mode)
             torch.cuda.synchronize()
+            _lib.check(L.vgg_dev_blocks_timing(1), "blocks timing")
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             tot = 0.0
-            for _ in range(reps):
-                flush.fill_(1.0)
-                a.record()
-                out = ba.build_blocks(uv_, mask_, poses_, intr_, X_, model, mode)
-                b.record()
-                torch.cuda.synchronize()
-                tot += a.elapsed_time(b)
-                del out
-            return tot / reps
+            tot_k = 0.0
+            k_ms = ctypes.c_double(0.0)
+            try:
+                for _ in range(reps):
+                    flush.fill_(1.0)
+                    a.record()
+                    out = ba.build_blocks(uv_, mask_, poses_, intr_, X_, model, mode)
+                    b.record()
+                    torch.cuda.synchronize()
+                    tot += a.elapsed_time(b)
+                    _lib.check(L.vgg_dev_blocks_last_ms(ctypes.byref(k_ms)), "blocks timing")
+                    tot_k += k_ms.value
+                    del out
+            finally:
+                L.vgg_dev_blocks_timing(0)
+            return tot_k / reps, tot / reps
 
-        ms = time_blocks(uv, mask, poses0, intr0, pts0, 10)
+        ms, ms_call = time_blocks(uv, mask, poses0, intr0, pts0, 10)
         ab = algo_bytes(S_FRAMES, n_loc)
         ach = ab / (ms * 1e-3) / 1e9
         roof = {"kernel": "ba_blocks_kernel<SIMPLE_RADIAL,INTR_SHARED,TMA>", "bound": "hbm", "achieved": ach,
@@ -553,8 +572,9 @@ def run_gpu(args):
                 # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the ncu --set full capture
                 # profiles/r02_ncu_blocks_c3.txt (19.0 MB + 178.5 MB; part of W is still in the 126 MB L2 when the counters stop)
                 "traffic": 1.975e8 if n_loc == N_TRACKS else None,
-                "bytes_per_launch": ab, "ms_per_launch": ms, "observations": obs,
-                "note": "event time includes the accumulator memset, the W-tail memset2D and the 256 MB L2 flush is outside"}
+                "bytes_per_launch": ab, "ms_per_launch": ms, "ms_per_call": ms_call, "observations": obs,
+                "note": "ms_per_launch: CUDA event pair on the launching stream directly around the kernel; ms_per_call adds "
+                        "the accumulator memset and the W-tail memset2D of one build_blocks call; 256 MB L2 flush before each"}
         # scaled synthetic: 400 x 131072 tracks = 52 M observations, 8 GB of coupling blocks
         try:
             NS_ = 131072
@@ -563,11 +583,11 @@ def run_gpu(args):
             uv_s = uv.repeat(1, rep, 1)[:, :NS_].contiguous()
             mk_s = mask.repeat(1, rep)[:, :NS_].contiguous()
             X_s = pts0.repeat(rep, 1)[:NS_].contiguous()
-            ms_s = time_blocks(uv_s, mk_s, poses0, intr0, X_s, 5)
+            ms_s, ms_s_call = time_blocks(uv_s, mk_s, poses0, intr0, X_s, 5)
             ab_s = algo_bytes(S_FRAMES, NS_)
             ach_s = ab_s / (ms_s * 1e-3) / 1e9
             roof["scaled"] = {"workload": "400 x 131072 tracks", "achieved": ach_s, "frac": ach_s / peak,
-                              "bytes_per_launch": ab_s, "ms_per_launch": ms_s,
+                              "bytes_per_launch": ab_s, "ms_per_launch": ms_s, "ms_per_call": ms_s_call,
                               # dram__bytes_read.sum + dram__bytes_write.sum of this launch shape from the ncu --set full
                               # capture kept in profiles/r01_ncu_full_summary_k1_scaled.txt (0.58 GB + 7.51 GB)
                               "traffic": 8.09e9}

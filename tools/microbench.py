@@ -77,6 +77,24 @@ if mode in ("pose", "pipeline"):
           f"valid frames {int(out[6].sum())}")
     sys.exit(0)
 
+if mode == "chol128":
+    import ctypes
+    from vggsfm_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.default_rng(0)
+    B = rng.standard_normal((128, 160))
+    A = np.ascontiguousarray(B @ B.T / 160 + 0.5 * np.eye(128))
+    names = ["leaf(0)", "trsm(b)", "lookahead work", "lookahead wait", "dmma rank-32", "leaf(t0)"]
+    for leaf in (0, 1):
+        Lo = np.zeros((128, 128))
+        prof = np.zeros(13, dtype=np.int64)
+        _lib.check(L.vgg_dev_chol128_probe(leaf, 5, A.ctypes.data, Lo.ctypes.data, prof.ctypes.data), "probe")
+        err = np.abs(Lo @ Lo.T - A).max() / np.abs(A).max()
+        print(f"[{tag}] POTRF128 leaf={leaf}: {prof[12]} cycles  |LL^T-A|/|A| = {err:.2e}")
+        for w in (0, 1):
+            print("    warp %d: " % w + "  ".join(f"{n} {prof[w * 6 + i]}" for i, n in enumerate(names)))
+    sys.exit(0)
+
 if mode == "chol":
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 2403
     rng = np.random.default_rng(0)
@@ -116,7 +134,21 @@ else:
     if mode == "blocks":
         ms = timeit(lambda: ba.build_blocks(uv, mask, poses, intr_t, X, model, mode_i), reps=10)
         nbytes = S * N * 153
-        print(f"[{tag}] build_blocks 400x{N}: {ms:.4f} ms  {nbytes / ms / 1e6:.0f} GB/s (153 B/obs)")
+        import ctypes
+        from vggsfm_b200 import _lib
+        L = _lib.lib()
+        L.vgg_dev_blocks_timing(1)
+        flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)
+        k = ctypes.c_double(0.0)
+        tot = 0.0
+        for _ in range(10):
+            flush.fill_(1.0)
+            ba.build_blocks(uv, mask, poses, intr_t, X, model, mode_i)
+            _lib.check(L.vgg_dev_blocks_last_ms(ctypes.byref(k)), "timing")
+            tot += k.value
+        L.vgg_dev_blocks_timing(0)
+        kms = tot / 10
+        print(f"[{tag}] build_blocks 400x{N}: call {ms:.4f} ms  {nbytes / ms / 1e6:.0f} GB/s;  kernel alone (L2 flushed) {kms:.4f} ms  {nbytes / kms / 1e6:.0f} GB/s (153 B/obs)")
     else:
         opt = ba.default_options()
         opt.max_num_iterations = 10

@@ -26,8 +26,14 @@
 #include <stdlib.h>
 #include <utility>
 #include "common.cuh"
+#include "dev_probes.h"
 
 namespace vgg {
+
+// kernel-only timing for bench.py's roofline (csrc/dev_probes.h): an event pair on the launching stream, directly
+// around the ba_blocks_kernel launch (the accumulator memsets stay outside)
+static bool g_blocks_timing = false;
+static cudaEvent_t g_blocks_ev[2] = {nullptr, nullptr};
 
 constexpr int BW = 4;            // warps per CTA
 constexpr int BT = BW * 32;      // threads per CTA
@@ -440,6 +446,7 @@ static int launch_blocks(const vgg_ba_problem* p, double* cost, double* camrec, 
   }
   // MINB = 3 caps registers at 168 (12 resident warps/SM, a few spills); MINB = 2 lets ptxas use ~250 (no spills,
   // 8 warps/SM) and is the default.  VGG_K1_MINB=2|3 selects for A/B runs.
+  if (g_blocks_timing) VGG_CUDA_CHECK(cudaEventRecord(g_blocks_ev[0], stream));
   if (tma_ok && minb == 2) {
     auto kern = ba_blocks_kernel<MODEL, MODE, true, 2>;
     VGG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -457,6 +464,7 @@ static int launch_blocks(const vgg_ba_problem* p, double* cost, double* camrec, 
                                      p->point_const, cost, camrec, g_p, H_pp, W, shared_out);
   }
   VGG_LAUNCH_CHECK();
+  if (g_blocks_timing) VGG_CUDA_CHECK(cudaEventRecord(g_blocks_ev[1], stream));
   return VGG_OK;
 }
 
@@ -476,3 +484,23 @@ int ba_build_blocks(const vgg_ba_problem* p, double* cost, double* camrec, doubl
 }
 
 }  // namespace vgg
+
+extern "C" int vgg_dev_blocks_timing(int enable) {
+  using namespace vgg;
+  if (enable && !g_blocks_ev[0]) {
+    VGG_CUDA_CHECK(cudaEventCreate(&g_blocks_ev[0]));
+    VGG_CUDA_CHECK(cudaEventCreate(&g_blocks_ev[1]));
+  }
+  g_blocks_timing = enable != 0;
+  return VGG_OK;
+}
+
+extern "C" int vgg_dev_blocks_last_ms(double* ms) {
+  using namespace vgg;
+  VGG_REQUIRE(g_blocks_ev[0] && ms, "blocks timing was never enabled");
+  VGG_CUDA_CHECK(cudaEventSynchronize(g_blocks_ev[1]));
+  float f = 0.f;
+  VGG_CUDA_CHECK(cudaEventElapsedTime(&f, g_blocks_ev[0], g_blocks_ev[1]));
+  *ms = (double)f;
+  return VGG_OK;
+}

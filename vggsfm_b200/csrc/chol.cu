@@ -43,57 +43,141 @@ __device__ __forceinline__ void chol_dmma(double& d0, double& d1, double a, doub
 //     REST OF THE SUB-PANEL only (<= 24 columns), two threads per row;
 //   * after each sub-panel ONE rank-32 update of everything to its right with mma.sync.m8n8k4.f64 (DMMA), 32x16 warp
 //     tiles straight from the row-major block (row stride 132: conflict-free fragments).
-// 1/sqrt(p) for p > 0: float seed + two Newton steps in double (full double accuracy from the 22-bit seed: 22 -> 44 ->
-// 88 bits); ~100 cycles of latency instead of ~150 for rsqrt(double) -- this sits on the 128-deep pivot chain of every panel.
+// 1/sqrt(p) for normal p > 0: the hardware's double-precision seed (rsqrt.approx.ftz.f64 -> MUFU.RSQ64H, relative error
+// 2^-22.4 over the whole double range) + two Newton steps (-> 2^-44 -> below one ulp).  No float round trip, no range
+// check and no select in front of it: this sits on the 128-deep pivot chain of every panel, and the first version
+// (float seed: F2F, FSETP, FMUL, MUFU, FMUL, F2F before the first Newton step, behind a DSETP/FSEL range guard) spent
+// about as long getting to the seed as refining it.  Callers test the pivot in parallel and discard the result if the
+// pivot was not a normal positive number.
 __device__ __forceinline__ double fast_rsqrt(double p) {
-  double r = (double)rsqrtf((float)p);
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(p));
   const double hp = 0.5 * p;
   r = r * fma(-hp * r, r, 1.5);
   r = r * fma(-hp * r, r, 1.5);
   return r;
 }
+constexpr double CHOL_PMIN = 2.2250738585072014e-308;      // smallest normal double: pivots below it count as non-positive
 
-__device__ __forceinline__ int cta_chol128(double* Ls, double* dinv, int* fail_sm, int tid) {
+// LEAF selects the 8x8 leaf (0: one pivot per step, 1: two pivots per step); PROBE adds clock64 phase counters for
+// tools/microbench.py chol128 (threads 0 and 32 = warp 0 / warp 1; prof[warp][phase], see the MARK sites).
+template <int LEAF, bool PROBE>
+__device__ __forceinline__ int cta_chol128(double* Ls, double* dinv, int* fail_sm, int tid, long long* prof = nullptr) {
   const int lane = tid & 31, warp = tid >> 5;
   if (tid == 0) *fail_sm = 0;
   __syncthreads();
-  // 8x8 leaf by warp 0, shuffle-free: EVERY lane holds the whole lower triangle (36 doubles) and runs the same
-  // straight-line factorisation, so the pivot chain is rsqrt -> one multiply -> one FMA per column with the other
-  // updates in its shadow (r02 source-correlated profile of the one-row-per-lane version: ~300 cycles per pivot, half
-  // of them 64-bit shuffles; 45 % of the panel kernel's warp samples waited on barriers for this chain)
-  auto leaf = [&](int c0) {
-    double a[36];
+  long long pacc[6] = {0, 0, 0, 0, 0, 0}, plast = 0;
+  const bool ptid = PROBE && (tid == 0 || tid == 32);
+  if (ptid) plast = clock64();
+#define CHOL_MARK(ph)                         \
+  if (ptid) {                                 \
+    const long long t_ = clock64();           \
+    pacc[ph] += t_ - plast;                   \
+    plast = t_;                               \
+  }
+  // 8x8 leaf by warp 0: one row per lane (lanes 8..31 mirror lanes 0..7), pivot columns through shuffles, TWO pivots
+  // per step.  For the 2x2 block [[A, B], [B, C]] both reciprocal square roots come from independent inputs:
+  //   1/L00 = rsqrt(A),   1/L11 = rsqrt(C - B^2/A) = sqrt(A) * rsqrt(A C - B^2),
+  // so the serial chain per PAIR is shuffle -> det -> rsqrt -> two scalings -> shuffle -> two FMAs (~220 cycles) where the
+  // one-pivot-per-step version paid ~300 cycles per pivot (r02 source-correlated profile: 45 % of the panel kernel's
+  // warp samples waited on barriers behind this chain).  det = A C - B^2 carries the same relative error bound as
+  // C - (B/sqrt A)^2 (both ~ eps C / (C - B^2/A)); if A C leaves the comfortable exponent range the second pivot falls
+  // back to the sequential formula (warp-uniform branch).  A shuffle-free variant (every lane holds the whole
+  // 36-element triangle) measured SLOWER: panel 51.6 vs 48.6 us -- 36 broadcast loads + 64 predicated stores per leaf
+  // cost more than the shuffles they replace.
+  auto leaf1 = [&](int c0) {
+    double a[8];
+    const int r = c0 + (lane & 7);
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int c = 0; c < 8; c += 2) {
+      const double2 v = *reinterpret_cast<const double2*>(Ls + r * CLD + c0 + c);
+      a[c] = v.x;
+      a[c + 1] = v.y;
+    }
+    int fail = 0;
 #pragma unroll
-      for (int j = 0; j <= i; ++j) a[i * (i + 1) / 2 + j] = Ls[(c0 + i) * CLD + c0 + j];
-    double dv[8];
+    for (int j = 0; j < 8; j += 2) {
+      const double A = __shfl_sync(0xffffffffu, a[j], j);
+      const double B = __shfl_sync(0xffffffffu, a[j], j + 1);
+      const double C = __shfl_sync(0xffffffffu, a[j + 1], j + 1);
+      const double AC = A * C;
+      const double det = fma(-B, B, AC);
+      double ia = fast_rsqrt(A);
+      double ib = (A * ia) * fast_rsqrt(det);
+      double l10 = B * ia;
+      // the tests run in the shadow of the two rsqrt chains; the branch is warp-uniform (every lane holds A, B, C)
+      const bool good = A >= CHOL_PMIN && det >= CHOL_PMIN && AC < 1e280 && AC > 1e-280;
+      if (!good) {
+        if (!(A >= CHOL_PMIN)) {
+          if (fail == 0) fail = c0 + j + 1;
+          ia = 1.0;
+          l10 = B;
+        }
+        const double p1 = fma(-l10, l10, C);
+        if (!(p1 >= CHOL_PMIN)) {
+          if (fail == 0) fail = c0 + j + 2;
+          ib = 1.0;
+        } else {
+          ib = rsqrt(p1);
+        }
+      }
+      const double x0 = a[j] * ia;                          // lane j: A * ia = sqrt(A)
+      const double x1 = fma(-x0, l10, a[j + 1]) * ib;       // lane j+1: (C - l10^2) / sqrt(C - l10^2)
+      a[j] = x0;
+      a[j + 1] = x1;
+      if (lane == j) {
+        dinv[c0 + j] = ia;
+        dinv[c0 + j + 1] = ib;
+      }
+#pragma unroll
+      for (int c = j + 2; c < 8; ++c) {
+        const double l0 = __shfl_sync(0xffffffffu, x0, c);
+        const double l1 = __shfl_sync(0xffffffffu, x1, c);
+        if (lane >= c) a[c] = fma(-x1, l1, fma(-x0, l0, a[c]));
+      }
+    }
+    if (lane < 8) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) Ls[r * CLD + c0 + c] = (c <= lane) ? a[c] : 0.0;
+    }
+    if (lane == 0 && fail && *fail_sm == 0) *fail_sm = fail;
+  };
+  // one pivot per step (the r02 default until the two-pivot leaf; kept for A/B through the probe)
+  auto leaf0 = [&](int c0) {
+    double a[8];
+    const int r = c0 + (lane & 7);
+#pragma unroll
+    for (int c = 0; c < 8; c += 2) {
+      const double2 v = *reinterpret_cast<const double2*>(Ls + r * CLD + c0 + c);
+      a[c] = v.x;
+      a[c + 1] = v.y;
+    }
     int fail = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const double pj = a[j * (j + 1) / 2 + j];
-      if (!(pj > 0.0) && fail == 0) fail = c0 + j + 1;
-      const double inv = fast_rsqrt(pj > 0.0 ? pj : 1.0);
-      dv[j] = inv;
-      a[j * (j + 1) / 2 + j] = pj * inv;
+      const double pj = __shfl_sync(0xffffffffu, a[j], j);
+      double inv = fast_rsqrt(pj);
+      if (!(pj >= CHOL_PMIN)) {                               // uniform; tested in the shadow of the rsqrt chain
+        if (fail == 0) fail = c0 + j + 1;
+        inv = 1.0;
+      }
+      a[j] = a[j] * inv;                                      // lane j: pj * inv = sqrt(pj)
+      if (lane == j) dinv[c0 + j] = inv;
 #pragma unroll
-      for (int i = j + 1; i < 8; ++i) a[i * (i + 1) / 2 + j] *= inv;
-#pragma unroll
-      for (int k = j + 1; k < 8; ++k)
-#pragma unroll
-        for (int i = k; i < 8; ++i)
-          a[i * (i + 1) / 2 + k] = fma(-a[i * (i + 1) / 2 + j], a[k * (k + 1) / 2 + j], a[i * (i + 1) / 2 + k]);
-    }
-    // lane l stores row l (zeros above the diagonal) and dinv[l]
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (lane == i) {
-#pragma unroll
-        for (int c = 0; c < 8; ++c) Ls[(c0 + i) * CLD + c0 + c] = (c <= i) ? a[i * (i + 1) / 2 + c] : 0.0;
-        dinv[c0 + i] = dv[i];
+      for (int c = j + 1; c < 8; ++c) {
+        const double lc = __shfl_sync(0xffffffffu, a[j], c);
+        if (lane >= c) a[c] = fma(-a[j], lc, a[c]);
       }
     }
+    if (lane < 8) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) Ls[r * CLD + c0 + c] = (c <= lane) ? a[c] : 0.0;
+    }
     if (lane == 0 && fail && *fail_sm == 0) *fail_sm = fail;
+  };
+  auto leaf = [&](int c0) {
+    if constexpr (LEAF == 0) leaf0(c0);
+    else leaf1(c0);
   };
   // C[r][j] -= sum_k L[r][c0+k] L[j][c0+k] for j = jb, jb+js, ... <= jend (two columns in flight)
   auto row_update = [&](int r, int c0, int jb, int js, int jend) {
@@ -135,6 +219,7 @@ __device__ __forceinline__ int cta_chol128(double* Ls, double* dinv, int* fail_s
   };
   if (warp == 0) leaf(0);
   __syncthreads();
+  CHOL_MARK(0)
   for (int sp = 0; sp < CB / 32; ++sp) {
     const int c32 = sp * 32;
     for (int mp = 0; mp < 4; ++mp) {
@@ -161,6 +246,7 @@ __device__ __forceinline__ int cta_chol128(double* Ls, double* dinv, int* fail_s
         }
       }
       __syncthreads();
+      CHOL_MARK(1)
       // (c) rank-8 update of the remaining columns of THIS sub-panel (c0+8 .. c32+31), all rows below -- with one
       //     micro-panel of lookahead: warp 0 first finishes the next 8x8 diagonal block and factors it (the pivot chain,
       //     ~1.3k cycles) while warps 1..7 update everything else (two threads per row, alternate columns)
@@ -181,7 +267,9 @@ __device__ __forceinline__ int cta_chol128(double* Ls, double* dinv, int* fail_s
             row_update(r, c0, n0 + half, 2, jend);
           }
         }
+        CHOL_MARK(2)
         __syncthreads();
+        CHOL_MARK(3)
       }
     }
     // rank-32 update of the block to the right of the sub-panel: C[i][j] -= sum_k L[i][c32+k] L[j][c32+k], i >= j >= c32+32
@@ -233,17 +321,46 @@ __device__ __forceinline__ int cta_chol128(double* Ls, double* dinv, int* fail_s
         }
       }
       __syncthreads();
+      CHOL_MARK(4)
       // first leaf of the next sub-panel (its block is now complete)
       if (warp == 0) leaf(t0);
       __syncthreads();
+      CHOL_MARK(5)
     }
   }
+#undef CHOL_MARK
+  if (ptid) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) prof[(tid == 32 ? 6 : 0) + i] = pacc[i];
+  }
   return *fail_sm;
+}
+
+// one-CTA probe: factor a 128 x 128 block `reps` times (reloading it each time), report the cycles of the last pass
+template <int LEAF>
+__global__ void __launch_bounds__(C_THREADS, 1) chol128_probe_kernel(const double* __restrict__ A, double* __restrict__ L,
+                                                                      long long* __restrict__ prof, int reps) {
+  extern __shared__ __align__(16) double cp_smem[];
+  __shared__ double dinv[CB];
+  __shared__ int fail_sm;
+  const int tid = threadIdx.x;
+  long long total = 0;
+  for (int rep = 0; rep < reps; ++rep) {
+    for (int e = tid; e < CB * CB; e += C_THREADS) cp_smem[(e >> 7) * CLD + (e & 127)] = A[e];
+    __syncthreads();
+    const long long t0 = clock64();
+    cta_chol128<LEAF, true>(cp_smem, dinv, &fail_sm, tid, prof);
+    __syncthreads();
+    total = clock64() - t0;
+  }
+  if (tid == 0) prof[12] = total;
+  for (int e = tid; e < CB * CB; e += C_THREADS) L[e] = ((e & 127) <= (e >> 7)) ? cp_smem[(e >> 7) * CLD + (e & 127)] : 0.0;
 }
 
 // grid.x = 1 + number of 16-row chunks below the diagonal block; block 256.  CTA 0 stores the factored block: L^T into
 // the strict upper triangle in place (nobody reads it), L itself into the side buffer Ldiag -- the other CTAs of this
 // launch may still be loading the unfactored block, so it is copied into place by chol_copy_diag_kernel at the end.
+template <int LEAF>
 __global__ void __launch_bounds__(C_THREADS, 1) chol_panel_kernel(int n, int lda, int k0, double* __restrict__ A,
                                                                    double* __restrict__ Ldiag /*[nblk][128*128]*/,
                                                                    int* __restrict__ info) {
@@ -277,7 +394,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) chol_panel_kernel(int n, int lda
   cp_async_commit();
   cp_async_wait<0>();
   __syncthreads();
-  const int fail = cta_chol128(Ls, dinv, &fail_sm, tid);
+  const int fail = cta_chol128<LEAF, false>(Ls, dinv, &fail_sm, tid);
   if (fail && blockIdx.x == 0 && tid == 0) atomicCAS(info, 0, k0 + fail);
   // mirror: Ls[m][j] = L[j][m] for j > m (the solve below reads column m of L as a contiguous row; CTA 0 stores it as L^T)
   for (int e = tid; e < CB * CB; e += C_THREADS) {
@@ -471,10 +588,18 @@ int chol_streams(CholStreams** out) {
   return VGG_OK;
 }
 
+// VGG_CHOL_LEAF=0|1 (A/B): 8x8 leaf with one / two pivots per step
+int chol_leaf() {
+  static const int v = [] { const char* e = getenv("VGG_CHOL_LEAF"); return (e && e[0] == '1') ? 1 : 0; }();
+  return v;
+}
+
 int chol_set_attrs() {
   static bool done = false;
   if (done) return VGG_OK;
-  VGG_CUDA_CHECK(cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  VGG_CUDA_CHECK(cudaFuncSetAttribute(chol_panel_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(sizeof(double) * (CB + C_RPC) * CLD)));
+  VGG_CUDA_CHECK(cudaFuncSetAttribute(chol_panel_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(sizeof(double) * (CB + C_RPC) * CLD)));
   VGG_CUDA_CHECK(cudaFuncSetAttribute(chol_update_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(sizeof(double) * 2 * CT * CLD)));
@@ -493,7 +618,8 @@ int chol_enqueue(int n, int lda, double* A, double* Ldiag, int* info, cudaStream
     const int k0 = b * CB;
     const int below = n - (k0 + CB);
     const int chunks = below > 0 ? (below + C_RPC - 1) / C_RPC : 0;
-    chol_panel_kernel<<<1 + chunks, C_THREADS, smem_p, s2>>>(n, lda, k0, A, Ldiag, info);
+    if (chol_leaf() == 1) chol_panel_kernel<1><<<1 + chunks, C_THREADS, smem_p, s2>>>(n, lda, k0, A, Ldiag, info);
+    else chol_panel_kernel<0><<<1 + chunks, C_THREADS, smem_p, s2>>>(n, lda, k0, A, Ldiag, info);
     VGG_LAUNCH_CHECK();
     return VGG_OK;
   };
@@ -576,3 +702,32 @@ int chol_lower_inplace(int n, int lda, double* A, double* Ldiag, int* info, cuda
 }
 
 }  // namespace vgg
+
+// tools/microbench.py chol128: one CTA, POTRF128 of A (host, row-major SPD 128 x 128), cycles per phase
+extern "C" int vgg_dev_chol128_probe(int leaf, int reps, const double* A_host, double* L_host, long long* prof13_host) {
+  using namespace vgg;
+  VGG_REQUIRE(A_host && L_host && prof13_host && reps > 0, "chol128 probe: bad arguments");
+  double *dA = nullptr, *dL = nullptr;
+  long long* dP = nullptr;
+  VGG_CUDA_CHECK(cudaMalloc(&dA, sizeof(double) * CB * CB));
+  VGG_CUDA_CHECK(cudaMalloc(&dL, sizeof(double) * CB * CB));
+  VGG_CUDA_CHECK(cudaMalloc(&dP, sizeof(long long) * 13));
+  VGG_CUDA_CHECK(cudaMemcpy(dA, A_host, sizeof(double) * CB * CB, cudaMemcpyHostToDevice));
+  VGG_CUDA_CHECK(cudaMemset(dP, 0, sizeof(long long) * 13));
+  const int smem = (int)(sizeof(double) * CB * CLD);
+  if (leaf == 1) {
+    VGG_CUDA_CHECK(cudaFuncSetAttribute(chol128_probe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    chol128_probe_kernel<1><<<1, C_THREADS, smem>>>(dA, dL, dP, reps);
+  } else {
+    VGG_CUDA_CHECK(cudaFuncSetAttribute(chol128_probe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    chol128_probe_kernel<0><<<1, C_THREADS, smem>>>(dA, dL, dP, reps);
+  }
+  VGG_LAUNCH_CHECK();
+  VGG_CUDA_CHECK(cudaDeviceSynchronize());
+  VGG_CUDA_CHECK(cudaMemcpy(L_host, dL, sizeof(double) * CB * CB, cudaMemcpyDeviceToHost));
+  VGG_CUDA_CHECK(cudaMemcpy(prof13_host, dP, sizeof(long long) * 13, cudaMemcpyDeviceToHost));
+  cudaFree(dA);
+  cudaFree(dL);
+  cudaFree(dP);
+  return VGG_OK;
+}
