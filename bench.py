@@ -570,8 +570,8 @@ def run_gpu(args):
         roof = {"kernel": "ba_blocks_kernel<SIMPLE_RADIAL,INTR_SHARED,TMA>", "bound": "hbm", "achieved": ach,
                 "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": ach / peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of this launch from the ncu --set full capture
-                # profiles/r02_ncu_blocks_c3.txt (19.0 MB + 178.5 MB; part of W is still in the 126 MB L2 when the counters stop)
-                "traffic": 1.975e8 if n_loc == N_TRACKS else None,
+                # profiles/r02_ncu_blocks_c3b.txt (16.0 MB + 176.7 MB; part of W is still in the 126 MB L2 when the counters stop)
+                "traffic": 1.927e8 if n_loc == N_TRACKS else None,
                 "bytes_per_launch": ab, "ms_per_launch": ms, "ms_per_call": ms_call, "observations": obs,
                 "note": "ms_per_launch: CUDA event pair on the launching stream directly around the kernel; ms_per_call adds "
                         "the accumulator memset and the W-tail memset2D of one build_blocks call; 256 MB L2 flush before each"}

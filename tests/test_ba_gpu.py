@@ -241,7 +241,7 @@ def test_cholesky_matches_lapack(cuda_dev, n):
     lda = (n + 127) // 128 * 128
     buf = torch.zeros(n, lda, dtype=torch.float64, device=cuda_dev)
     buf[:, :n] = torch.from_numpy(np.tril(A)).to(cuda_dev)
-    ws = torch.empty(((n + 127) // 128) * 131072 + 256, dtype=torch.uint8, device=cuda_dev)
+    ws = torch.empty(((n + 127) // 128) * 131072 + 1024, dtype=torch.uint8, device=cuda_dev)
     info = ctypes.c_int(-1)
     L = _lib.lib()
     _lib.check(L.vgg_cholesky_lower(n, lda, buf.data_ptr(), ws.data_ptr(), ws.numel(), ctypes.byref(info),

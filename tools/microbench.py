@@ -104,7 +104,7 @@ if mode == "chol":
     src = torch.zeros(n, lda, dtype=torch.float64, device=dev)
     src[:, :n] = torch.from_numpy(A).to(dev)
     buf = src.clone()
-    ws = torch.empty(((n + 127) // 128) * 131072 + 256, dtype=torch.uint8, device=dev)
+    ws = torch.empty(((n + 127) // 128) * 131072 + 1024, dtype=torch.uint8, device=dev)
     L = _lib.lib()
     st = torch.cuda.current_stream().cuda_stream
 

@@ -24,7 +24,7 @@ if mode == "chol":
     lda = (n + 127) // 128 * 128
     src = torch.zeros(n, lda, dtype=torch.float64, device=dev)
     src[:, :n] = torch.from_numpy(A).to(dev)
-    ws = torch.empty(((n + 127) // 128) * 131072 + 256, dtype=torch.uint8, device=dev)
+    ws = torch.empty(((n + 127) // 128) * 131072 + 1024, dtype=torch.uint8, device=dev)
     L = _lib.lib()
     for _ in range(2):
         buf = src.clone()

@@ -61,11 +61,23 @@ constexpr double CHOL_PMIN = 2.2250738585072014e-308;      // smallest normal do
 
 // LEAF selects the 8x8 leaf (0: one pivot per step, 1: two pivots per step); PROBE adds clock64 phase counters for
 // tools/microbench.py chol128 (threads 0 and 32 = warp 0 / warp 1; prof[warp][phase], see the MARK sites).
+//
+// xr (0 or C_RPC) extra rows stored right below the block (rows 128 .. 128+xr-1 of Ls) ride along: they take part in the
+// micro-panel solves and in the rank-8 / rank-32 updates, so when the block is factored they hold X = A_ik L^-T -- the
+// panel rows this CTA owns -- with no separate triangular solve afterwards (r02: that solve was a 128-step
+// multiply/shuffle/FMA chain, ~3 us after every POTRF128, plus a transposing pass over the block to feed it).
 template <int LEAF, bool PROBE>
-__device__ __forceinline__ int cta_chol128(double* Ls, double* dinv, int* fail_sm, int tid, long long* prof = nullptr) {
+__device__ __forceinline__ int cta_chol128(double* Ls, double* dinv, int* fail_sm, int tid, int xr,
+                                           long long* prof = nullptr) {
   const int lane = tid & 31, warp = tid >> 5;
   if (tid == 0) *fail_sm = 0;
   __syncthreads();
+  // packed lower-triangle entry of an 8 x 8 block owned by this lane in the look-ahead prep: e = lane (and lane + 32 for
+  // lanes 0..3; the other lanes recompute entry 35 and drop it)
+  auto tri_row = [](int e) { return (e >= 1) + (e >= 3) + (e >= 6) + (e >= 10) + (e >= 15) + (e >= 21) + (e >= 28); };
+  const int pi0 = tri_row(lane), pj0 = lane - pi0 * (pi0 + 1) / 2;
+  const int e1 = lane < 4 ? lane + 32 : 35;
+  const int pi1 = tri_row(e1), pj1 = e1 - pi1 * (pi1 + 1) / 2;
   long long pacc[6] = {0, 0, 0, 0, 0, 0}, plast = 0;
   const bool ptid = PROBE && (tid == 0 || tid == 32);
   if (ptid) plast = clock64();
@@ -227,7 +239,7 @@ __device__ __forceinline__ int cta_chol128(double* Ls, double* dinv, int* fail_s
       // (b) rows below the micro-block: x L^T = a, one thread per row
       {
         const int r = c0 + 8 + tid;
-        if (r < CB) {
+        if (r < CB + xr) {
           double x[8];
 #pragma unroll
           for (int c = 0; c < 8; c += 2) {
@@ -253,12 +265,39 @@ __device__ __forceinline__ int cta_chol128(double* Ls, double* dinv, int* fail_s
       if (mp < 3) {
         const int n0 = c0 + 8;                                   // first row/column of the next micro-panel
         if (warp == 0) {
-          if (lane < 8) row_update(n0 + lane, c0, n0, 1, n0 + lane);      // the next leaf's lower triangle
+          // the next leaf's lower triangle, one entry (i, j) per lane (36 entries: lanes 0..3 take a second one): a
+          // length-8 dot product in two chains.  (r02 probe: eight lanes walking their rows cost ~900 of the ~2300
+          // cycles this section took per micro-panel -- and the section is the critical path of the factorisation.)
+          {
+            const double* ri = Ls + (n0 + pi0) * CLD + c0;
+            const double* rj = Ls + (n0 + pj0) * CLD + c0;
+            const double* ri1 = Ls + (n0 + pi1) * CLD + c0;
+            const double* rj1 = Ls + (n0 + pj1) * CLD + c0;
+            double s0 = Ls[(n0 + pi0) * CLD + n0 + pj0], s1 = 0.0;
+            double u0 = Ls[(n0 + pi1) * CLD + n0 + pj1], u1 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 8; k += 4) {
+              const double2 a0 = *reinterpret_cast<const double2*>(ri + k), a1 = *reinterpret_cast<const double2*>(ri + k + 2);
+              const double2 b0 = *reinterpret_cast<const double2*>(rj + k), b1 = *reinterpret_cast<const double2*>(rj + k + 2);
+              const double2 c0v = *reinterpret_cast<const double2*>(ri1 + k), c1v = *reinterpret_cast<const double2*>(ri1 + k + 2);
+              const double2 d0 = *reinterpret_cast<const double2*>(rj1 + k), d1 = *reinterpret_cast<const double2*>(rj1 + k + 2);
+              s0 = fma(-a0.x, b0.x, s0);
+              s1 = fma(-a0.y, b0.y, s1);
+              u0 = fma(-c0v.x, d0.x, u0);
+              u1 = fma(-c0v.y, d0.y, u1);
+              s0 = fma(-a1.x, b1.x, s0);
+              s1 = fma(-a1.y, b1.y, s1);
+              u0 = fma(-c1v.x, d1.x, u0);
+              u1 = fma(-c1v.y, d1.y, u1);
+            }
+            Ls[(n0 + pi0) * CLD + n0 + pj0] = s0 + s1;
+            if (lane < 4) Ls[(n0 + pi1) * CLD + n0 + pj1] = u0 + u1;
+          }
           __syncwarp();
           leaf(n0);
         } else {
           const int t = tid - 32;                                 // 224 threads: row = n0 + t/2 (skipping nothing), half
-          for (int rr = t >> 1; n0 + rr < CB; rr += 112) {
+          for (int rr = t >> 1; n0 + rr < CB + xr; rr += 112) {
             const int r = n0 + rr, half = t & 1;
             const int jend = min(r, c32 + 31);
             // rows of the next leaf block (r < n0+8) own only columns right of it?  no: their columns <= r all lie inside
@@ -277,11 +316,22 @@ __device__ __forceinline__ int cta_chol128(double* Ls, double* dinv, int* fail_s
     const int nrb = (CB - t0) / 32;                  // 32-row blocks: 3, 2, 1, 0
     if (nrb > 0) {
       const int ntile = nrb * (nrb + 1);             // sum over rb of (2 rb + 2) 16-column tiles
+      const int nxt = xr ? (CB - t0) / 16 : 0;       // 16 x 16 tiles of the ride-along rows (two 8-row MMA blocks)
       const int g = lane >> 2, q = lane & 3;
-      for (int t = warp; t < ntile; t += C_THREADS / 32) {
-        int rb = 0, cb = t;
-        while (cb >= 2 * rb + 2) { cb -= 2 * rb + 2; ++rb; }
-        const int R0 = t0 + rb * 32, C0 = t0 + cb * 16;
+      // warp 0 updates tile 0 (it holds the next sub-panel's first 8 x 8 block), then factors that block while warps
+      // 1..7 finish the other tiles (r02 probe: the three unoverlapped leaves were 9 % of the POTRF128)
+      for (int t = warp == 0 ? 0 : warp; t < ntile + nxt; t += (warp == 0 ? ntile + nxt : C_THREADS / 32 - 1)) {
+        int R0, C0, nrow8 = 4;
+        if (t < ntile) {
+          int rb = 0, cb = t;
+          while (cb >= 2 * rb + 2) { cb -= 2 * rb + 2; ++rb; }
+          R0 = t0 + rb * 32;
+          C0 = t0 + cb * 16;
+        } else {
+          R0 = CB;
+          C0 = t0 + (t - ntile) * 16;
+          nrow8 = 2;
+        }
         double c[4][2][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -293,16 +343,20 @@ __device__ __forceinline__ int cta_chol128(double* Ls, double* dinv, int* fail_s
         for (int k4 = 0; k4 < 8; ++k4) {
           double a[4], b[2];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) a[i] = arow[i * 8 * CLD + k4 * 4];
+          for (int i = 0; i < 4; ++i) a[i] = (i < nrow8) ? arow[i * 8 * CLD + k4 * 4] : 0.0;
 #pragma unroll
           for (int j = 0; j < 2; ++j) b[j] = brow[j * 8 * CLD + k4 * 4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
+          for (int i = 0; i < 4; ++i) {
+            if (i < nrow8) {                               // warp-uniform
 #pragma unroll
-            for (int j = 0; j < 2; ++j) chol_dmma(c[i][j][0], c[i][j][1], a[i], b[j]);
+              for (int j = 0; j < 2; ++j) chol_dmma(c[i][j][0], c[i][j][1], a[i], b[j]);
+            }
+          }
         }
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+          if (i >= nrow8) continue;
           const int r = R0 + i * 8 + g;
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
@@ -320,10 +374,11 @@ __device__ __forceinline__ int cta_chol128(double* Ls, double* dinv, int* fail_s
           }
         }
       }
-      __syncthreads();
       CHOL_MARK(4)
-      // first leaf of the next sub-panel (its block is now complete)
-      if (warp == 0) leaf(t0);
+      if (warp == 0) {
+        __syncwarp();
+        leaf(t0);
+      }
       __syncthreads();
       CHOL_MARK(5)
     }
@@ -339,7 +394,7 @@ __device__ __forceinline__ int cta_chol128(double* Ls, double* dinv, int* fail_s
 // one-CTA probe: factor a 128 x 128 block `reps` times (reloading it each time), report the cycles of the last pass
 template <int LEAF>
 __global__ void __launch_bounds__(C_THREADS, 1) chol128_probe_kernel(const double* __restrict__ A, double* __restrict__ L,
-                                                                      long long* __restrict__ prof, int reps) {
+                                                                      long long* __restrict__ prof, int reps, int xr) {
   extern __shared__ __align__(16) double cp_smem[];
   __shared__ double dinv[CB];
   __shared__ int fail_sm;
@@ -347,9 +402,11 @@ __global__ void __launch_bounds__(C_THREADS, 1) chol128_probe_kernel(const doubl
   long long total = 0;
   for (int rep = 0; rep < reps; ++rep) {
     for (int e = tid; e < CB * CB; e += C_THREADS) cp_smem[(e >> 7) * CLD + (e & 127)] = A[e];
+    for (int e = tid; e < xr * CB; e += C_THREADS)          // ride-along rows: copies of the block's last rows
+      cp_smem[(CB + (e >> 7)) * CLD + (e & 127)] = A[(CB - xr + (e >> 7)) * CB + (e & 127)];
     __syncthreads();
     const long long t0 = clock64();
-    cta_chol128<LEAF, true>(cp_smem, dinv, &fail_sm, tid, prof);
+    cta_chol128<LEAF, true>(cp_smem, dinv, &fail_sm, tid, xr, prof);
     __syncthreads();
     total = clock64() - t0;
   }
@@ -357,19 +414,34 @@ __global__ void __launch_bounds__(C_THREADS, 1) chol128_probe_kernel(const doubl
   for (int e = tid; e < CB * CB; e += C_THREADS) L[e] = ((e & 127) <= (e >> 7)) ? cp_smem[(e >> 7) * CLD + (e & 127)] : 0.0;
 }
 
-// grid.x = 1 + number of 16-row chunks below the diagonal block; block 256.  CTA 0 stores the factored block: L^T into
-// the strict upper triangle in place (nobody reads it), L itself into the side buffer Ldiag -- the other CTAs of this
-// launch may still be loading the unfactored block, so it is copied into place by chol_copy_diag_kernel at the end.
+// grid.x = 1 + number of 16-row chunks below the diagonal block; block 256.  Every CTA factors the diagonal block
+// redundantly with its own 16 panel rows riding along (xr = C_RPC), so those rows come out solved.  CTA 0 stores the
+// factored block: L^T into the strict upper triangle in place (nobody reads it), L itself into the side buffer Ldiag --
+// the other CTAs of this launch may still be loading the unfactored block, so it is copied into place by
+// chol_copy_diag_kernel at the end.
+//
+// fuse != 0: the CTA then applies THIS panel's update to its own rows of the NEXT block column,
+//   A[r0.., t0..t0+127] -= X P^T,   X = its solved rows,  P = L[t0..t0+127][k0..k0+127]  (block row k+1 of the panel),
+// so that column is complete when the kernel ends and the next panel kernel can follow directly (r02: the separate
+// critical-path update kernel and its two cross-stream graph edges cost ~12 us per panel step on top of the ~9 us the
+// kernel ran).  P is produced by CTAs 1..8 of this launch: they publish their rows (fence + flags[panel]++), everyone
+// spins on the counter (bounded), then loads P through L2.  A CTA only ever waits for lower-numbered CTAs, which the
+// hardware dispatched before it, so the wait cannot deadlock even when the grid is not co-resident.  The subtraction
+// uses f64 REDs: the trailing-update kernel of the PREVIOUS panel may still be adding into the same tiles.
+constexpr int CHOL_SPIN_LIMIT = 1 << 22;
+constexpr int CHOL_INFO_STALLED = 0x7fffffff;
+
 template <int LEAF>
 __global__ void __launch_bounds__(C_THREADS, 1) chol_panel_kernel(int n, int lda, int k0, double* __restrict__ A,
                                                                    double* __restrict__ Ldiag /*[nblk][128*128]*/,
-                                                                   int* __restrict__ info) {
+                                                                   int* __restrict__ info, int* __restrict__ flags,
+                                                                   int fuse) {
   extern __shared__ __align__(16) double cp_smem[];
   double* Ls = cp_smem;                        // [128][CLD]
-  double* Ts = cp_smem + CB * CLD;             // [16][CLD]
+  double* Ts = cp_smem + CB * CLD;             // [16][CLD]: rows 128.. of the same array (ride-along rows)
   __shared__ double dinv[CB];
   __shared__ int fail_sm;
-  const int tid = threadIdx.x, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = min(CB, n - k0);
   const bool solver = blockIdx.x > 0;
   const int r0 = k0 + CB + ((int)blockIdx.x - 1) * C_RPC;
@@ -384,61 +456,27 @@ __global__ void __launch_bounds__(C_THREADS, 1) chol_panel_kernel(int n, int lda
       *reinterpret_cast<double2*>(Ls + i * CLD + j) = make_double2(j == i ? 1.0 : 0.0, j + 1 == i ? 1.0 : 0.0);
     }
   }
-  if (solver) {
-    for (int e = tid; e < C_RPC * (CB / 2); e += C_THREADS) {
-      const int r = e >> 6, j = (e & 63) * 2;
-      if (r0 + r < n) cp_async16(Ts + r * CLD + j, A + (size_t)(r0 + r) * lda + k0 + j);
-      else *reinterpret_cast<double2*>(Ts + r * CLD + j) = make_double2(0.0, 0.0);
-    }
+  for (int e = tid; e < C_RPC * (CB / 2); e += C_THREADS) {
+    const int r = e >> 6, j = (e & 63) * 2;
+    if (solver && r0 + r < n) cp_async16(Ts + r * CLD + j, A + (size_t)(r0 + r) * lda + k0 + j);
+    else *reinterpret_cast<double2*>(Ts + r * CLD + j) = make_double2(0.0, 0.0);
   }
   cp_async_commit();
   cp_async_wait<0>();
   __syncthreads();
-  const int fail = cta_chol128<LEAF, false>(Ls, dinv, &fail_sm, tid);
+  const int fail = cta_chol128<LEAF, false>(Ls, dinv, &fail_sm, tid, C_RPC);
   if (fail && blockIdx.x == 0 && tid == 0) atomicCAS(info, 0, k0 + fail);
-  // mirror: Ls[m][j] = L[j][m] for j > m (the solve below reads column m of L as a contiguous row; CTA 0 stores it as L^T)
-  for (int e = tid; e < CB * CB; e += C_THREADS) {
-    const int i = e >> 7, j = e & 127;
-    if (j > i) Ls[i * CLD + j] = Ls[j * CLD + i];
-  }
-  __syncthreads();
   if (!solver) {
     double* dst = Ldiag + (size_t)(k0 / CB) * CB * CB;
     for (int e = tid; e < CB * CB; e += C_THREADS) {
       const int i = e >> 7, j = e & 127;
       if (i < nb && j < nb) {
-        if (j > i) A[(size_t)(k0 + i) * lda + k0 + j] = Ls[i * CLD + j];
+        if (j > i) A[(size_t)(k0 + i) * lda + k0 + j] = Ls[j * CLD + i];      // L^T (transposed read: CTA 0 is off the critical path)
         else dst[e] = Ls[i * CLD + j];
       }
     }
     return;
   }
-  // X L^T = A_ik, right-looking: 16 threads per row, thread q owns columns j = q + 16*jj
-  {
-    const int r = tid >> 4, q = tid & 15;
-    double a[8];
-#pragma unroll
-    for (int jj = 0; jj < 8; ++jj) a[jj] = Ts[r * CLD + q + 16 * jj];
-#pragma unroll
-    for (int m = 0; m < CB; ++m) {
-      const int qm = m & 15, jm = m >> 4;
-      double x = a[jm] * dinv[m];
-      x = __shfl_sync(0xffffffffu, x, qm, 16);
-      if (q == qm) a[jm] = x;
-      const double* lrow = Ls + m * CLD;
-#pragma unroll
-      for (int jj = 0; jj < 8; ++jj) {
-        if (16 * jj + 15 > m) {                      // compile-time prune; exact test below
-          const int j = q + 16 * jj;
-          if (j > m) a[jj] = fma(-x, lrow[j], a[jj]);
-        }
-      }
-    }
-#pragma unroll
-    for (int jj = 0; jj < 8; ++jj) Ts[r * CLD + q + 16 * jj] = a[jj];
-  }
-  __syncthreads();
-  (void)lane;
   // row-major store of the solved rows ...
   for (int e = tid; e < C_RPC * CB; e += C_THREADS) {
     const int r = e >> 7, c = e & 127;
@@ -449,11 +487,86 @@ __global__ void __launch_bounds__(C_THREADS, 1) chol_panel_kernel(int n, int lda
     const int c = e >> 4, r = e & 15;
     if (r0 + r < n && c < nb) A[(size_t)(k0 + c) * lda + r0 + r] = Ts[r * CLD + c];
   }
+  if (!fuse) return;
+
+  // ---- fused update of block column k+1 with this panel
+  const int t0 = k0 + CB;
+  const int nprod = min(CB / C_RPC, (int)gridDim.x - 1);       // CTAs 1..nprod own block row k+1
+  int* flag = flags + k0 / CB;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    if ((int)blockIdx.x <= nprod) atomicAdd(flag, 1);           // after the fence: this CTA's rows are visible device-wide
+    int spins = 0, seen;
+    do {
+      asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flag) : "memory");
+    } while (seen < nprod && ++spins < CHOL_SPIN_LIMIT);
+    if (seen < nprod) atomicCAS(info, 0, CHOL_INFO_STALLED);
+  }
+  __syncthreads();
+  // P = rows t0 .. t0+127 of the panel -> Ls (the factored block is no longer needed here); two K halves
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    for (int e = tid; e < CB * 16; e += C_THREADS) {
+      const int row = e >> 4, ch = (e & 15) * 4 + half * 64;
+      double* dst = Ls + row * CLD + ch;
+      if (t0 + row < n) {
+        const double* src = A + (size_t)(t0 + row) * lda + k0 + ch;
+        cp_async16(dst, src);
+        cp_async16(dst + 2, src + 2);
+      } else {
+        *reinterpret_cast<double2*>(dst) = make_double2(0.0, 0.0);
+        *reinterpret_cast<double2*>(dst + 2) = make_double2(0.0, 0.0);
+      }
+    }
+    cp_async_commit();
+  }
+  {
+    const int g = lane >> 2, q = lane & 3;
+    double c[2][2][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 2; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+    const double* arow = Ts + g * CLD + q;
+    const double* brow = Ls + (warp * 16 + g) * CLD + q;
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      if (half == 0) cp_async_wait<1>();
+      else cp_async_wait<0>();
+      __syncthreads();
+#pragma unroll 4
+      for (int k4 = half * 16; k4 < half * 16 + 16; ++k4) {
+        double a[2], b[2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i) a[i] = arow[i * 8 * CLD + k4 * 4];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) b[j] = brow[j * 8 * CLD + k4 * 4];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) chol_dmma(c[i][j][0], c[i][j][1], a[i], b[j]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int r = r0 + i * 8 + g;
+      if (r >= n) continue;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int col = t0 + warp * 16 + j * 8 + 2 * q;
+        double* p = A + (size_t)r * lda + col;
+        if (col <= r) atomicAdd(p, -c[i][j][0]);
+        if (col + 1 <= r) atomicAdd(p + 1, -c[i][j][1]);
+      }
+    }
+  }
 }
 
 // A[t0.., t0..] -= P P^T (lower part), P = A[t0.., k0..k0+127].  Tiles of TM rows x 64 columns, 8 warps.
 //   TM = 64 (trailing update off the critical path): tile (bi, bj), bj <= bi, warps 2x4, warp tile 32x16; mode 2 = tile
-//            columns >= 2, mode 0 = all.
+//            columns >= 2, mode 0 = all; mode 3 = mode 2 with f64 REDs on tile columns 2 and 3 (the block column the
+//            fused panel kernel of the next step is adding into at the same time).
 //   TM = 32 (mode 1, the next panel's 128 columns = tile columns 0 and 1, ON the critical path): twice as many CTAs so
 //            the ~140 tiles of a 2400-row matrix fill the 148 SMs with one short tile each; warps 1x8, warp tile 32x8.
 template <int TM>
@@ -476,7 +589,7 @@ __global__ void __launch_bounds__(C_THREADS, 1) chol_update_kernel(int n, int ld
       while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
       while (bi * (bi + 1) / 2 > t) --bi;
       bj = t - bi * (bi + 1) / 2;
-      if (mode == 2) { bi += 2; bj += 2; }
+      if (mode >= 2) { bi += 2; bj += 2; }
     }
   }
   const bool diag = TM == 64 && bi == bj;
@@ -539,7 +652,10 @@ __global__ void __launch_bounds__(C_THREADS, 1) chol_update_kernel(int n, int ld
       const int col = rj + wn * (8 * NJ) + j * 8 + 2 * q;
       if (col > r) continue;                         // lower triangle only (col <= r < n)
       double* p = A + (size_t)r * lda + col;
-      if (col + 1 <= r) {
+      if (TM == 64 && mode == 3 && bj < 4) {
+        atomicAdd(p, -c[i][j][0]);
+        if (col + 1 <= r) atomicAdd(p + 1, -c[i][j][1]);
+      } else if (col + 1 <= r) {
         double2 v = *reinterpret_cast<double2*>(p);
         v.x -= c[i][j][0];
         v.y -= c[i][j][1];
@@ -562,14 +678,16 @@ __global__ void chol_copy_diag_kernel(int n, int lda, const double* __restrict__
 
 size_t chol_workspace_doubles(int n) {
   const int nblk = (n + CB - 1) / CB;
-  return (size_t)nblk * CB * CB;          // factored diagonal blocks, parked until the end of the factorisation
+  // factored diagonal blocks, parked until the end of the factorisation + one int per panel (the fused update's
+  // "block row published" counters)
+  return (size_t)nblk * CB * CB + (size_t)(nblk + 1) / 2 + 1;
 }
 
 namespace {
 
 struct CholStreams {
   cudaStream_t side = nullptr, cap = nullptr;
-  cudaEvent_t ev_col = nullptr, ev_panel = nullptr;
+  cudaEvent_t ev_col = nullptr, ev_panel = nullptr, ev_upd[2] = {nullptr, nullptr};
   bool ready = false;
 };
 
@@ -582,15 +700,17 @@ int chol_streams(CholStreams** out) {
     VGG_CUDA_CHECK(cudaStreamCreateWithFlags(&s.cap, cudaStreamNonBlocking));
     VGG_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_col, cudaEventDisableTiming));
     VGG_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_panel, cudaEventDisableTiming));
+    VGG_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_upd[0], cudaEventDisableTiming));
+    VGG_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_upd[1], cudaEventDisableTiming));
     s.ready = true;
   }
   *out = &s;
   return VGG_OK;
 }
 
-// VGG_CHOL_LEAF=0|1 (A/B): 8x8 leaf with one / two pivots per step
+// VGG_CHOL_LEAF=0|1 (A/B): 8x8 leaf with one / two (default) pivots per step
 int chol_leaf() {
-  static const int v = [] { const char* e = getenv("VGG_CHOL_LEAF"); return (e && e[0] == '1') ? 1 : 0; }();
+  static const int v = [] { const char* e = getenv("VGG_CHOL_LEAF"); return (e && e[0] == '0') ? 0 : 1; }();
   return v;
 }
 
@@ -609,22 +729,63 @@ int chol_set_attrs() {
   return VGG_OK;
 }
 
-// the launch sequence on (st, side); with lookahead == false everything goes to st in program order
-int chol_enqueue(int n, int lda, double* A, double* Ldiag, int* info, cudaStream_t st, CholStreams* cs, bool lookahead) {
+// VGG_CHOL_FUSE=0 (A/B): the r02 schedule with a separate critical-path update kernel per panel
+bool chol_fuse() {
+  static const bool v = [] { const char* e = getenv("VGG_CHOL_FUSE"); return !(e && e[0] == '0'); }();
+  return v;
+}
+
+// The launch sequence on (st, side).
+//   fused (default): step(b) = panel b + its update of block column b+1, all on st back to back; the rest of panel b's
+//     trailing update (block columns >= b+2) runs on the side stream behind step(b) and has to be finished before
+//     step(b+2) -- it shares block column b+2 with step(b+1)'s fused update, both sides use REDs there.
+//   unfused lookahead: update<32>(b) [critical tiles] -> panel(b+1) on the side stream, update<64>(b) on st.
+//   lookahead == false: everything on st in program order.
+int chol_enqueue(int n, int lda, double* A, double* Ldiag, int* info, int* flags, cudaStream_t st, CholStreams* cs,
+                 bool lookahead) {
   const int nblk = (n + CB - 1) / CB;
   const size_t smem_p = sizeof(double) * (CB + C_RPC) * CLD;
   const size_t smem_u = sizeof(double) * 2 * CT * CLD;
+  const bool fuse = lookahead && chol_fuse();
   auto panel = [&](int b, cudaStream_t s2) -> int {
     const int k0 = b * CB;
     const int below = n - (k0 + CB);
     const int chunks = below > 0 ? (below + C_RPC - 1) / C_RPC : 0;
-    if (chol_leaf() == 1) chol_panel_kernel<1><<<1 + chunks, C_THREADS, smem_p, s2>>>(n, lda, k0, A, Ldiag, info);
-    else chol_panel_kernel<0><<<1 + chunks, C_THREADS, smem_p, s2>>>(n, lda, k0, A, Ldiag, info);
+    if (chol_leaf() == 1)
+      chol_panel_kernel<1><<<1 + chunks, C_THREADS, smem_p, s2>>>(n, lda, k0, A, Ldiag, info, flags, fuse ? 1 : 0);
+    else
+      chol_panel_kernel<0><<<1 + chunks, C_THREADS, smem_p, s2>>>(n, lda, k0, A, Ldiag, info, flags, fuse ? 1 : 0);
     VGG_LAUNCH_CHECK();
     return VGG_OK;
   };
   int rc;
   if ((rc = panel(0, st))) return rc;
+  if (fuse) {
+    int pending = -1;                                   // index of the last ev_upd recorded and not yet waited for by st
+    for (int b = 0; b + 1 < nblk; ++b) {
+      const int k0 = b * CB, t0 = k0 + CB;
+      const int T = (n - t0 + CT - 1) / CT;
+      const int n_rest = T > 2 ? (T - 2) * (T - 1) / 2 : 0;
+      int prev = pending;
+      if (n_rest > 0) {
+        VGG_CUDA_CHECK(cudaEventRecord(cs->ev_col, st));                 // step(b) done
+        VGG_CUDA_CHECK(cudaStreamWaitEvent(cs->side, cs->ev_col, 0));
+        chol_update_kernel<64><<<n_rest, C_THREADS, smem_u, cs->side>>>(n, lda, k0, t0, 3, A);
+        VGG_LAUNCH_CHECK();
+        VGG_CUDA_CHECK(cudaEventRecord(cs->ev_upd[b & 1], cs->side));
+        pending = b & 1;
+      } else {
+        pending = -1;
+      }
+      // step(b+1) factors block column b+1: the trailing update of panel b-1 (the last one that touches it) must be done
+      if (prev >= 0) VGG_CUDA_CHECK(cudaStreamWaitEvent(st, cs->ev_upd[prev], 0));
+      if ((rc = panel(b + 1, st))) return rc;
+    }
+    if (pending >= 0) VGG_CUDA_CHECK(cudaStreamWaitEvent(st, cs->ev_upd[pending], 0));
+    chol_copy_diag_kernel<<<nblk, 256, 0, st>>>(n, lda, Ldiag, A);
+    VGG_LAUNCH_CHECK();
+    return VGG_OK;
+  }
   for (int b = 0; b + 1 < nblk; ++b) {
     const int k0 = b * CB, t0 = k0 + CB;
     const int T = (n - t0 + CT - 1) / CT;
@@ -664,12 +825,15 @@ int chol_lower_inplace(int n, int lda, double* A, double* Ldiag, int* info, cuda
   int rc;
   if ((rc = chol_set_attrs())) return rc;
   VGG_CUDA_CHECK(cudaMemsetAsync(info, 0, sizeof(int), st));
+  const int nblk0 = (n + CB - 1) / CB;
+  int* flags = reinterpret_cast<int*>(Ldiag + (size_t)nblk0 * CB * CB);
+  VGG_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)nblk0, st));
   static const bool lookahead = [] { const char* e = getenv("VGG_CHOL_LOOKAHEAD"); return !(e && e[0] == '0'); }();
   static const bool use_graph = [] { const char* e = getenv("VGG_CHOL_GRAPH"); return !(e && e[0] == '0'); }();
   const int nblk = (n + CB - 1) / CB;
   CholStreams* cs = nullptr;
   if ((rc = chol_streams(&cs))) return rc;
-  if (nblk < 3 || !use_graph) return chol_enqueue(n, lda, A, Ldiag, info, st, cs, lookahead && nblk >= 3);
+  if (nblk < 3 || !use_graph) return chol_enqueue(n, lda, A, Ldiag, info, flags, st, cs, lookahead && nblk >= 3);
   // one captured graph per (matrix, order): ~60 launches + events become a single cudaGraphLaunch
   typedef std::tuple<double*, int, int, int*, double*, bool> Key;
   static thread_local std::map<Key, cudaGraphExec_t> cache;
@@ -679,7 +843,7 @@ int chol_lower_inplace(int n, int lda, double* A, double* Ldiag, int* info, cuda
     const long long launches_before = g_launch_count;
     cudaGraph_t graph = nullptr;
     VGG_CUDA_CHECK(cudaStreamBeginCapture(cs->cap, cudaStreamCaptureModeThreadLocal));
-    rc = chol_enqueue(n, lda, A, Ldiag, info, cs->cap, cs, lookahead);
+    rc = chol_enqueue(n, lda, A, Ldiag, info, flags, cs->cap, cs, lookahead);
     const cudaError_t ce = cudaStreamEndCapture(cs->cap, &graph);
     g_launch_count = launches_before;
     if (rc) {
@@ -697,7 +861,7 @@ int chol_lower_inplace(int n, int lda, double* A, double* Ldiag, int* info, cuda
     it = cache.emplace(key, exec).first;
   }
   VGG_CUDA_CHECK(cudaGraphLaunch(it->second, st));
-  g_launch_count += 2 + 3 * (nblk - 1);          // kernels inside the graph
+  g_launch_count += 2 + (lookahead && chol_fuse() ? 2 : 3) * (nblk - 1);          // kernels inside the graph
   return VGG_OK;
 }
 
@@ -714,13 +878,13 @@ extern "C" int vgg_dev_chol128_probe(int leaf, int reps, const double* A_host, d
   VGG_CUDA_CHECK(cudaMalloc(&dP, sizeof(long long) * 13));
   VGG_CUDA_CHECK(cudaMemcpy(dA, A_host, sizeof(double) * CB * CB, cudaMemcpyHostToDevice));
   VGG_CUDA_CHECK(cudaMemset(dP, 0, sizeof(long long) * 13));
-  const int smem = (int)(sizeof(double) * CB * CLD);
+  const int smem = (int)(sizeof(double) * (CB + C_RPC) * CLD);
   if (leaf == 1) {
     VGG_CUDA_CHECK(cudaFuncSetAttribute(chol128_probe_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    chol128_probe_kernel<1><<<1, C_THREADS, smem>>>(dA, dL, dP, reps);
+    chol128_probe_kernel<1><<<1, C_THREADS, smem>>>(dA, dL, dP, reps, C_RPC);
   } else {
     VGG_CUDA_CHECK(cudaFuncSetAttribute(chol128_probe_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    chol128_probe_kernel<0><<<1, C_THREADS, smem>>>(dA, dL, dP, reps);
+    chol128_probe_kernel<0><<<1, C_THREADS, smem>>>(dA, dL, dP, reps, C_RPC);
   }
   VGG_LAUNCH_CHECK();
   VGG_CUDA_CHECK(cudaDeviceSynchronize());
