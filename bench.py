@@ -52,6 +52,16 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_tensor_peak():
+    """Measured dense bf16 TFLOP/s of this pool's B200s (burst: a kernel timed alone), else the profiling recipe's figure."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        if "bf16_tflops" in d:
+            return float(d["bf16_tflops"]), "measured cuBLAS bf16 (MEASURED_PEAKS.json)"
+    return 1650.0, "fallback (B200_PROFILING.md)"
+
+
 class ClockSampler:
     """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md recipe), sampled in-process through
     NVML every 250 ms (an `nvidia-smi -lms` child process was measured to slow the timed region by ~30 %)."""
@@ -287,8 +297,19 @@ def corr_section(dev, hbm_peak):
             foot = sum(min((2 * r + 2), H >> l) * min((2 * r + 2), W >> l) for l in range(L)) * C * 2
             ab = B * S * N * (foot + C * 4 + 8 + L * K * K * 4)
             rec = {"shape": [B, S, C, H, W], "queries": N, "levels": L, "radius": r, "ms_fused": ms,
-                   "algorithmic_bytes": ab, "achieved_gbs": ab / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": ab / (ms * 1e-3) / 1e9 / hbm_peak,
                    "pairs_per_s": B * S * N / (ms * 1e-3)}
+            if getattr(ours._pyr, "tc_tiles", None) is not None:
+                # tcgen05 path (csrc/corr_tc.cu): the dense per-level correlation runs on the tensor cores (kind::f16,
+                # fp32 accumulators in TMEM) and is sampled from TMEM -- tensor-bound, not HBM-bound
+                fl = 2.0 * B * S * N * C * sum((H >> l) * (W >> l) for l in range(L))
+                tpk, tsrc = load_tensor_peak()
+                rec.update({"kernel": "corr_tc_kernel (tcgen05.mma kind::f16, M=128 N=256, TMEM accumulators)", "bound": "tensor",
+                            "flops": fl, "achieved_tflops": fl / (ms * 1e-3) / 1e12, "tensor_peak_tflops": tpk,
+                            "tensor_peak_source": tsrc, "frac_of_tensor_peak": fl / (ms * 1e-3) / 1e12 / tpk,
+                            "ncu": "profiles/r02_ncu_corr_tc8.txt: sm__pipe_tensor_subpipe_hmma_cycles_active 38.7 %"})
+            else:
+                rec.update({"kernel": "corr_sample footprint kernel (CUDA cores)", "bound": "hbm", "algorithmic_bytes": ab,
+                            "achieved_gbs": ab / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": ab / (ms * 1e-3) / 1e9 / hbm_peak})
             res = run_ours()
             del ours
             try:

@@ -22,7 +22,8 @@ if len(sys.argv) > 1 and sys.argv[1] == "probe":
 if len(sys.argv) > 1 and sys.argv[1] == "rate":
     L = _lib.lib()
     torch.zeros(1, device=dev)
-    for mode, name in [(0, "SW64  N=128"), (1, "SW64  N=256"), (2, "SW128 N=128"), (3, "SW128 N=256"), (4, "none  N=128"), (5, "none  N=256")]:
+    for mode, name in [(0, "SW64  N=128"), (1, "SW64  N=256"), (2, "SW128 N=128"), (3, "SW128 N=256"), (4, "none  N=128"), (5, "none  N=256"),
+                       (8, "SW64  N=128 A-in-TMEM"), (9, "SW64  N=256 A-in-TMEM")]:
         c = ctypes.c_double()
         _lib.check(L.vgg_syrk_ozaki_mma_rate(4096, mode, ctypes.byref(c), None), "rate")
         n = 256 if mode & 1 else 128

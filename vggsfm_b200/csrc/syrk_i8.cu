@@ -39,6 +39,9 @@ constexpr int OZ_STAGES = 2;
 constexpr int OZ_STAGE_TILES = 14;
 constexpr int OZ_STAGE_BYTES = OZ_STAGE_TILES * OZ_TILE_BYTES;   // 112 KB
 constexpr int OZ_THREADS = 320;                  // producer warp, MMA warp, 8 epilogue warps
+constexpr int OZ_THREADS_TS = 448;               // + 4 warps that stage the A operand in tensor memory (A-in-TMEM variant)
+constexpr int OZ_TS_ACOL = 384;                  // TMEM columns 384..495: two buffers x 7 slices x 8 columns (K = 32 int8)
+constexpr int OZ_TS_ABUF = 56;
 constexpr int OZ_MAX_PAIRS = 20;
 constexpr int OZ_MAX_ITEM_KB = 256;               // k blocks per work item: 7 pairs x 128^2 x 256 x 64 < 2^31 (exact int32 accumulators)
 constexpr int OZ_PREFETCH = 4;                   // k blocks of L2 prefetch distance ahead of the bulk copies
@@ -164,6 +167,19 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// same with the A operand in tensor memory (128 lanes = rows, 8 32-bit columns = 32 int8 of K per row): the MMA then
+// reads only B from shared memory
+__device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // arrive on an mbarrier once all previously issued tcgen05.mma of this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -184,6 +200,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "r"(taddr));
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// 32 lanes x 8 columns: lane l of the warp writes its 32 bytes (one row of an int8 A operand, K = 32) into TMEM lane
+// (warp % 4) * 32 + l, columns taddr .. taddr + 7
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint4& a, const uint4& b) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};\n" ::"r"(taddr), "r"(a.x), "r"(a.y),
+               "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // shared-memory matrix descriptor: K-major, 64-byte swizzle, 8-row atoms 512 B apart, sm_100 descriptor version
 __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
@@ -193,7 +217,14 @@ constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) 
 
 // ---------------------------------------------------------------------------------------------------------
 // 3. persistent tcgen05 SYRK
-__global__ void __launch_bounds__(OZ_THREADS, 1)
+// TS = true: A-in-TMEM variant.  r01 found the SS kernel bound by shared-memory bandwidth, not by the tensor pipe: every
+// N = 128 MMA re-reads its 4 KB A operand and its 4 KB B operand (28 pairs x 2 x 8 KB = 448 KB per 64-byte k-block, plus
+// the 112 KB the bulk copies write, at 128 B/clk = 4.4 k clk against 3.6 k clk of tensor work).  Here four extra warps
+// copy the <= 7 A slices of a k-block from shared memory into tensor memory once (tcgen05.st, 8 columns per slice and
+// K = 32 half, double buffered) and the MMAs take A from there: 224 KB of B reads + 56 KB of staging reads per k-block.
+// Tensor memory: three 128-column accumulators (order groups of <= 3) + 112 columns of A.
+template <bool TS>
+__global__ void __maxnreg__(TS ? 144 : 168)      // 448 x 144 / 320 x 168 registers: one CTA per SM either way (224 KB smem)
     oz_syrk_kernel(const __grid_constant__ OzPlan plan, const OzWork* __restrict__ work, int nwork, int KB,
                    const int8_t* __restrict__ slices, size_t slice_stride, const int* __restrict__ expo,
                    const double* __restrict__ pow2, int Dpad, double* __restrict__ Cmat, ptrdiff_t mc_off,
@@ -204,7 +235,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
   uint64_t* empty = full + OZ_STAGES;
   uint64_t* tmem_full = empty + OZ_STAGES;
   uint64_t* tmem_empty = tmem_full + 1;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+  uint64_t* a_full = tmem_empty + 1;             // [2] (TS): A buffer staged in tensor memory, one arrive per staging warp
+  uint64_t* a_empty = a_full + 2;                // [2] (TS): the MMAs that read the buffer have completed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(a_empty + 2);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
@@ -214,6 +247,10 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     }
     mbar_init(tmem_full, 1);
     mbar_init(tmem_empty, 8);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&a_full[s], 4);
+      mbar_init(&a_empty[s], 1);
+    }
     mbar_fence_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, 512);
@@ -260,6 +297,9 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
     // ===== MMA issuer =====
     if (lane == 0) {
       int stage = 0, phase = 0, it = 0;
+      int abuf = 0, aphase = 0;
+      (void)abuf;
+      (void)aphase;
       for (int w = blockIdx.x; w < nwork; w += gridDim.x, ++it) {
         const OzWork wk = work[w];
         const OzGroup& g = plan.g[wk.group];
@@ -271,15 +311,32 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t base = smem_u32(tiles + (size_t)stage * OZ_STAGE_BYTES);
-          for (int pr = 0; pr < g.n_pairs; ++pr) {
-            const uint32_t a_addr = base + (uint32_t)g.pair_a[pr] * OZ_TILE_BYTES;
-            const uint32_t b_addr = base + (uint32_t)(diag ? g.pair_b_diag[pr] : g.n_a + g.pair_b[pr]) * OZ_TILE_BYTES;
-            const uint32_t acc = g.pair_acc[pr];
-#pragma unroll
+          if (TS) {
             for (int ks = 0; ks < OZ_BK / 32; ++ks) {
-              umma_i8(tmem_base + acc * 128u, smem_desc_sw64(a_addr + ks * 32), smem_desc_sw64(b_addr + ks * 32),
-                      OZ_IDESC, (acc_used >> acc) & 1u);
-              acc_used |= 1u << acc;
+              mbar_wait(&a_full[abuf], aphase);
+              tc_fence_after();
+              const uint32_t a_base = tmem_base + (uint32_t)(OZ_TS_ACOL + abuf * OZ_TS_ABUF);
+              for (int pr = 0; pr < g.n_pairs; ++pr) {
+                const uint32_t b_addr = base + (uint32_t)(diag ? g.pair_b_diag[pr] : g.n_a + g.pair_b[pr]) * OZ_TILE_BYTES;
+                const uint32_t acc = g.pair_acc[pr];
+                umma_i8_ts(tmem_base + acc * 128u, a_base + (uint32_t)g.pair_a[pr] * 8u, smem_desc_sw64(b_addr + ks * 32),
+                           OZ_IDESC, (acc_used >> acc) & 1u);
+                acc_used |= 1u << acc;
+              }
+              umma_commit(&a_empty[abuf]);
+              if ((abuf ^= 1) == 0) aphase ^= 1;
+            }
+          } else {
+            for (int pr = 0; pr < g.n_pairs; ++pr) {
+              const uint32_t a_addr = base + (uint32_t)g.pair_a[pr] * OZ_TILE_BYTES;
+              const uint32_t b_addr = base + (uint32_t)(diag ? g.pair_b_diag[pr] : g.n_a + g.pair_b[pr]) * OZ_TILE_BYTES;
+              const uint32_t acc = g.pair_acc[pr];
+#pragma unroll
+              for (int ks = 0; ks < OZ_BK / 32; ++ks) {
+                umma_i8(tmem_base + acc * 128u, smem_desc_sw64(a_addr + ks * 32), smem_desc_sw64(b_addr + ks * 32),
+                        OZ_IDESC, (acc_used >> acc) & 1u);
+                acc_used |= 1u << acc;
+              }
             }
           }
           umma_commit(&empty[stage]);
@@ -289,6 +346,40 @@ __global__ void __launch_bounds__(OZ_THREADS, 1)
           }
         }
         umma_commit(tmem_full);
+      }
+    }
+  } else if (TS && warp >= 10) {
+    // ===== A staging (4 warps, TMEM lane quarter = warp % 4): shared memory -> tensor memory, one K = 32 half at a time =====
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    const uint32_t sw = (uint32_t)((row >> 1) & 3);
+    int stage = 0, phase = 0, abuf = 0, aphase = 0;
+    for (int w = blockIdx.x; w < nwork; w += gridDim.x) {
+      const OzWork wk = work[w];
+      const OzGroup& g = plan.g[wk.group];
+      for (int kb = wk.kb0; kb < wk.kb1; ++kb) {
+        mbar_wait(&full[stage], phase);                       // this k-block's tile images have landed
+        const uint8_t* st_tiles = tiles + (size_t)stage * OZ_STAGE_BYTES + (size_t)row * OZ_BK;
+        for (int ks = 0; ks < OZ_BK / 32; ++ks) {
+          mbar_wait(&a_empty[abuf], (uint32_t)(aphase ^ 1));  // the MMAs that read this buffer two halves ago are done
+          tc_fence_after();
+          const uint32_t t_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(OZ_TS_ACOL + abuf * OZ_TS_ABUF);
+          for (int i = 0; i < g.n_a; ++i) {
+            const uint8_t* trow = st_tiles + (size_t)i * OZ_TILE_BYTES;
+            const uint4 v0 = *reinterpret_cast<const uint4*>(trow + ((((uint32_t)(2 * ks)) ^ sw) << 4));
+            const uint4 v1 = *reinterpret_cast<const uint4*>(trow + ((((uint32_t)(2 * ks + 1)) ^ sw) << 4));
+            tmem_st8(t_base + (uint32_t)i * 8u, v0, v1);
+          }
+          tmem_wait_st();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[abuf]);
+          if ((abuf ^= 1) == 0) aphase ^= 1;
+        }
+        if (++stage == OZ_STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
       }
     }
   } else {
@@ -693,7 +784,8 @@ __global__ void __launch_bounds__(128, 1) oz_mma_rate_kernel(int iters, int mode
     const uint32_t base = smem_u32(tiles);
     const int n = (mode & 1) ? 256 : 128;
     const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((128u >> 4) << 24);
-    const int layout = mode >> 1;            // 0: SW64 (64 B rows), 1: SW128 (128 B rows), 2: no swizzle
+    const int layout = (mode >> 1) & 3;      // 0: SW64 (64 B rows), 1: SW128 (128 B rows), 2: no swizzle
+    const bool a_tmem = (mode & 8) != 0;     // A operand from tensor memory (columns 384..), B from shared memory
     const long long t0 = clock64();
     for (int it = 0; it < iters; ++it) {
       const uint32_t a = base + (uint32_t)(it & 1) * 32, b = base + 32768 + (uint32_t)(it & 1) * 32;
@@ -707,7 +799,8 @@ __global__ void __launch_bounds__(128, 1) oz_mma_rate_kernel(int iters, int mode
         da = (uint64_t)((a >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
         db = (uint64_t)((b >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
       }
-      umma_i8(tb, da, db, idesc, 1u);
+      if (a_tmem) umma_i8_ts(tb, tb + 384u + (uint32_t)(it & 1) * 8u, db, idesc, 1u);
+      else umma_i8(tb, da, db, idesc, 1u);
     }
     umma_commit(&bar);
     mbar_wait(&bar, 0);
@@ -720,16 +813,16 @@ __global__ void __launch_bounds__(128, 1) oz_mma_rate_kernel(int iters, int mode
 
 // ---------------------------------------------------------------------------------------------------------
 // host side: order groups and work list
-bool build_plan(int s, OzPlan* plan) {
+bool build_plan(int s, OzPlan* plan, int max_acc) {
   if (s < 3 || s > 7) return false;
   plan->slices = s;
   const int B = 8 * s - 2;
   const int tlast = s + 1;                       // orders 2 .. s+1 are kept
   int ng = 0;
-  for (int t0 = 2; t0 <= tlast; t0 += 4) {
+  for (int t0 = 2; t0 <= tlast; t0 += max_acc) {
     if (ng >= OZ_MAX_GROUPS) return false;
     OzGroup& g = plan->g[ng++];
-    const int t1 = std::min(t0 + 3, tlast);
+    const int t1 = std::min(t0 + max_acc - 1, tlast);
     g.n_acc = t1 - t0 + 1;
     g.exp_base = 8 * (2 * s - t1) - 2 * B;
     int slot_a[8], slot_b[8];
@@ -818,6 +911,12 @@ struct OzHostState {
   size_t pinned2_cap = 0;
 };
 
+// VGG_SYRK_TS=1: A operand from tensor memory; default: both operands from shared memory (the r01 kernel)
+bool use_ts_kernel() {
+  static const bool v = [] { const char* e = getenv("VGG_SYRK_TS"); return e && e[0] == '1'; }();
+  return v;
+}
+
 bool use_pair_kernel() {
   static int v = -1;
   if (v < 0) {
@@ -867,11 +966,12 @@ int launch_syrk_i8(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t
   const int nb = Dpad / OZ_BM;
   OzHostState& hs = g_oz;
   if (hs.Kpad != Kpad || hs.Dpad != Dpad || hs.slices != s) {
-    VGG_REQUIRE(build_plan(s, &hs.plan), "syrk_i8: slices must be in [3,7]");
+    VGG_REQUIRE(build_plan(s, &hs.plan, use_ts_kernel() ? 3 : 4), "syrk_i8: slices must be in [3,7]");
     int dev = 0;
     VGG_CUDA_CHECK(cudaGetDevice(&dev));
     VGG_CUDA_CHECK(cudaDeviceGetAttribute(&hs.sms, cudaDevAttrMultiProcessorCount, dev));
-    VGG_CUDA_CHECK(cudaFuncSetAttribute(oz_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES));
+    VGG_CUDA_CHECK(cudaFuncSetAttribute(oz_syrk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES));
+    VGG_CUDA_CHECK(cudaFuncSetAttribute(oz_syrk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)OZ_SMEM_BYTES));
     // work items: (tile, group, k range), longest first (build_work_list picks the k-split granularity)
     {
       std::vector<OzTileJob> jobs;
@@ -940,8 +1040,12 @@ int launch_syrk_i8(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t
                                                                          expo, pow2, Dpad, Cmat, mc_off, g_fill_upper);
   } else {
     const int grid = std::min(hs.sms, nwork);
-    oz_syrk_kernel<<<grid, OZ_THREADS, OZ_SMEM_BYTES, st>>>(hs.plan, work_d, nwork, KB, slices, slice_stride, expo, pow2,
-                                                          Dpad, Cmat, mc_off, g_fill_upper, g_fabric_dev);
+    if (use_ts_kernel())
+      oz_syrk_kernel<true><<<grid, OZ_THREADS_TS, OZ_SMEM_BYTES, st>>>(hs.plan, work_d, nwork, KB, slices, slice_stride, expo,
+                                                                    pow2, Dpad, Cmat, mc_off, g_fill_upper, g_fabric_dev);
+    else
+      oz_syrk_kernel<false><<<grid, OZ_THREADS, OZ_SMEM_BYTES, st>>>(hs.plan, work_d, nwork, KB, slices, slice_stride, expo,
+                                                                  pow2, Dpad, Cmat, mc_off, g_fill_upper, g_fabric_dev);
   }
   VGG_LAUNCH_CHECK();
   return VGG_OK;

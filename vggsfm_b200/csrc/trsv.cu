@@ -95,10 +95,17 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
       xs[tid] = v;
     }
     __syncthreads();
-    double s = 0.0;
+    // four independent chains: the FP64 pipe's dependent-issue latency (~20 cycles) makes one 16-long chain 320 cycles
+    // of every hop's critical path
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) s = fma(tile[k], xs[seg * 16 + k], s);
-    acc += s;
+    for (int k = 0; k < 16; k += 4) {
+      s0 = fma(tile[k], xs[seg * 16 + k], s0);
+      s1 = fma(tile[k + 1], xs[seg * 16 + k + 1], s1);
+      s2 = fma(tile[k + 2], xs[seg * 16 + k + 2], s2);
+      s3 = fma(tile[k + 3], xs[seg * 16 + k + 3], s3);
+    }
+    acc += (s0 + s1) + (s2 + s3);
     __syncthreads();                           // xs is rewritten in the next round
   };
   int j = nb - 1;
@@ -123,12 +130,16 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
   __syncthreads();
   // ---- x_b = inv(U_bb) acc: four threads per row, published element by element
   {
-    double s = 0.0;
+    double q0 = 0.0, q1 = 0.0, q2 = 0.0, q3 = 0.0;
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
+    for (int k = 0; k < 16; k += 4) {
       const int c = seg * 16 + k;
-      s = fma(c >= r ? Vi[r][c] : 0.0, accs[c], s);
+      q0 = fma(c >= r ? Vi[r][c] : 0.0, accs[c], q0);
+      q1 = fma(c + 1 >= r ? Vi[r][c + 1] : 0.0, accs[c + 1], q1);
+      q2 = fma(c + 2 >= r ? Vi[r][c + 2] : 0.0, accs[c + 2], q2);
+      q3 = fma(c + 3 >= r ? Vi[r][c + 3] : 0.0, accs[c + 3], q3);
     }
+    double s = (q0 + q1) + (q2 + q3);
     s += __shfl_xor_sync(0xffffffffu, s, 1);
     s += __shfl_xor_sync(0xffffffffu, s, 2);
     if (seg == 0 && r < rows) {
