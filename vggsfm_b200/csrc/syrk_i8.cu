@@ -224,7 +224,7 @@ constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) 
 // K = 32 half, double buffered) and the MMAs take A from there: 224 KB of B reads + 56 KB of staging reads per k-block.
 // Tensor memory: three 128-column accumulators (order groups of <= 3) + 112 columns of A.
 template <bool TS>
-__global__ void __maxnreg__(TS ? 144 : 168)      // 448 x 144 / 320 x 168 registers: one CTA per SM either way (224 KB smem)
+__global__ void __maxnreg__(TS ? 128 : 168)      // 448 x 128 / 320 x 168 registers (448 x 144 does not launch: "too many resources")
     oz_syrk_kernel(const __grid_constant__ OzPlan plan, const OzWork* __restrict__ work, int nwork, int KB,
                    const int8_t* __restrict__ slices, size_t slice_stride, const int* __restrict__ expo,
                    const double* __restrict__ pow2, int Dpad, double* __restrict__ Cmat, ptrdiff_t mc_off,

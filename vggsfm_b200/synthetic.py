@@ -103,3 +103,79 @@ def perturb(scene: Scene, rot_deg=1.0, trans_frac=0.02, focal_frac=0.05, point_s
     extra = None if scene.extra_params is None else scene.extra_params * 0.5
     pts = scene.points3d + rng.normal(size=scene.points3d.shape) * point_sigma
     return extr, K, extra, pts
+
+
+@dataclasses.dataclass
+class VideoScene:
+    """Forward-moving camera over a long corridor of points (BASELINE.json configs[4]: the sequential video runner).
+    Point j is created in window ``birth[j]`` and observed in the frames of ``lifetime`` consecutive windows."""
+    extrinsics: np.ndarray      # [F,3,4] ground truth
+    focal: float
+    pp: np.ndarray              # [2]
+    points3d: np.ndarray        # [P,3] ground truth
+    birth: np.ndarray           # [P] window index
+    first_frame: np.ndarray     # [P]
+    last_frame: np.ndarray      # [P] exclusive
+    window: int
+    init_window: int
+    noise_px: float
+    seed: int
+
+    def window_range(self, w):
+        """frames [start, end) of window w (window 0 is the init window)."""
+        if w == 0:
+            return 0, self.init_window
+        s = self.init_window + (w - 1) * self.window
+        return s, min(s + self.window, self.extrinsics.shape[0])
+
+    def num_windows(self):
+        F = self.extrinsics.shape[0]
+        return 1 + (F - self.init_window + self.window - 1) // self.window
+
+    def observe(self, ids, f0, f1):
+        """noisy pixel tracks [f1-f0, len(ids), 2] float32 and the usable mask (inside the point's lifetime, in front of the
+        camera, inside the 1024^2 image).  Noise is a pure function of (seed, frame, point): every call agrees."""
+        ids = np.asarray(ids)
+        uv, z = project_np(self.extrinsics[f0:f1], self.focal, self.pp, 0.0, self.points3d[ids])
+        fr = np.arange(f0, f1)[:, None]
+        h = (fr.astype(np.uint64) * np.uint64(2654435761) + ids[None].astype(np.uint64) * np.uint64(40503) + np.uint64(self.seed)) % np.uint64(2 ** 31)
+        rng_u = (h.astype(np.float64) + 0.5) / 2 ** 31
+        h2 = (h * np.uint64(1103515245) + np.uint64(12345)) % np.uint64(2 ** 31)
+        rng_v = (h2.astype(np.float64) + 0.5) / 2 ** 31
+        # Box-Muller from the two hashed uniforms
+        g0 = np.sqrt(-2.0 * np.log(rng_u)) * np.cos(2 * np.pi * rng_v)
+        g1 = np.sqrt(-2.0 * np.log(rng_u)) * np.sin(2 * np.pi * rng_v)
+        uv = uv + np.stack([g0, g1], -1) * self.noise_px
+        ok = (fr >= self.first_frame[ids][None]) & (fr < self.last_frame[ids][None]) & (z > 0.1)
+        ok &= (uv[..., 0] > 0) & (uv[..., 0] < 1024) & (uv[..., 1] > 0) & (uv[..., 1] < 1024)
+        return uv.astype(np.float32), ok
+
+
+def make_video_scene(F=1000, window=16, init_window=32, new_per_window=512, lifetime=3, step=0.06, noise_px=0.3,
+                     focal=1000.0, seed=0) -> VideoScene:
+    """Camera i at (i*step, 0, 0) with a slow yaw wobble, looking down +z; the points of window w sit around the camera
+    positions of the middle of their lifetime at depth ~4, so each is seen in about ``lifetime`` windows."""
+    rng = np.random.default_rng(seed)
+    i = np.arange(F, dtype=np.float64)
+    R = _rot_y(0.05 * np.sin(i / 40.0))
+    C = np.stack([i * step, 0.02 * np.sin(i / 25.0), np.zeros(F)], -1)
+    t = -np.einsum("fij,fj->fi", R, C)
+    extr = np.concatenate([R, t[:, :, None]], axis=2)
+    sc = VideoScene(extr, focal, np.array([512.0, 512.0]), np.zeros((0, 3)), np.zeros(0, int), np.zeros(0, int), np.zeros(0, int),
+                    window, init_window, noise_px, seed)
+    pts, birth, f0s, f1s = [], [], [], []
+    for w in range(sc.num_windows()):
+        s, e = sc.window_range(w)
+        last = min(F, s + lifetime * window) if w else min(F, init_window + (lifetime - 1) * window)
+        mid = 0.5 * (s + last) * step
+        n = new_per_window * (2 if w == 0 else 1)
+        X = np.stack([mid + rng.uniform(-1.2, 1.2, n), rng.normal(0, 0.5, n), rng.normal(4.0, 0.5, n)], -1)
+        pts.append(X)
+        birth.append(np.full(n, w))
+        f0s.append(np.full(n, s))
+        f1s.append(np.full(n, last))
+    sc.points3d = np.concatenate(pts)
+    sc.birth = np.concatenate(birth)
+    sc.first_frame = np.concatenate(f0s)
+    sc.last_frame = np.concatenate(f1s)
+    return sc

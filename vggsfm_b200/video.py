@@ -15,6 +15,9 @@ from . import pose_refinement as pr
 from . import triangulation as tri
 
 
+last_joint_summary = None       # Summary of the most recent joint_BA solve (iterations, costs), for drivers and benches
+
+
 def filter_points_and_compute_masks(points, tracks, extrinsics, intrinsics, extra_params, min_valid_track_length=3,
                                     max_reproj_error=4):
     """video_runner.py:907-939.  intrinsics [1,3,3] / extra_params [1,1] are the runner's shared camera.
@@ -102,9 +105,11 @@ def joint_BA(points3D, extrinsics, intrinsics, extra_params, tracks, masks, came
     poses, pts = extrinsics.double(), points3D.double()
     if normalize:
         poses, pts = ba.normalize(poses, pts, 5.0, 0.1, 0.9)                             # :503-504
+    global last_joint_summary
     pts_o, extr, K_o, ex_o, valid_idx, summary = ba.bundle_adjustment(
         pts, poses, K, ex, tracks, masks, shared_camera=True, camera_type=camera_type, options=ba.default_options(),
         filter_reconstruction=False)
+    last_joint_summary = summary
     out = pts.clone()
     out[valid_idx] = pts_o
     _, detail = tri.filter_all_points3D(out, tracks, extr, K_o, extra_params=ex_o, max_reproj_error=reproj_error,
