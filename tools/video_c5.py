@@ -167,14 +167,53 @@ def run(frames=1000, new_per_window=512, joint_every=6, seed=0, dev=None, verbos
             "trajectory_length": float(np.linalg.norm(Cg[-1] - Cg[0])), "store_points": store.num_points}
 
 
+def final_problem(frames=1000, new_per_window=512, seed=0, dev=None, reps=1):
+    """Only the LAST joint BA of the sequence, built directly from the synthetic scene (ground truth + noise instead of
+    the sequential estimates): the problem the launch lists and the multi-GPU leg look at."""
+    dev = dev or torch.device("cuda:0")
+    sc = make_video_scene(F=frames, new_per_window=new_per_window, seed=seed)
+    rng = np.random.default_rng(seed + 2)
+    T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    P = sc.points3d.shape[0]
+    uv = np.zeros((frames, P, 2), np.float32)
+    ok = np.zeros((frames, P), bool)
+    for w in range(sc.num_windows()):                       # window by window: observe() works on [frames, points] blocks
+        ids = np.nonzero(sc.birth == w)[0]
+        f0, f1 = int(sc.first_frame[ids[0]]), int(sc.last_frame[ids[0]])
+        u, o = sc.observe(ids, f0, f1)
+        uv[f0:f1, ids] = u
+        ok[f0:f1, ids] = o
+    keep = ok.sum(0) >= 3
+    w = rng.normal(size=(frames, 3))
+    w = w / np.linalg.norm(w, axis=1, keepdims=True) * np.deg2rad(0.2)
+    extr = sc.extrinsics.copy()
+    extr[:, :, :3] = _exp_so3(w) @ extr[:, :, :3]
+    extr[:, :, 3] += rng.normal(size=(frames, 3)) * 0.005
+    pts = sc.points3d[keep] + rng.normal(size=(int(keep.sum()), 3)) * 0.01
+    K = torch.tensor([[[sc.focal, 0.0, sc.pp[0]], [0.0, sc.focal, sc.pp[1]], [0.0, 0.0, 1.0]]], dtype=torch.float64, device=dev)
+    tracks, masks = T(uv[:, keep]), T(ok[:, keep])
+    xyz, ex0 = T(pts), T(extr)
+    times, its = [], []
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        video.joint_BA(xyz, ex0, K, None, tracks, masks, camera_type="SIMPLE_PINHOLE")
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+        its.append(int(video.last_joint_summary.iterations))
+    return {"workload": f"C5 final joint BA: {frames} frames x {int(keep.sum())} points, dense grid fill {float(ok[:, keep].mean()):.3f}",
+            "seconds": times, "lm_iterations": its, "lm_it_per_s": [i / t for i, t in zip(its, times)]}
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--frames", type=int, default=1000)
     ap.add_argument("--new", type=int, default=512)
     ap.add_argument("--json", default=None)
     ap.add_argument("-v", action="store_true")
+    ap.add_argument("--final-only", type=int, default=0, help="time only the last joint BA, this many repetitions")
     a = ap.parse_args()
-    out = run(a.frames, a.new, verbose=a.v)
+    out = final_problem(a.frames, a.new, reps=a.final_only) if a.final_only else run(a.frames, a.new, verbose=a.v)
     line = json.dumps(out)
     print(line)
     if a.json:

@@ -328,13 +328,96 @@ struct Fabric2 {
   }
 };
 
+extern std::vector<int> g_syrk_kb_ranges;     // csrc/syrk_i8.cu: band hint of the current solve
+
 // resets the process-wide kernel switches when a solve ends, on every exit path
 struct SolveGuard {
   ~SolveGuard() {
     g_fabric_dev.world = 0;
     g_fill_upper = 0;
+    g_syrk_kb_ranges.clear();
   }
 };
+
+// first / last visible point of every frame (N / -1 when the frame sees nothing): the band structure of sequential
+// (video) problems, where a point lives for a few windows and the dense [S, N] grid is mostly masked out
+__global__ void __launch_bounds__(256) frame_point_range_kernel(int S, int N, const uint8_t* __restrict__ mask,
+                                                                int* __restrict__ out) {
+  __shared__ int s_lo[256], s_hi[256];
+  const int s = blockIdx.x;
+  int lo = N, hi = -1;
+  for (int n = threadIdx.x; n < N; n += 256)
+    if (mask[(size_t)s * N + n]) {
+      lo = min(lo, n);
+      hi = max(hi, n);
+    }
+  s_lo[threadIdx.x] = lo;
+  s_hi[threadIdx.x] = hi;
+  __syncthreads();
+  for (int w = 128; w > 0; w >>= 1) {
+    if ((int)threadIdx.x < w) {
+      s_lo[threadIdx.x] = min(s_lo[threadIdx.x], s_lo[threadIdx.x + w]);
+      s_hi[threadIdx.x] = max(s_hi[threadIdx.x], s_hi[threadIdx.x + w]);
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    out[2 * s] = s_lo[0];
+    out[2 * s + 1] = s_hi[0];
+  }
+}
+
+// Per 128-column row block of Zt: the 64-row k-block range outside which the block is exactly zero (Zt row 3n+c belongs to
+// point n; column d < S*dc to frame d / dc; the shared-intrinsics columns see every point).  Leaves the hint empty when
+// the grid is (nearly) dense.  One small kernel + a 8 S byte read-back per solve.
+static int compute_band_hint(const vgg_ba_problem* prob, int dc, int D, int Dpad, int Kpad, cudaStream_t st) {
+  g_syrk_kb_ranges.clear();
+  const char* env = getenv("VGG_BAND");                 // read per solve so that a test can compare both paths in one process
+  const bool off = env && env[0] == '0';
+  const int S = prob->S, N = prob->N, nb = Dpad / 128, KB = (Kpad + 63) / 64;
+  if (off || nb < 6 || N < 1024) return VGG_OK;
+  static thread_local int* dev = nullptr;
+  static thread_local int cap = 0;
+  if (cap < 2 * S) {
+    if (dev) cudaFree(dev);
+    VGG_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&dev), sizeof(int) * 2 * (size_t)S));
+    cap = 2 * S;
+  }
+  frame_point_range_kernel<<<S, 256, 0, st>>>(S, N, prob->mask, dev);
+  VGG_LAUNCH_CHECK();
+  std::vector<int> fr(2 * (size_t)S);
+  VGG_CUDA_CHECK(cudaMemcpyAsync(fr.data(), dev, sizeof(int) * fr.size(), cudaMemcpyDeviceToHost, st));
+  VGG_CUDA_CHECK(cudaStreamSynchronize(st));
+  std::vector<int> rg(2 * (size_t)nb);
+  for (int rb = 0; rb < nb; ++rb) {
+    const int d0 = rb * 128, d1 = std::min(D, d0 + 128) - 1;
+    int lo = KB, hi = 0;
+    if (d1 >= d0) {
+      if (d1 >= S * dc) {
+        lo = 0;
+        hi = KB;
+      } else {
+        for (int f = d0 / dc; f <= d1 / dc; ++f) {
+          if (fr[2 * f + 1] < 0) continue;
+          lo = std::min(lo, 3 * fr[2 * f] / 64);
+          hi = std::max(hi, (3 * fr[2 * f + 1] + 2) / 64 + 1);
+        }
+      }
+    }
+    if (hi <= lo) lo = hi = 0;
+    rg[2 * rb] = lo;
+    rg[2 * rb + 1] = std::min(hi, KB);
+  }
+  // worth it only if a good part of the tile x k volume disappears
+  double kept = 0.0, all = 0.0;
+  for (int bi = 0; bi < nb; ++bi)
+    for (int bj = 0; bj <= bi; ++bj) {
+      all += KB;
+      kept += std::max(0, std::min(rg[2 * bi + 1], rg[2 * bj + 1]) - std::max(rg[2 * bi], rg[2 * bj]));
+    }
+  if (kept < 0.7 * all) g_syrk_kb_ranges = rg;
+  return VGG_OK;
+}
 
 // Schur complement of blk onto AR (Sraw, rhs, hdiag, gvec) at the given radius
 static int schur_build(const Layout& L, const BlockSet& b, const uint8_t* point_const, double radius, double min_diag,
@@ -560,6 +643,7 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
       VGG_REQUIRE(allreduce, "fabric v1 needs the hook for its barrier (op 2)");
     }
   }
+  if (L.oz_bytes && (rc = compute_band_hint(prob, dc, D, L.Dpad, L.Kpad, st))) return rc;
   double* Sraw = L.AR;
   double* rhs = L.AR + (size_t)D * L.Dpad;
   double* hdiag = rhs + L.Dpad;

@@ -614,7 +614,8 @@ __global__ void __launch_bounds__(C_THREADS, 1) chol_panel_kernel(int n, int lda
 // A[t0.., t0..] -= P P^T (lower part), P = A[t0.., k0..k0+127].  Tiles of TM rows x 64 columns, 8 warps.
 //   TM = 64 (trailing update off the critical path): tile (bi, bj), bj <= bi, warps 2x4, warp tile 32x16; mode 2 = tile
 //            columns >= 2, mode 0 = all; mode 3 = mode 2 with f64 REDs on tile columns 2 and 3 (the block column the
-//            fused panel kernel of the next step is adding into at the same time).
+//            fused panel kernel of the next step is adding into at the same time); mode 4 = tile columns 2 and 3 only
+//            (REDs), mode 5 = tile columns >= 4 (REDs on 4 and 5): the two halves of mode 3 with different deadlines.
 //   TM = 32 (mode 1, the next panel's 128 columns = tile columns 0 and 1, ON the critical path): twice as many CTAs so
 //            the ~140 tiles of a 2400-row matrix fill the 148 SMs with one short tile each; warps 1x8, warp tile 32x8.
 // Shared memory holds ONE K half (64 panel columns) of both operands at a time, row stride 68 doubles (fragment loads
@@ -638,12 +639,18 @@ __global__ void __launch_bounds__(C_THREADS, 2) chol_update_kernel(int n, int ld
       const int T = (n - t0 + 31) / 32;           // 32-row tiles; tile column 1 starts at row tile 2
       if (t < T) { bi = t; bj = 0; }
       else { bi = t - T + 2; bj = 1; }
+    } else if (mode == 4) {                         // tile columns 2 and 3 only (= block column k+2)
+      const int T = (n - t0 + 63) / 64;
+      if (t < T - 2) { bi = 2 + t; bj = 2; }
+      else { bi = 3 + (t - (T - 2)); bj = 3; }
     } else {
       bi = (int)((sqrtf(8.0f * (float)t + 1.0f) - 1.0f) * 0.5f);
       while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
       while (bi * (bi + 1) / 2 > t) --bi;
       bj = t - bi * (bi + 1) / 2;
-      if (mode >= 2) { bi += 2; bj += 2; }
+      const int skip = mode == 5 ? 4 : (mode >= 2 ? 2 : 0);
+      bi += skip;
+      bj += skip;
     }
   }
   const bool diag = TM == 64 && bi == bj;
@@ -703,7 +710,7 @@ __global__ void __launch_bounds__(C_THREADS, 2) chol_update_kernel(int n, int ld
       const int col = rj + wn * (8 * NJ) + j * 8 + 2 * q;
       if (col > r) continue;                         // lower triangle only (col <= r < n)
       double* p = A + (size_t)r * lda + col;
-      if (TM == 64 && mode == 3 && bj < 4) {
+      if (TM == 64 && ((mode == 3 && bj < 4) || mode == 4 || (mode == 5 && bj < 6))) {
         atomicAdd(p, -c[i][j][0]);
         if (col + 1 <= r) atomicAdd(p + 1, -c[i][j][1]);
       } else if (col + 1 <= r) {
@@ -728,8 +735,8 @@ size_t chol_workspace_doubles(int n) {
 namespace {
 
 struct CholStreams {
-  cudaStream_t side = nullptr, side_lo = nullptr, cap = nullptr;
-  cudaEvent_t ev_col = nullptr, ev_panel = nullptr, ev_upd[2] = {nullptr, nullptr};
+  cudaStream_t side = nullptr, side_lo = nullptr, side_mid = nullptr, cap = nullptr;
+  cudaEvent_t ev_col = nullptr, ev_panel = nullptr, ev_upd[2] = {nullptr, nullptr}, ev_bulk[3] = {nullptr, nullptr, nullptr};
   bool ready = false;
 };
 
@@ -743,11 +750,13 @@ int chol_streams(CholStreams** out) {
     // an SM has room for it instead of queueing behind the remaining update CTAs.
     VGG_CUDA_CHECK(cudaStreamCreateWithPriority(&s.side, cudaStreamNonBlocking, hi));
     VGG_CUDA_CHECK(cudaStreamCreateWithPriority(&s.side_lo, cudaStreamNonBlocking, lo));
+    VGG_CUDA_CHECK(cudaStreamCreateWithPriority(&s.side_mid, cudaStreamNonBlocking, (lo + hi) / 2));
     VGG_CUDA_CHECK(cudaStreamCreateWithPriority(&s.cap, cudaStreamNonBlocking, hi));
     VGG_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_col, cudaEventDisableTiming));
     VGG_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_panel, cudaEventDisableTiming));
     VGG_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_upd[0], cudaEventDisableTiming));
     VGG_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_upd[1], cudaEventDisableTiming));
+    for (int i = 0; i < 3; ++i) VGG_CUDA_CHECK(cudaEventCreateWithFlags(&s.ev_bulk[i], cudaEventDisableTiming));
     s.ready = true;
   }
   *out = &s;
@@ -807,28 +816,56 @@ int chol_enqueue(int n, int lda, double* A, double* Ldiag, int* info, int* flags
   int rc;
   if ((rc = panel(0, st))) return rc;
   if (fuse) {
-    int pending = -1;                                   // index of the last ev_upd recorded and not yet waited for by st
+    // Panel b's trailing update in two pieces with different deadlines: U1(b) = block column b+2 (needed by step(b+2),
+    // one step of slack, medium priority) and U2(b) = block columns >= b+3 (needed by step(b+3), two steps of slack,
+    // lowest priority).  r02: as ONE kernel with one step of slack the update of the first six panels did not fit
+    // next to the following step and 0.15 ms of it showed up on the critical path.
+    static const bool skip_bulk = getenv("VGG_CHOL_TIMING_SKIP_BULK") != nullptr;   // timing experiment only: WRONG factor
+    static const bool split = [] { const char* e = getenv("VGG_CHOL_SPLIT"); return !(e && e[0] == '0'); }();
+    bool have_u1[2] = {false, false}, have_u2[3] = {false, false, false};
     for (int b = 0; b + 1 < nblk; ++b) {
       const int k0 = b * CB, t0 = k0 + CB;
       const int T = (n - t0 + CT - 1) / CT;
+      const int n_u1 = T > 2 ? (T - 2) + (T > 3 ? T - 3 : 0) : 0;
+      const int n_u2 = T > 4 ? (T - 4) * (T - 3) / 2 : 0;
       const int n_rest = T > 2 ? (T - 2) * (T - 1) / 2 : 0;
-      int prev = pending;
-      static const bool skip_bulk = getenv("VGG_CHOL_TIMING_SKIP_BULK") != nullptr;   // timing experiment only: WRONG factor
+      have_u1[b & 1] = false;
+      have_u2[b % 3] = false;
       if (n_rest > 0 && !skip_bulk) {
         VGG_CUDA_CHECK(cudaEventRecord(cs->ev_col, st));                 // step(b) done
-        VGG_CUDA_CHECK(cudaStreamWaitEvent(cs->side_lo, cs->ev_col, 0));
-        chol_update_kernel<64><<<n_rest, C_THREADS, smem_u, cs->side_lo>>>(n, lda, k0, t0, 3, A);
-        VGG_LAUNCH_CHECK();
-        VGG_CUDA_CHECK(cudaEventRecord(cs->ev_upd[b & 1], cs->side_lo));
-        pending = b & 1;
-      } else {
-        pending = -1;
+        if (split) {
+          VGG_CUDA_CHECK(cudaStreamWaitEvent(cs->side_mid, cs->ev_col, 0));
+          // U2(b-2) still writes block column b+2 with plain read-modify-writes (only its first block column uses REDs)
+          if (b >= 2 && have_u2[(b - 2) % 3]) VGG_CUDA_CHECK(cudaStreamWaitEvent(cs->side_mid, cs->ev_bulk[(b - 2) % 3], 0));
+          chol_update_kernel<64><<<n_u1, C_THREADS, smem_u, cs->side_mid>>>(n, lda, k0, t0, 4, A);
+          VGG_LAUNCH_CHECK();
+          VGG_CUDA_CHECK(cudaEventRecord(cs->ev_upd[b & 1], cs->side_mid));
+          have_u1[b & 1] = true;
+          if (n_u2 > 0) {
+            VGG_CUDA_CHECK(cudaStreamWaitEvent(cs->side_lo, cs->ev_col, 0));
+            chol_update_kernel<64><<<n_u2, C_THREADS, smem_u, cs->side_lo>>>(n, lda, k0, t0, 5, A);
+            VGG_LAUNCH_CHECK();
+            VGG_CUDA_CHECK(cudaEventRecord(cs->ev_bulk[b % 3], cs->side_lo));
+            have_u2[b % 3] = true;
+          }
+        } else {
+          VGG_CUDA_CHECK(cudaStreamWaitEvent(cs->side_lo, cs->ev_col, 0));
+          chol_update_kernel<64><<<n_rest, C_THREADS, smem_u, cs->side_lo>>>(n, lda, k0, t0, 3, A);
+          VGG_LAUNCH_CHECK();
+          VGG_CUDA_CHECK(cudaEventRecord(cs->ev_upd[b & 1], cs->side_lo));
+          have_u1[b & 1] = true;
+        }
       }
-      // step(b+1) factors block column b+1: the trailing update of panel b-1 (the last one that touches it) must be done
-      if (prev >= 0) VGG_CUDA_CHECK(cudaStreamWaitEvent(st, cs->ev_upd[prev], 0));
+      // step(b+1) factors block column b+1: U1(b-1) (the last update of panel b-1 that touches it) and U2(b-2) must be done
+      if (b >= 1 && have_u1[(b - 1) & 1]) VGG_CUDA_CHECK(cudaStreamWaitEvent(st, cs->ev_upd[(b - 1) & 1], 0));
+      if (b >= 2 && have_u2[(b - 2) % 3]) VGG_CUDA_CHECK(cudaStreamWaitEvent(st, cs->ev_bulk[(b - 2) % 3], 0));
       if ((rc = panel(b + 1, st))) return rc;
     }
-    if (pending >= 0) VGG_CUDA_CHECK(cudaStreamWaitEvent(st, cs->ev_upd[pending], 0));
+    // join whatever the last two panels left on the side streams (capture needs every forked stream back)
+    for (int i = 0; i < 2; ++i)
+      if (have_u1[i]) VGG_CUDA_CHECK(cudaStreamWaitEvent(st, cs->ev_upd[i], 0));
+    for (int i = 0; i < 3; ++i)
+      if (have_u2[i]) VGG_CUDA_CHECK(cudaStreamWaitEvent(st, cs->ev_bulk[i], 0));
     return VGG_OK;
   }
   for (int b = 0; b + 1 < nblk; ++b) {
@@ -904,7 +941,7 @@ int chol_lower_inplace(int n, int lda, double* A, double* Ldiag, int* info, cuda
     it = cache.emplace(key, exec).first;
   }
   VGG_CUDA_CHECK(cudaGraphLaunch(it->second, st));
-  g_launch_count += 1 + (lookahead && chol_fuse() ? 2 : 3) * (nblk - 1);          // kernels inside the graph
+  g_launch_count += 1 + 3 * (nblk - 1);          // kernels inside the graph (upper bound: the last panels have no bulk update)
   return VGG_OK;
 }
 

@@ -93,8 +93,12 @@ __global__ void __launch_bounds__(512) oz_slice_kernel(int Kpad, int Dpad, int K
                                                        const double* __restrict__ Zt,
                                                        const unsigned long long* __restrict__ amax,
                                                        int* __restrict__ expo, double* __restrict__ pow2,
-                                                       int8_t* __restrict__ slices, size_t slice_stride) {
+                                                       int8_t* __restrict__ slices, size_t slice_stride,
+                                                       const int* __restrict__ kb_range /* [nb][2] or null */) {
   const int rb = blockIdx.x, kb = blockIdx.y;
+  // banded problems (csrc/ba_solve.cu computes the ranges from the visibility mask): outside [lo, hi) this row block of Z
+  // is zero and no work item reads its tile images
+  const bool skip = kb_range && (kb < kb_range[2 * rb] || kb >= kb_range[2 * rb + 1]);
   const int r = (threadIdx.x >> 5) * 8 + ((threadIdx.x & 31) >> 2), cphys = threadIdx.x & 3;
   const int c = cphys ^ ((r >> 1) & 3);
   const int d = rb * OZ_BM + r;
@@ -114,6 +118,7 @@ __global__ void __launch_bounds__(512) oz_slice_kernel(int Kpad, int Dpad, int K
     expo[d] = bad ? OZ_EXPO_BAD : e;
     pow2[d] = bad ? 0.0 : ldexp(1.0, e);
   }
+  if (skip) return;
   const int B = 8 * s - 2;
   const double scale = (bad || zero) ? 0.0 : __longlong_as_double((long long)(1023 + B - e) << 52);   // 2^(B-e), exact
   const unsigned long long bias = 0x0080808080808080ull >> (8 * (7 - s));
@@ -223,6 +228,10 @@ constexpr uint32_t OZ_IDESC = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) 
 // copy the <= 7 A slices of a k-block from shared memory into tensor memory once (tcgen05.st, 8 columns per slice and
 // K = 32 half, double buffered) and the MMAs take A from there: 224 KB of B reads + 56 KB of staging reads per k-block.
 // Tensor memory: three 128-column accumulators (order groups of <= 3) + 112 columns of A.
+// MEASURED (r02, 400 x 4096: Dpad 2432, K 12288): exact (6.6e-16, all parity tests pass with VGG_SYRK_TS=1) but SLOWER,
+// 1.86 ms per call against 1.07 ms: with tensor memory full there is room for two K = 32 halves of A only, so every
+// half pays a staging round (wait for the MMAs two halves back, 7 x (2 LDS.128 + tcgen05.st), wait::st, fence, barrier)
+// that is longer than the ~15 MMAs it feeds.  Kept behind VGG_SYRK_TS=1 as a record; the default stays the SS kernel.
 template <bool TS>
 __global__ void __maxnreg__(TS ? 128 : 168)      // 448 x 128 / 320 x 168 registers (448 x 144 does not launch: "too many resources")
     oz_syrk_kernel(const __grid_constant__ OzPlan plan, const OzWork* __restrict__ work, int nwork, int KB,
@@ -865,29 +874,33 @@ bool build_plan(int s, OzPlan* plan, int max_acc) {
 // targets and keeping the best makespan (+ a small charge per item for its epilogue).
 struct OzTileJob {
   int bi0, bi1, bj, dup;
+  int kb0 = 0, kb1 = -1;       // k-block range in which BOTH row blocks can be non-zero (kb1 < 0: all of K)
 };
 template <class Work, class Make>
 void build_work_list(const OzPlan& plan, const std::vector<OzTileJob>& jobs, int KB, int nworkers, Make make,
                      std::vector<Work>* out) {
-  long long total = 0;
-  for (int g = 0; g < plan.n_groups; ++g) total += (long long)plan.g[g].n_pairs * KB;
-  total *= (long long)jobs.size();
+  long long total = 0, pairs_all = 0;
+  for (int g = 0; g < plan.n_groups; ++g) pairs_all += plan.g[g].n_pairs;
+  for (const OzTileJob& jb : jobs) total += pairs_all * (long long)((jb.kb1 < 0 ? KB : jb.kb1) - jb.kb0);
   const long long epilogue_cost = 24;            // pair-kblock equivalents of one item's TMEM drain + REDs (not overlapped part)
   long long best = -1;
   for (int div = 2; div <= 10; ++div) {
     const long long target = std::max<long long>(1, total / ((long long)nworkers * div));
     std::vector<std::pair<long long, Work>> items;
-    for (const OzTileJob& jb : jobs)
+    for (const OzTileJob& jb : jobs) {
+      const int jk0 = jb.kb0, jk1 = jb.kb1 < 0 ? KB : jb.kb1, len = jk1 - jk0;
+      if (len <= 0) continue;
       for (int g = 0; g < plan.n_groups; ++g) {
-        const long long cost = (long long)plan.g[g].n_pairs * KB;
+        const long long cost = (long long)plan.g[g].n_pairs * len;
         int parts = (int)std::min<long long>(16, std::max<long long>(1, (cost + target / 2) / target));
-        parts = std::max(parts, (KB + OZ_MAX_ITEM_KB - 1) / OZ_MAX_ITEM_KB);      // int32 accumulators stay exact
-        parts = std::min(parts, KB);
+        parts = std::max(parts, (len + OZ_MAX_ITEM_KB - 1) / OZ_MAX_ITEM_KB);      // int32 accumulators stay exact
+        parts = std::min(parts, len);
         for (int p = 0; p < parts; ++p) {
-          const int k0 = (int)((long long)KB * p / parts), k1 = (int)((long long)KB * (p + 1) / parts);
+          const int k0 = jk0 + (int)((long long)len * p / parts), k1 = jk0 + (int)((long long)len * (p + 1) / parts);
           items.push_back({(long long)plan.g[g].n_pairs * (k1 - k0), make(jb, g, k0, k1)});
         }
       }
+    }
     std::stable_sort(items.begin(), items.end(), [](const auto& a, const auto& b) { return a.first > b.first; });
     std::vector<long long> load(nworkers, 0);
     for (size_t i = 0; i < items.size(); ++i) load[i % nworkers] += items[i].first + epilogue_cost;
@@ -902,6 +915,9 @@ void build_work_list(const OzPlan& plan, const std::vector<OzTileJob>& jobs, int
 
 struct OzHostState {
   int Kpad = -1, Dpad = -1, slices = -1, sms = 0;
+  std::vector<int> ranges;        // k-block range per row block the cached work list was built for (empty: dense)
+  int* ranges_dev = nullptr;      // device copy for the slicing kernel
+  size_t ranges_cap = 0;
   OzPlan plan;
   std::vector<OzWork> work;
   OzWork* pinned = nullptr;       // page-locked copy of `work`, so the per-call upload is a true async copy
@@ -956,6 +972,9 @@ int syrk_i8_reset_amax(void* ws, int Dpad, cudaStream_t st) {
 // Sraw -= Zt^T Zt with s int8 slices.  Zt [Kpad][Dpad] (Dpad % 128 == 0), Cmat [Dpad][Dpad] row-major, LOWER triangle
 // written (plus the mirror when g_fill_upper), same contract as launch_syrk.
 extern int g_fill_upper;      // csrc/ba_schur.cu
+// Band hint of the current solve (csrc/ba_solve.cu): [lo, hi) k-block range per 128-column row block of Zt outside which
+// the block is exactly zero; empty = dense.  Tiles whose two ranges do not intersect are skipped, the others shortened.
+std::vector<int> g_syrk_kb_ranges;
 extern FabricDev g_fabric_dev;  // csrc/ba_schur.cu: reduce-scatter destinations of the current multi-GPU solve (world <= 1: off)
 
 int launch_syrk_i8(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t mc_off, int s, void* ws,
@@ -965,7 +984,18 @@ int launch_syrk_i8(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t
   const int KB = (Kpad + OZ_BK - 1) / OZ_BK;
   const int nb = Dpad / OZ_BM;
   OzHostState& hs = g_oz;
-  if (hs.Kpad != Kpad || hs.Dpad != Dpad || hs.slices != s) {
+  const bool banded = (int)g_syrk_kb_ranges.size() == 2 * nb;
+  if (hs.Kpad != Kpad || hs.Dpad != Dpad || hs.slices != s || (banded ? hs.ranges != g_syrk_kb_ranges : !hs.ranges.empty())) {
+    hs.ranges = banded ? g_syrk_kb_ranges : std::vector<int>();
+    if (banded) {
+      if (hs.ranges_cap < hs.ranges.size()) {
+        if (hs.ranges_dev) cudaFree(hs.ranges_dev);
+        hs.ranges_cap = hs.ranges.size();
+        VGG_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&hs.ranges_dev), sizeof(int) * hs.ranges_cap));
+      }
+      VGG_CUDA_CHECK(cudaMemcpyAsync(hs.ranges_dev, hs.ranges.data(), sizeof(int) * hs.ranges.size(), cudaMemcpyHostToDevice, st));
+      VGG_CUDA_CHECK(cudaStreamSynchronize(st));          // the source is pageable host memory; once per (re)plan
+    }
     VGG_REQUIRE(build_plan(s, &hs.plan, use_ts_kernel() ? 3 : 4), "syrk_i8: slices must be in [3,7]");
     int dev = 0;
     VGG_CUDA_CHECK(cudaGetDevice(&dev));
@@ -976,7 +1006,15 @@ int launch_syrk_i8(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t
     {
       std::vector<OzTileJob> jobs;
       for (int bi = 0; bi < nb; ++bi)
-        for (int bj = 0; bj <= bi; ++bj) jobs.push_back({bj, bj, bi, 0});     // upper tile (row block bj <= column block bi)
+        for (int bj = 0; bj <= bi; ++bj) {                                    // upper tile (row block bj <= column block bi)
+          OzTileJob jb{bj, bj, bi, 0};
+          if (banded) {
+            jb.kb0 = std::max(hs.ranges[2 * bi], hs.ranges[2 * bj]);
+            jb.kb1 = std::min(hs.ranges[2 * bi + 1], hs.ranges[2 * bj + 1]);
+            if (jb.kb1 <= jb.kb0) continue;
+          }
+          jobs.push_back(jb);
+        }
       build_work_list<OzWork>(hs.plan, jobs, KB, hs.sms,
                               [](const OzTileJob& j, int g, int k0, int k1) { return OzWork{j.bi0, j.bj, g, k0, k1}; }, &hs.work);
     }
@@ -1021,7 +1059,7 @@ int launch_syrk_i8(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t
   const size_t slice_stride = (size_t)nb * KB * OZ_TILE_BYTES;
   const int nwork = (int)hs.work.size();
 
-  const bool pair = use_pair_kernel() && hs.sms >= 2 && g_fabric_dev.world <= 1;   // the reduce-scatter epilogue lives in oz_syrk_kernel
+  const bool pair = use_pair_kernel() && hs.sms >= 2 && g_fabric_dev.world <= 1 && !banded;   // the reduce-scatter epilogue lives in oz_syrk_kernel
   if (pair) VGG_CUDA_CHECK(cudaMemcpyAsync(work_raw, hs.pinned2, sizeof(OzWork2) * hs.work2.size(), cudaMemcpyHostToDevice, st));
   else VGG_CUDA_CHECK(cudaMemcpyAsync(work_d, hs.pinned, sizeof(OzWork) * nwork, cudaMemcpyHostToDevice, st));
   if (!amax_ready) {
@@ -1031,7 +1069,8 @@ int launch_syrk_i8(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t
     oz_rowmax_kernel<<<dim3(Dpad / 128, ksplit), 128, 0, st>>>(Kpad, Dpad, k_per, Zt, amax);
     VGG_LAUNCH_CHECK();
   }
-  oz_slice_kernel<<<dim3(nb, KB), 512, 0, st>>>(Kpad, Dpad, KB, s, Zt, amax, expo, pow2, slices, slice_stride);
+  oz_slice_kernel<<<dim3(nb, KB), 512, 0, st>>>(Kpad, Dpad, KB, s, Zt, amax, expo, pow2, slices, slice_stride,
+                                                banded ? hs.ranges_dev : nullptr);
   VGG_LAUNCH_CHECK();
   if (pair) {
     const int nwork2 = (int)hs.work2.size();
