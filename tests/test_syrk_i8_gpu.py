@@ -76,3 +76,32 @@ def test_cta_pair_variant_in_subprocess(cuda_dev):
     assert out.returncode == 0, out.stderr[-500:]
     m = re.search(r"= ([0-9.e+-]+)\s+symmetric", out.stdout)
     assert m and float(m.group(1)) < 2.0 ** -44, out.stdout[-300:]
+
+
+def test_band_hint_skips_only_zero_blocks(cuda_dev):
+    """With the band hint installed (k-block range per 128-column row block outside which Zt is zero) the kernel skips
+    tiles whose ranges do not meet and shortens the rest: the result must equal the dense product of the same Z."""
+    from vggsfm_b200 import _lib
+    L = _lib.lib()
+    Dpad, KB = 1024, 24
+    Z = _case(Dpad, KB * 64, 11)
+    nb = Dpad // 128
+    rg = np.zeros((nb, 2), dtype=np.int32)
+    for rb in range(nb):
+        lo, hi = (0, KB) if rb == nb - 1 else (2 * rb, min(KB, 2 * rb + 7))        # last block: dense (the shared camera's column)
+        rg[rb] = (lo, hi)
+        Z[:lo * 64, rb * 128:(rb + 1) * 128] = 0.0
+        Z[hi * 64:, rb * 128:(rb + 1) * 128] = 0.0
+    ref = -(Z.T @ Z)
+    bound = np.abs(Z).T @ np.abs(Z)
+    dense = _run(Z, 7, cuda_dev)
+    _lib.check(L.vgg_dev_set_syrk_ranges(rg.ctypes.data, rg.size), "ranges")
+    try:
+        got = _run(Z, 7, cuda_dev)
+    finally:
+        L.vgg_dev_set_syrk_ranges(None, 0)
+    for name, m in (("dense", dense), ("band", got)):
+        err = np.abs(m - ref)
+        assert np.all(err <= 2.0 ** -44 * bound + 1e-300), (name, (err / (bound + 1e-300)).max())
+    again = _run(Z, 7, cuda_dev)                       # and the plan goes back to dense when the hint is gone
+    assert np.all(np.abs(again - ref) <= 2.0 ** -44 * bound + 1e-300)

@@ -329,6 +329,8 @@ struct Fabric2 {
 };
 
 extern std::vector<int> g_syrk_kb_ranges;     // csrc/syrk_i8.cu: band hint of the current solve
+extern std::vector<int> g_chol_band_end;      // csrc/chol.cu: block structure of the reduced system (banded + arrow)
+extern int g_chol_arrow_blk;
 
 // resets the process-wide kernel switches when a solve ends, on every exit path
 struct SolveGuard {
@@ -336,6 +338,8 @@ struct SolveGuard {
     g_fabric_dev.world = 0;
     g_fill_upper = 0;
     g_syrk_kb_ranges.clear();
+    g_chol_band_end.clear();
+    g_chol_arrow_blk = 0;
   }
 };
 
@@ -372,6 +376,8 @@ __global__ void __launch_bounds__(256) frame_point_range_kernel(int S, int N, co
 // the grid is (nearly) dense.  One small kernel + a 8 S byte read-back per solve.
 static int compute_band_hint(const vgg_ba_problem* prob, int dc, int D, int Dpad, int Kpad, cudaStream_t st) {
   g_syrk_kb_ranges.clear();
+  g_chol_band_end.clear();
+  g_chol_arrow_blk = 0;
   const char* env = getenv("VGG_BAND");                 // read per solve so that a test can compare both paths in one process
   const bool off = env && env[0] == '0';
   const int S = prob->S, N = prob->N, nb = Dpad / 128, KB = (Kpad + 63) / 64;
@@ -415,7 +421,34 @@ static int compute_band_hint(const vgg_ba_problem* prob, int dc, int D, int Dpad
       all += KB;
       kept += std::max(0, std::min(rg[2 * bi + 1], rg[2 * bj + 1]) - std::max(rg[2 * bi], rg[2 * bj]));
     }
-  if (kept < 0.7 * all) g_syrk_kb_ranges = rg;
+  if (kept < 0.7 * all) {
+    g_syrk_kb_ranges = rg;
+    // the same structure for the factorisation: block (i, b) of the reduced system is non-zero iff the k ranges of row
+    // blocks i and b meet; the blocks from the first shared-intrinsics column on (and the bordered right-hand-side row)
+    // are the dense "arrow".  end[b] = one past the last band block of column b, made non-decreasing (the envelope
+    // Cholesky fills) and >= b + 2 so that block row b + 1 always counts as band.
+    const int arrow = (S * dc) / 128;
+    if (arrow >= 4) {
+      std::vector<int> end(nb);
+      int prev = 0;
+      for (int b = 0; b < nb; ++b) {
+        int e = b;
+        if (b < arrow) {
+          for (int i = b + 1; i < arrow; ++i)
+            if (std::min(rg[2 * i + 1], rg[2 * b + 1]) > std::max(rg[2 * i], rg[2 * b])) e = i;
+          e = std::max(e + 1, std::min(b + 2, arrow));
+          e = std::max(e, prev);
+          e = std::min(e, arrow);
+        } else {
+          e = nb;
+        }
+        end[b] = e;
+        prev = e;
+      }
+      g_chol_band_end = end;
+      g_chol_arrow_blk = arrow;
+    }
+  }
   return VGG_OK;
 }
 

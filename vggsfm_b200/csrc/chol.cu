@@ -16,7 +16,9 @@
 // VGG_CHOL_FUSE=0 (separate critical-path update kernel + panel on a side stream, the first r02 schedule),
 // VGG_CHOL_LOOKAHEAD=0 (everything in program order), VGG_CHOL_GRAPH=0, VGG_CHOL_LEAF=0.
 #include <stdlib.h>
+#include <algorithm>
 #include <map>
+#include <vector>
 #include <tuple>
 #include "common.cuh"
 
@@ -459,7 +461,9 @@ template <int LEAF>
 __global__ void __launch_bounds__(C_THREADS, 1) chol_panel_kernel(int n, int lda, int k0, double* __restrict__ A,
                                                                    double* __restrict__ Ldiag /*[nblk][128*128]*/,
                                                                    int* __restrict__ info, int* __restrict__ flags,
-                                                                   int fuse) {
+                                                                   int fuse, int band_end, int arrow_lo) {
+  // Rows below the diagonal block that can be non-zero in this block column: [k0+128, band_end) and [arrow_lo, n)
+  // (band_end = arrow_lo = n: everything, the dense case).  The CTAs cover exactly these rows, 16 each.
   extern __shared__ __align__(16) double cp_smem[];
   double* Ls = cp_smem;                        // [128][CLD]
   double* Ts = cp_smem + CB * CLD;             // [16][CLD]: rows 128.. of the same array (ride-along rows)
@@ -468,7 +472,9 @@ __global__ void __launch_bounds__(C_THREADS, 1) chol_panel_kernel(int n, int lda
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = min(CB, n - k0);
   const bool solver = blockIdx.x > 0;
-  const int r0 = k0 + CB + ((int)blockIdx.x - 1) * C_RPC;
+  const int chunks1r = (max(0, min(band_end, n) - (k0 + CB)) + C_RPC - 1) / C_RPC;   // banded: band_end is a multiple of 128
+  const int cidx = (int)blockIdx.x - 1;
+  const int r0 = cidx < chunks1r ? k0 + CB + cidx * C_RPC : arrow_lo + (cidx - chunks1r) * C_RPC;
   // diagonal block (rows < nb: whole 128-double rows, the part above the diagonal is never read; identity padding
   // beyond nb) and this CTA's 16 panel rows: cp.async, all 16-byte chunks in flight at once (r02: the plain
   // load -> store loop serialised 32 L2 round trips per thread, a third of the kernel)
@@ -539,7 +545,11 @@ __global__ void __launch_bounds__(C_THREADS, 1) chol_panel_kernel(int n, int lda
 
   // ---- fused update of block column k+1 with this panel
   const int t0 = k0 + CB;
-  const int nprod = min(CB / C_RPC, (int)gridDim.x - 1);       // CTAs 1..nprod own block row k+1
+  // CTAs 1..nprod own block row k+1 (the band's first block, or the arrow block when it is the next one); a block
+  // row that is structurally zero in this column has no producers and there is nothing to subtract
+  const bool p_active = band_end > t0 || arrow_lo == t0;
+  const int nprod = p_active ? min(CB / C_RPC, (int)gridDim.x - 1) : 0;
+  if (nprod == 0) return;
   int* flag = flags + k0 / CB;
   __threadfence();
   __syncthreads();
@@ -626,7 +636,8 @@ __global__ void __launch_bounds__(C_THREADS, 1) chol_panel_kernel(int n, int lda
 constexpr int CUD = 68;
 template <int TM>
 __global__ void __launch_bounds__(C_THREADS, 2) chol_update_kernel(int n, int lda, int k0, int t0, int mode,
-                                                                    double* __restrict__ A) {
+                                                                    double* __restrict__ A, int band_end, int arrow_lo,
+                                                                    int all_red) {
   constexpr int WN = TM == 64 ? 4 : 8;            // warps along the 64 tile columns
   constexpr int NJ = 64 / WN / 8;                 // 8-column MMA tiles per warp: 2 or 1
   extern __shared__ __align__(16) double cu_smem[];
@@ -640,7 +651,7 @@ __global__ void __launch_bounds__(C_THREADS, 2) chol_update_kernel(int n, int ld
       if (t < T) { bi = t; bj = 0; }
       else { bi = t - T + 2; bj = 1; }
     } else if (mode == 4) {                         // tile columns 2 and 3 only (= block column k+2)
-      const int T = (n - t0 + 63) / 64;
+      const int T = (max(0, min(band_end, n) - t0) + 63) / 64 + (band_end >= n ? 0 : (n - arrow_lo + 63) / 64);
       if (t < T - 2) { bi = 2 + t; bj = 2; }
       else { bi = 3 + (t - (T - 2)); bj = 3; }
     } else {
@@ -655,7 +666,11 @@ __global__ void __launch_bounds__(C_THREADS, 2) chol_update_kernel(int n, int ld
   }
   const bool diag = TM == 64 && bi == bj;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int ri = t0 + bi * TM, rj = t0 + bj * 64;
+  // banded matrices: 64-row tile v of the ACTIVE rows -- the band part [t0, band_end) first, then the arrow part
+  // [arrow_lo, n) (band_end = n: the plain dense mapping)
+  const int T1v = band_end >= n ? (1 << 30) : (band_end - t0) / 64;
+  auto vrow = [&](int v) { return v < T1v ? t0 + v * 64 : arrow_lo + (v - T1v) * 64; };
+  const int ri = TM == 64 ? vrow(bi) : t0 + bi * TM, rj = TM == 64 ? vrow(bj) : t0 + bj * 64;
   const double* bs = diag ? As : Bs;
   const int wm = warp / WN, wn = warp % WN;
   const int g = lane >> 2, q = lane & 3;
@@ -710,7 +725,7 @@ __global__ void __launch_bounds__(C_THREADS, 2) chol_update_kernel(int n, int ld
       const int col = rj + wn * (8 * NJ) + j * 8 + 2 * q;
       if (col > r) continue;                         // lower triangle only (col <= r < n)
       double* p = A + (size_t)r * lda + col;
-      if (TM == 64 && ((mode == 3 && bj < 4) || mode == 4 || (mode == 5 && bj < 6))) {
+      if (TM == 64 && (all_red || (mode == 3 && bj < 4) || mode == 4 || (mode == 5 && bj < 6))) {
         atomicAdd(p, -c[i][j][0]);
         if (col + 1 <= r) atomicAdd(p + 1, -c[i][j][1]);
       } else if (col + 1 <= r) {
@@ -784,6 +799,17 @@ int chol_set_attrs() {
   return VGG_OK;
 }
 
+}  // namespace
+
+// Block structure of a banded + arrow matrix (sequential / video problems; set by csrc/ba_solve.cu for the duration of
+// a solve, empty = dense): in block column b the rows that can be non-zero below the diagonal block are the band
+// [128 (b+1), 128 end_blk[b]) and the arrow [128 arrow_blk, n).  end_blk is non-decreasing (the envelope the
+// factorisation fills) and end_blk[b] >= b + 2 while b + 1 < arrow_blk, so block row b+1 is always in the band.
+std::vector<int> g_chol_band_end;
+int g_chol_arrow_blk = 0;
+
+namespace {
+
 // VGG_CHOL_FUSE=0 (A/B): the r02 schedule with a separate critical-path update kernel per panel
 bool chol_fuse() {
   static const bool v = [] { const char* e = getenv("VGG_CHOL_FUSE"); return !(e && e[0] == '0'); }();
@@ -802,14 +828,29 @@ int chol_enqueue(int n, int lda, double* A, double* Ldiag, int* info, int* flags
   const size_t smem_p = sizeof(double) * (CB + C_RPC) * CLD;
   const size_t smem_u = sizeof(double) * 2 * CT * CUD;
   const bool fuse = lookahead && chol_fuse();
+  static const bool split = [] { const char* e = getenv("VGG_CHOL_SPLIT"); return !(e && e[0] == '0'); }();
+  // the band structure is honoured by the default (fused + split) schedule only; the A/B schedules treat the matrix as dense
+  const bool banded = fuse && split && (int)g_chol_band_end.size() >= nblk && g_chol_arrow_blk > 0;
+  auto band_rows = [&](int b, int* band_end, int* arrow_lo) {
+    if (!banded) {
+      *band_end = *arrow_lo = n;
+      return;
+    }
+    *band_end = std::min(n, g_chol_band_end[b] * CB);
+    *arrow_lo = std::min(n, std::max(g_chol_arrow_blk * CB, *band_end));
+    if (*band_end >= n || *arrow_lo <= *band_end) *band_end = *arrow_lo = n;      // no gap left: plain dense rows
+  };
   auto panel = [&](int b, cudaStream_t s2) -> int {
     const int k0 = b * CB;
-    const int below = n - (k0 + CB);
-    const int chunks = below > 0 ? (below + C_RPC - 1) / C_RPC : 0;
+    int band_end, arrow_lo;
+    band_rows(b, &band_end, &arrow_lo);
+    const int below1 = std::max(0, std::min(band_end, n) - (k0 + CB));
+    const int below2 = band_end >= n ? 0 : n - arrow_lo;
+    const int chunks = (below1 + C_RPC - 1) / C_RPC + (below2 + C_RPC - 1) / C_RPC;
     if (chol_leaf() == 1)
-      chol_panel_kernel<1><<<1 + chunks, C_THREADS, smem_p, s2>>>(n, lda, k0, A, Ldiag, info, flags, fuse ? 1 : 0);
+      chol_panel_kernel<1><<<1 + chunks, C_THREADS, smem_p, s2>>>(n, lda, k0, A, Ldiag, info, flags, fuse ? 1 : 0, band_end, arrow_lo);
     else
-      chol_panel_kernel<0><<<1 + chunks, C_THREADS, smem_p, s2>>>(n, lda, k0, A, Ldiag, info, flags, fuse ? 1 : 0);
+      chol_panel_kernel<0><<<1 + chunks, C_THREADS, smem_p, s2>>>(n, lda, k0, A, Ldiag, info, flags, fuse ? 1 : 0, band_end, arrow_lo);
     VGG_LAUNCH_CHECK();
     return VGG_OK;
   };
@@ -821,11 +862,13 @@ int chol_enqueue(int n, int lda, double* A, double* Ldiag, int* info, int* flags
     // lowest priority).  r02: as ONE kernel with one step of slack the update of the first six panels did not fit
     // next to the following step and 0.15 ms of it showed up on the critical path.
     static const bool skip_bulk = getenv("VGG_CHOL_TIMING_SKIP_BULK") != nullptr;   // timing experiment only: WRONG factor
-    static const bool split = [] { const char* e = getenv("VGG_CHOL_SPLIT"); return !(e && e[0] == '0'); }();
     bool have_u1[2] = {false, false}, have_u2[3] = {false, false, false};
     for (int b = 0; b + 1 < nblk; ++b) {
       const int k0 = b * CB, t0 = k0 + CB;
-      const int T = (n - t0 + CT - 1) / CT;
+      int band_end, arrow_lo;
+      band_rows(b, &band_end, &arrow_lo);
+      const int T = (std::max(0, std::min(band_end, n) - t0) + CT - 1) / CT + (band_end >= n ? 0 : (n - arrow_lo + CT - 1) / CT);
+      const int all_red = band_end >= n ? 0 : 1;     // banded: tile columns no longer map to consecutive block columns
       const int n_u1 = T > 2 ? (T - 2) + (T > 3 ? T - 3 : 0) : 0;
       const int n_u2 = T > 4 ? (T - 4) * (T - 3) / 2 : 0;
       const int n_rest = T > 2 ? (T - 2) * (T - 1) / 2 : 0;
@@ -837,20 +880,20 @@ int chol_enqueue(int n, int lda, double* A, double* Ldiag, int* info, int* flags
           VGG_CUDA_CHECK(cudaStreamWaitEvent(cs->side_mid, cs->ev_col, 0));
           // U2(b-2) still writes block column b+2 with plain read-modify-writes (only its first block column uses REDs)
           if (b >= 2 && have_u2[(b - 2) % 3]) VGG_CUDA_CHECK(cudaStreamWaitEvent(cs->side_mid, cs->ev_bulk[(b - 2) % 3], 0));
-          chol_update_kernel<64><<<n_u1, C_THREADS, smem_u, cs->side_mid>>>(n, lda, k0, t0, 4, A);
+          chol_update_kernel<64><<<n_u1, C_THREADS, smem_u, cs->side_mid>>>(n, lda, k0, t0, 4, A, band_end, arrow_lo, all_red);
           VGG_LAUNCH_CHECK();
           VGG_CUDA_CHECK(cudaEventRecord(cs->ev_upd[b & 1], cs->side_mid));
           have_u1[b & 1] = true;
           if (n_u2 > 0) {
             VGG_CUDA_CHECK(cudaStreamWaitEvent(cs->side_lo, cs->ev_col, 0));
-            chol_update_kernel<64><<<n_u2, C_THREADS, smem_u, cs->side_lo>>>(n, lda, k0, t0, 5, A);
+            chol_update_kernel<64><<<n_u2, C_THREADS, smem_u, cs->side_lo>>>(n, lda, k0, t0, 5, A, band_end, arrow_lo, all_red);
             VGG_LAUNCH_CHECK();
             VGG_CUDA_CHECK(cudaEventRecord(cs->ev_bulk[b % 3], cs->side_lo));
             have_u2[b % 3] = true;
           }
         } else {
           VGG_CUDA_CHECK(cudaStreamWaitEvent(cs->side_lo, cs->ev_col, 0));
-          chol_update_kernel<64><<<n_rest, C_THREADS, smem_u, cs->side_lo>>>(n, lda, k0, t0, 3, A);
+          chol_update_kernel<64><<<n_rest, C_THREADS, smem_u, cs->side_lo>>>(n, lda, k0, t0, 3, A, n, n, 0);
           VGG_LAUNCH_CHECK();
           VGG_CUDA_CHECK(cudaEventRecord(cs->ev_upd[b & 1], cs->side_lo));
           have_u1[b & 1] = true;
@@ -875,19 +918,19 @@ int chol_enqueue(int n, int lda, double* A, double* Ldiag, int* info, int* flags
     const int n_col = T32 + (T32 > 2 ? T32 - 2 : 0);       // 32-row tiles of tile columns 0 and 1
     const int n_rest = T > 2 ? (T - 2) * (T - 1) / 2 : 0;
     if (!lookahead) {
-      chol_update_kernel<64><<<T * (T + 1) / 2, C_THREADS, smem_u, st>>>(n, lda, k0, t0, 0, A);
+      chol_update_kernel<64><<<T * (T + 1) / 2, C_THREADS, smem_u, st>>>(n, lda, k0, t0, 0, A, n, n, 0);
       VGG_LAUNCH_CHECK();
       if ((rc = panel(b + 1, st))) return rc;
       continue;
     }
-    chol_update_kernel<32><<<n_col, C_THREADS, sizeof(double) * (32 + CT) * CUD, st>>>(n, lda, k0, t0, 1, A);
+    chol_update_kernel<32><<<n_col, C_THREADS, sizeof(double) * (32 + CT) * CUD, st>>>(n, lda, k0, t0, 1, A, n, n, 0);
     VGG_LAUNCH_CHECK();
     VGG_CUDA_CHECK(cudaEventRecord(cs->ev_col, st));
     VGG_CUDA_CHECK(cudaStreamWaitEvent(cs->side, cs->ev_col, 0));
     if ((rc = panel(b + 1, cs->side))) return rc;
     VGG_CUDA_CHECK(cudaEventRecord(cs->ev_panel, cs->side));
     if (n_rest > 0) {
-      chol_update_kernel<64><<<n_rest, C_THREADS, smem_u, st>>>(n, lda, k0, t0, 2, A);
+      chol_update_kernel<64><<<n_rest, C_THREADS, smem_u, st>>>(n, lda, k0, t0, 2, A, n, n, 0);
       VGG_LAUNCH_CHECK();
     }
     VGG_CUDA_CHECK(cudaStreamWaitEvent(st, cs->ev_panel, 0));
@@ -915,9 +958,11 @@ int chol_lower_inplace(int n, int lda, double* A, double* Ldiag, int* info, cuda
   if ((rc = chol_streams(&cs))) return rc;
   if (nblk < 3 || !use_graph) return chol_enqueue(n, lda, A, Ldiag, info, flags, st, cs, lookahead && nblk >= 3);
   // one captured graph per (matrix, order): ~60 launches + events become a single cudaGraphLaunch
-  typedef std::tuple<double*, int, int, int*, double*, bool> Key;
+  typedef std::tuple<double*, int, int, int*, double*, bool, unsigned long long> Key;
   static thread_local std::map<Key, cudaGraphExec_t> cache;
-  const Key key(A, n, lda, info, Ldiag, lookahead);
+  unsigned long long band_hash = (unsigned long long)g_chol_arrow_blk;
+  for (int v : g_chol_band_end) band_hash = band_hash * 1000003ull + (unsigned long long)(v + 1);
+  const Key key(A, n, lda, info, Ldiag, lookahead, band_hash);
   auto it = cache.find(key);
   if (it == cache.end()) {
     const long long launches_before = g_launch_count;

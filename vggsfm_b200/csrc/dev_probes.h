@@ -20,6 +20,10 @@ int vgg_dev_blocks_last_ms(double* ms);
  * warp 1 (0 first leaf, 1 TRSM of the micro-panel, 2 look-ahead section work, 3 wait at its barrier, 4 rank-32 DMMA
  * update, 5 first leaf of the next sub-panel), [12] = total cycles of the last of `reps` passes. */
 int vgg_dev_chol128_probe(int leaf, int reps, const double* A_host, double* L_host, long long* prof13_host);
+/* Band hint of the tensor-core SYRK for tests: ranges_host[2*rb], [2*rb+1] = the 64-row k-block range outside which the
+ * 128-column row block rb of Zt is exactly zero (count = 2 * Dpad/128; count = 0 clears it).  vgg_ba_solve computes the
+ * same thing from the visibility mask and clears it when it returns. */
+int vgg_dev_set_syrk_ranges(const int* ranges_host, int count);
 
 #ifdef __cplusplus
 }

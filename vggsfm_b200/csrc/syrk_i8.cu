@@ -1094,6 +1094,13 @@ int launch_syrk_i8(int Kpad, int Dpad, const double* Zt, double* Cmat, ptrdiff_t
 
 extern "C" {
 
+/* development probe (csrc/dev_probes.h): install / clear (count = 0) the band hint the next SYRK calls plan with */
+int vgg_dev_set_syrk_ranges(const int* ranges_host, int count) {
+  using namespace vgg;
+  g_syrk_kb_ranges.assign(ranges_host, ranges_host + (count > 0 ? count : 0));
+  return VGG_OK;
+}
+
 int vgg_syrk_ozaki_workspace_bytes(int Kpad, int Dpad, int slices, size_t* bytes) {
   using namespace vgg;
   VGG_REQUIRE(bytes && Kpad > 0 && Dpad > 0 && Dpad % 128 == 0 && slices >= 3 && slices <= 7, "bad argument");
