@@ -32,6 +32,7 @@ namespace vgg {
 
 // kernel-only timing for bench.py's roofline (csrc/dev_probes.h): an event pair on the launching stream, directly
 // around the ba_blocks_kernel launch (the accumulator memsets stay outside)
+extern BandDev g_band_dev;         // csrc/ba_schur.cu
 static bool g_blocks_timing = false;
 static cudaEvent_t g_blocks_ev[2] = {nullptr, nullptr};
 
@@ -179,7 +180,8 @@ __global__ void __launch_bounds__(BT, MINB) ba_blocks_kernel(
     int S, int N, int tracks_per_warp, const float* __restrict__ uv, const uint8_t* __restrict__ mask,
     const double* __restrict__ poses, const double* __restrict__ intr, const double* __restrict__ points,
     const uint8_t* __restrict__ point_const, double* __restrict__ cost, double* __restrict__ camrec,
-    double* __restrict__ g_p, double* __restrict__ H_pp, double* __restrict__ W, double* __restrict__ shared_out) {
+    double* __restrict__ g_p, double* __restrict__ H_pp, double* __restrict__ W, double* __restrict__ shared_out,
+    const int* __restrict__ fg_tracks) {
   using C = BlkCfg<MODEL, MODE>;
   constexpr int DC = C::DC, NS = C::NS, KR = C::KR, NP = C::NP;
   constexpr int WB = DC * 3;                       // doubles per observation block
@@ -204,6 +206,9 @@ __global__ void __launch_bounds__(BT, MINB) ba_blocks_kernel(
   const int chunk = wid / ngroups;
   const int t_begin = (int)min((long long)N, (long long)chunk * tracks_per_warp);
   const int t_end = min(N, t_begin + tracks_per_warp);
+  // banded (sequential) problems: none of this warp's tracks is visible in its 32 frames.  Their W blocks stay at the zero
+  // the solver wrote once per solve, and z_build / backsub skip the same region (csrc/ba_solve.cu, compute_band_hint).
+  if (fg_tracks && (t_end <= fg_tracks[2 * g] || t_begin >= fg_tracks[2 * g + 1])) return;
   const int s = g * 32 + lane;
   const bool frame_ok = s < S;
   const int nf = min(32, S - g * 32);              // frames of this group that exist
@@ -451,17 +456,17 @@ static int launch_blocks(const vgg_ba_problem* p, double* cost, double* camrec, 
     auto kern = ba_blocks_kernel<MODEL, MODE, true, 2>;
     VGG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, BT, smem, stream>>>(S, N, tracks_per_warp, p->uv, p->mask, p->poses, p->intr, p->points,
-                                     p->point_const, cost, camrec, g_p, H_pp, W, shared_out);
+                                     p->point_const, cost, camrec, g_p, H_pp, W, shared_out, g_band_dev.fg_tracks);
   } else if (tma_ok) {
     auto kern = ba_blocks_kernel<MODEL, MODE, true, 3>;
     VGG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, BT, smem, stream>>>(S, N, tracks_per_warp, p->uv, p->mask, p->poses, p->intr, p->points,
-                                     p->point_const, cost, camrec, g_p, H_pp, W, shared_out);
+                                     p->point_const, cost, camrec, g_p, H_pp, W, shared_out, g_band_dev.fg_tracks);
   } else {
     auto kern = ba_blocks_kernel<MODEL, MODE, false, 3>;
     VGG_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, BT, smem, stream>>>(S, N, tracks_per_warp, p->uv, p->mask, p->poses, p->intr, p->points,
-                                     p->point_const, cost, camrec, g_p, H_pp, W, shared_out);
+                                     p->point_const, cost, camrec, g_p, H_pp, W, shared_out, g_band_dev.fg_tracks);
   }
   VGG_LAUNCH_CHECK();
   if (g_blocks_timing) VGG_CUDA_CHECK(cudaEventRecord(g_blocks_ev[1], stream));

@@ -18,6 +18,9 @@
 
 namespace vgg {
 
+// band structure of the running solve (csrc/ba_solve.cu, compute_band_hint); null pointers: dense
+BandDev g_band_dev = {nullptr, nullptr, nullptr, 0};
+
 // Add v to one element of the reduced-system buffer.  Single GPU: plain f64 RED on the local copy.  Track-sharded
 // multi-GPU ("fabric" mode): ONE multimem reduction on the NVSwitch multicast address, which lands the addend in every
 // rank's copy of the buffer -- the all-reduce of the reduced camera system happens inside the kernels that
@@ -165,11 +168,18 @@ constexpr int ZB_NT = 32;
 __global__ void __launch_bounds__(128) z_build_kernel(int D, int N, int Dpad, size_t pitch, const double* __restrict__ W,
                                                       const double* __restrict__ M, const double* __restrict__ q,
                                                       double* __restrict__ Zt, double* __restrict__ rhs,
-                                                      ptrdiff_t mc_off, unsigned long long* __restrict__ amax) {
+                                                      ptrdiff_t mc_off, unsigned long long* __restrict__ amax,
+                                                      const int* __restrict__ rb_range) {
   __shared__ double sm[ZB_NT][12];
   const int row = blockIdx.x * 128 + threadIdx.x;
   const int n0 = blockIdx.y * ZB_NT;
   const int nt = min(ZB_NT, N - n0);
+  // banded problems: these 32 tracks' rows of Zt lie outside the k range in which this 128-column block is non-zero --
+  // W is zero here (never written after the per-solve memset), nobody reads this part of Zt, nothing to add to rhs
+  if (rb_range) {
+    const int kb_first = (3 * n0) >> 6, kb_last = (3 * (n0 + nt - 1) + 2) >> 6;
+    if (kb_last < rb_range[2 * blockIdx.x] || kb_first >= rb_range[2 * blockIdx.x + 1]) return;
+  }
   for (int e = threadIdx.x; e < nt * 12; e += 128) {
     const int t = e / 12, k = e % 12;
     sm[t][k] = k < 9 ? M[(size_t)(n0 + t) * 9 + k] : q[(size_t)(n0 + t) * 3 + (k - 9)];
@@ -468,18 +478,30 @@ __global__ void cam_step_kernel(int D, const double* __restrict__ dcs, size_t dc
 
 // wacc[n][c] = sum_row W[n][row][c] d_c[row]: one warp per track, lanes stride over the contiguous rows
 __global__ void __launch_bounds__(256) backsub_kernel(int D, int N, size_t pitch, const double* __restrict__ W,
-                                                      const double* __restrict__ d_c, double* __restrict__ wacc) {
+                                                      const double* __restrict__ d_c, double* __restrict__ wacc,
+                                                      const int* __restrict__ kb_rows, int arrow_row) {
   const int lane = threadIdx.x & 31;
   const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (n >= N) return;
   const double* wp = W + (size_t)n * pitch * 3;
   double w0 = 0, w1 = 0, w2 = 0;
+  auto span = [&](int r0, int r1) {
 #pragma unroll 4
-  for (int r = lane; r < D; r += 32) {
-    const double d = __ldg(d_c + r);
-    w0 = fma(wp[(size_t)r * 3], d, w0);
-    w1 = fma(wp[(size_t)r * 3 + 1], d, w1);
-    w2 = fma(wp[(size_t)r * 3 + 2], d, w2);
+    for (int r = r0 + lane; r < r1; r += 32) {
+      const double d = __ldg(d_c + r);
+      w0 = fma(wp[(size_t)r * 3], d, w0);
+      w1 = fma(wp[(size_t)r * 3 + 1], d, w1);
+      w2 = fma(wp[(size_t)r * 3 + 2], d, w2);
+    }
+  };
+  if (kb_rows) {
+    // banded problems: the rows this point can touch (its two k-blocks' row ranges) and the dense arrow
+    const int ka = (3 * n) >> 6, kb = (3 * n + 2) >> 6;
+    const int lo = min(kb_rows[2 * ka], kb_rows[2 * kb]), hi = min(max(kb_rows[2 * ka + 1], kb_rows[2 * kb + 1]), arrow_row);
+    if (lo < hi) span(lo, hi);
+    span(min(arrow_row, D), D);
+  } else {
+    span(0, D);
   }
   w0 = warp_sum(w0); w1 = warp_sum(w1); w2 = warp_sum(w2);
   if (lane == 0) {
@@ -628,13 +650,14 @@ int launch_z_transpose(int D, int N, int Dpad, const double* W, const double* M,
                        double* rhs, ptrdiff_t mc_off, cudaStream_t st, unsigned long long* amax) {
   const size_t pitch = (size_t)(D + (D & 1));
   dim3 grid((D + 127) / 128, (N + ZB_NT - 1) / ZB_NT);
-  z_build_kernel<<<grid, 128, 0, st>>>(D, N, Dpad, pitch, W, M, q, Zt, rhs, mc_off, amax);
+  z_build_kernel<<<grid, 128, 0, st>>>(D, N, Dpad, pitch, W, M, q, Zt, rhs, mc_off, amax, g_band_dev.rb_range);
   VGG_LAUNCH_CHECK();
   return VGG_OK;
 }
 // 0 (default): the reduced system is kept as a row-major LOWER triangle (csrc/chol.cu); 1: both triangles, for the
 // library factorisation A/B (set by csrc/ba_solve.cu from VGG_CHOL)
 int g_fill_upper = 0;
+
 // reduce-scatter destinations of the running multi-GPU solve (set per iteration by csrc/ba_solve.cu; world <= 1: off)
 FabricDev g_fabric_dev = {0, 0, {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}};
 
@@ -682,7 +705,7 @@ int launch_cam_step(int D, const double* dcs, size_t dcs_stride, const double* s
 }
 int launch_backsub(int D, int N, const double* W, const double* d_c, double* wacc, cudaStream_t st) {
   const size_t pitch = (size_t)(D + (D & 1));
-  backsub_kernel<<<(N + 7) / 8, 256, 0, st>>>(D, N, pitch, W, d_c, wacc);
+  backsub_kernel<<<(N + 7) / 8, 256, 0, st>>>(D, N, pitch, W, d_c, wacc, g_band_dev.kb_rows, g_band_dev.arrow_row);
   VGG_LAUNCH_CHECK();
   return VGG_OK;
 }

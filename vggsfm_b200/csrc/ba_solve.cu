@@ -331,6 +331,7 @@ struct Fabric2 {
 extern std::vector<int> g_syrk_kb_ranges;     // csrc/syrk_i8.cu: band hint of the current solve
 extern std::vector<int> g_chol_band_end;      // csrc/chol.cu: block structure of the reduced system (banded + arrow)
 extern int g_chol_arrow_blk;
+extern BandDev g_band_dev;                    // csrc/ba_schur.cu: device tables for ba_blocks / z_build / backsub
 
 // resets the process-wide kernel switches when a solve ends, on every exit path
 struct SolveGuard {
@@ -340,6 +341,7 @@ struct SolveGuard {
     g_syrk_kb_ranges.clear();
     g_chol_band_end.clear();
     g_chol_arrow_blk = 0;
+    g_band_dev = BandDev{nullptr, nullptr, nullptr, 0};
   }
 };
 
@@ -374,10 +376,11 @@ __global__ void __launch_bounds__(256) frame_point_range_kernel(int S, int N, co
 // Per 128-column row block of Zt: the 64-row k-block range outside which the block is exactly zero (Zt row 3n+c belongs to
 // point n; column d < S*dc to frame d / dc; the shared-intrinsics columns see every point).  Leaves the hint empty when
 // the grid is (nearly) dense.  One small kernel + a 8 S byte read-back per solve.
-static int compute_band_hint(const vgg_ba_problem* prob, int dc, int D, int Dpad, int Kpad, cudaStream_t st) {
+static int compute_band_hint(const vgg_ba_problem* prob, int dc, int D, int Dpad, int Kpad, bool multi_rank, cudaStream_t st) {
   g_syrk_kb_ranges.clear();
   g_chol_band_end.clear();
   g_chol_arrow_blk = 0;
+  g_band_dev = BandDev{nullptr, nullptr, nullptr, 0};
   const char* env = getenv("VGG_BAND");                 // read per solve so that a test can compare both paths in one process
   const bool off = env && env[0] == '0';
   const int S = prob->S, N = prob->N, nb = Dpad / 128, KB = (Kpad + 63) / 64;
@@ -427,8 +430,10 @@ static int compute_band_hint(const vgg_ba_problem* prob, int dc, int D, int Dpad
     // blocks i and b meet; the blocks from the first shared-intrinsics column on (and the bordered right-hand-side row)
     // are the dense "arrow".  end[b] = one past the last band block of column b, made non-decreasing (the envelope
     // Cholesky fills) and >= b + 2 so that block row b + 1 always counts as band.
+    // Multi-GPU solves: the ranges above describe THIS rank's tracks only, which is all the kernels that touch its W / Zt
+    // need; the reduced system it factors is the sum over ranks, so the factorisation keeps the dense structure there.
     const int arrow = (S * dc) / 128;
-    if (arrow >= 4) {
+    if (arrow >= 4 && !multi_rank) {
       std::vector<int> end(nb);
       int prev = 0;
       for (int b = 0; b < nb; ++b) {
@@ -447,6 +452,45 @@ static int compute_band_hint(const vgg_ba_problem* prob, int dc, int D, int Dpad
       }
       g_chol_band_end = end;
       g_chol_arrow_blk = arrow;
+      // device tables for the kernels that walk the dense [frames, points] grid (VGG_BAND=2: SYRK/Cholesky hint only)
+      if (!(env && env[0] == '2')) {
+        const int ngroups = (S + 31) / 32;
+        std::vector<int> tab(2 * (size_t)(nb + KB + ngroups), 0);
+        int* t_rb = tab.data();
+        int* t_kb = t_rb + 2 * nb;
+        int* t_fg = t_kb + 2 * KB;
+        for (int i = 0; i < 2 * nb; ++i) t_rb[i] = rg[i];
+        for (int kb = 0; kb < KB; ++kb) {
+          int first = -1, last = -1;
+          for (int rb = 0; rb < arrow; ++rb)
+            if (rg[2 * rb] <= kb && kb < rg[2 * rb + 1]) {
+              if (first < 0) first = rb;
+              last = rb;
+            }
+          t_kb[2 * kb] = first < 0 ? 0 : first * 128;
+          t_kb[2 * kb + 1] = first < 0 ? 0 : (last + 1) * 128;
+        }
+        for (int g = 0; g < ngroups; ++g) {
+          int lo = N, hi = 0;
+          for (int f = 32 * g; f < std::min(S, 32 * g + 32); ++f) {
+            if (fr[2 * f + 1] < 0) continue;
+            lo = std::min(lo, fr[2 * f]);
+            hi = std::max(hi, fr[2 * f + 1] + 1);
+          }
+          t_fg[2 * g] = hi > lo ? lo : 0;
+          t_fg[2 * g + 1] = hi > lo ? hi : 0;
+        }
+        static thread_local int* tdev = nullptr;
+        static thread_local size_t tcap = 0;
+        if (tcap < tab.size()) {
+          if (tdev) cudaFree(tdev);
+          VGG_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&tdev), sizeof(int) * tab.size()));
+          tcap = tab.size();
+        }
+        VGG_CUDA_CHECK(cudaMemcpyAsync(tdev, tab.data(), sizeof(int) * tab.size(), cudaMemcpyHostToDevice, st));
+        VGG_CUDA_CHECK(cudaStreamSynchronize(st));           // pageable source
+        g_band_dev = BandDev{tdev, tdev + 2 * nb, tdev + 2 * (nb + KB), arrow * 128};
+      }
     }
   }
   return VGG_OK;
@@ -676,7 +720,13 @@ int vgg_ba_solve_fabric(const vgg_ba_problem* prob, const vgg_ba_options* opt_in
       VGG_REQUIRE(allreduce, "fabric v1 needs the hook for its barrier (op 2)");
     }
   }
-  if (L.oz_bytes && (rc = compute_band_hint(prob, dc, D, L.Dpad, L.Kpad, st))) return rc;
+  if (L.oz_bytes && (rc = compute_band_hint(prob, dc, D, L.Dpad, L.Kpad, allreduce != nullptr || fabric != nullptr, st))) return rc;
+  if (g_band_dev.fg_tracks) {
+    // the kernels skip the (track chunk, frame group) regions no observation falls into: their W blocks must read as zero
+    const size_t w_doubles = (size_t)N * (size_t)(D + (D & 1)) * 3;
+    VGG_CUDA_CHECK(cudaMemsetAsync(L.blk[0].W, 0, sizeof(double) * w_doubles, st));
+    VGG_CUDA_CHECK(cudaMemsetAsync(L.blk[1].W, 0, sizeof(double) * w_doubles, st));
+  }
   double* Sraw = L.AR;
   double* rhs = L.AR + (size_t)D * L.Dpad;
   double* hdiag = rhs + L.Dpad;
