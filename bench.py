@@ -547,6 +547,7 @@ def run_gpu(args):
     cpu_base = None
     corr = None
     small = None
+    c5 = None
     if rank == 0:
         peak, peak_src = load_peaks()
         dc, ns = ba.dims(model, mode)
@@ -628,6 +629,22 @@ def run_gpu(args):
         if world == 1 and not args.no_corr:
             torch.cuda.empty_cache()
             corr = corr_section(dev, peak)
+        if world == 1 and not args.no_c5:
+            # C5 (BASELINE.json configs[4]): the synthetic 1000-frame sequential run of tools/video_c5.py, and its last joint
+            # BA alone (second of two solves: the first one pays the CUDA-graph captures and the work-list plans)
+            try:
+                torch.cuda.empty_cache()
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                import video_c5
+                seq = video_c5.run(dev=dev)
+                fin = video_c5.final_problem(dev=dev, reps=2)
+                c5 = {"sequence": {k: seq[k] for k in ("workload", "frames", "seconds", "frames_per_s", "split_seconds", "windows",
+                                                         "joint_bas", "joint_iterations", "window_iterations",
+                                                         "camera_centre_rmse_vs_gt", "trajectory_length")},
+                      "final_joint_ba": {"workload": fin["workload"], "seconds": fin["seconds"][-1],
+                                         "lm_iterations": fin["lm_iterations"][-1], "lm_it_per_s": fin["lm_it_per_s"][-1]}}
+            except Exception as e:
+                c5 = {"error": str(e)[:200]}
         if world == 1:
             v, dt = cpu_ba_sample(sc, extr, K, extra, pts, 3)
             tv, tdt, tkind = cpu_tri_sample(sc, 16)
@@ -648,7 +665,7 @@ def run_gpu(args):
             "tracks_per_s": tracks_per_s, "tri_ms_per_pass": tri_ms / args.steps, "tri_median_point_error": tri_median_err,
             "e2e": {"value": e2e_value, "unit": "it/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "roofline_syrk": roof_syrk,
-            "cpu_baseline": cpu_base, "corr": corr, "small_problems": small,
+            "cpu_baseline": cpu_base, "corr": corr, "small_problems": small, "c5": c5,
         }
         line["config"]["syrk"] = os.environ.get("VGG_SYRK", "ozaki:7") + " (default: tcgen05 kind::i8, 7 Ozaki slices, FP64-equivalent)"
         if hook is not None:
@@ -668,6 +685,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-corr", action="store_true", help="skip the C4 correlation section (rank 0, N=1 only)")
+    ap.add_argument("--no-c5", action="store_true", help="skip the C5 sequential-video section (rank 0, N=1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

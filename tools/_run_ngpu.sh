@@ -3,7 +3,7 @@ N=$1
 set -x
 nvidia-smi -L | head -8
 for v in 2 0; do
-  VGG_FABRIC=$v timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$v bench.py --gpus $N --steps 5 --warmup 3 --no-corr > gpurun_out/r02_bench_${N}gpu_fabric$v.json 2> gpurun_out/r02_bench_${N}gpu_fabric$v.err
+  VGG_FABRIC=$v timeout 400 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 2951$v bench.py --gpus $N --steps 5 --warmup 3 --no-corr --no-c5 > gpurun_out/r02_bench_${N}gpu_fabric$v.json 2> gpurun_out/r02_bench_${N}gpu_fabric$v.err
   grep '^{' gpurun_out/r02_bench_${N}gpu_fabric$v.json | tail -1 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
