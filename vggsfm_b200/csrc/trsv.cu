@@ -23,7 +23,7 @@ constexpr unsigned long long TS_SENTINEL = 0xffffffffffffffffull;   // x is pre-
 
 __global__ void __launch_bounds__(TS_THREADS, 1)
     trsv_upper_kernel(int n, int lda, const double* __restrict__ A, const double* __restrict__ y, size_t y_stride,
-                      double* __restrict__ x, int* flags, int epoch) {
+                      double* __restrict__ x, int* flags, int epoch, int use_flag) {
   extern __shared__ __align__(16) double ts_smem[];
   double(*Ud)[TS_NB + 1] = reinterpret_cast<double(*)[TS_NB + 1]>(ts_smem);                            // diagonal block
   double(*Vi)[TS_NB + 1] = reinterpret_cast<double(*)[TS_NB + 1]>(ts_smem + TS_NB * (TS_NB + 1));      // its inverse
@@ -82,7 +82,21 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
   auto hop = [&](const double (&tile)[16], int j) {
     // x_j arrives as data: the buffer was pre-filled with a sentinel NaN pattern, every element is polled by one thread
     // (8-byte stores are single-copy atomic, so no flag, no fence and no second round trip are needed)
-    if (tid < TS_NB) {
+    if (use_flag) {
+      // ONE thread of the CTA watches block j's flag (with a short back-off), then 64 threads fetch the block through L2.
+      // The data-as-flag variant below has every waiting CTA poll 64 elements: up to 37 CTAs x 64 threads hammer the
+      // four L2 lines of the newest block, and the producer's stores queue behind them.
+      if (tid == 0) {
+        int seen;
+        while (true) {
+          asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flags + j) : "memory");
+          if (seen == epoch) break;
+          __nanosleep(40);
+        }
+      }
+      __syncthreads();
+      if (tid < TS_NB) xs[tid] = (j * TS_NB + tid < n) ? __ldcg(&x[j * TS_NB + tid]) : 0.0;
+    } else if (tid < TS_NB) {
       double v = 0.0;
       if (j * TS_NB + tid < n) {
         const volatile unsigned long long* src = reinterpret_cast<const volatile unsigned long long*>(&x[j * TS_NB + tid]);
@@ -148,6 +162,13 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
       *reinterpret_cast<volatile unsigned long long*>(&x[r0 + r]) = bits;
     }
   }
+  if (use_flag) {
+    __syncthreads();                                    // all 64 stores issued
+    if (tid == 0) {
+      __threadfence();
+      asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flags + b), "r"(epoch) : "memory");
+    }
+  }
 }
 
 }  // namespace
@@ -166,9 +187,17 @@ int launch_trsv_upper(int n, int lda, const double* A, const double* y, size_t y
     VGG_CUDA_CHECK(cudaFuncSetAttribute(trsv_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  (void)flags;
-  VGG_CUDA_CHECK(cudaMemsetAsync(x, 0xFF, sizeof(double) * (size_t)n, st));     // sentinel fill: x_j is polled as data
-  trsv_upper_kernel<<<nb, TS_THREADS, smem, st>>>(n, lda, A, y, y_stride, x, flags, epoch);
+  // VGG_TRSV_POLL=data: every waiting thread polls the solution elements themselves (the r01 hand-off); default: one flag
+  // per block row, one polling thread per CTA.
+  static const bool use_flag = [] { const char* e = getenv("VGG_TRSV_POLL"); return !(e && e[0] == 'd'); }();
+  if (use_flag) {
+    VGG_REQUIRE(flags, "trsv_upper: flag workspace missing");
+    epoch = 1;
+    VGG_CUDA_CHECK(cudaMemsetAsync(flags, 0, sizeof(int) * (size_t)nb, st));    // nobody has published anything yet
+  } else {
+    VGG_CUDA_CHECK(cudaMemsetAsync(x, 0xFF, sizeof(double) * (size_t)n, st));   // sentinel fill: x_j is polled as data
+  }
+  trsv_upper_kernel<<<nb, TS_THREADS, smem, st>>>(n, lda, A, y, y_stride, x, flags, epoch, use_flag ? 1 : 0);
   VGG_LAUNCH_CHECK();
   return VGG_OK;
 }
