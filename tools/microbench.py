@@ -77,6 +77,40 @@ if mode in ("pose", "pipeline"):
           f"valid frames {int(out[6].sum())}")
     sys.exit(0)
 
+if mode == "trsv":
+    import ctypes
+    from vggsfm_b200 import _lib
+    L = _lib.lib()
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 2402
+    lda = (n + 2 + 127) // 128 * 128
+    rng = np.random.default_rng(0)
+    U = np.triu(rng.normal(size=(n, n)) * 0.05) + np.eye(n)
+    A = np.zeros((n, lda))
+    A[:, :n] = U
+    y = rng.normal(size=n)
+    Ad, yd = torch.from_numpy(A).to(dev), torch.from_numpy(y).to(dev)
+    xd = torch.empty(n, dtype=torch.float64, device=dev)
+    nb = (n + 63) // 64
+    st = np.zeros(6 * nb, dtype=np.int64)
+    for _ in range(3):
+        _lib.check(L.vgg_dev_trsv_probe(n, lda, Ad.data_ptr(), yd.data_ptr(), xd.data_ptr(), st.ctypes.data), "probe")
+    x = xd.cpu().numpy()
+    print(f"[{tag}] trsv n={n}: |Ux-y|/|y| = {np.linalg.norm(U @ x - y) / np.linalg.norm(y):.2e}")
+    ent, lod, inv, see, pub, rhs = st[0::6], st[1::6], st[2::6], st[3::6], st[4::6], st[5::6]
+    t0 = pub[nb - 1]
+    print(f"  start-up of the last block row: entry -> block loaded {(lod[nb-1]-ent[nb-1])/1e3:.2f} us, -> inverse ready {(inv[nb-1]-lod[nb-1])/1e3:.2f} us, "
+          f"-> published {(pub[nb-1]-inv[nb-1])/1e3:.2f} us; entry spread over CTAs {(ent.max()-ent.min())/1e3:.2f} us; "
+          f"block row 0: inverse ready {(inv[0]-ent[0])/1e3:.2f} us after entry")
+    print("  per block row, us since its own kernel entry: diagonal block loaded / inverse ready / rhs in shared memory / saw-all / published")
+    for b in range(nb - 1, -1, -1):
+        print(f"    {b:3d}  {(lod[b]-ent[b])/1e3:7.2f} {(inv[b]-ent[b])/1e3:7.2f} rhs {(rhs[b]-ent[b])/1e3:7.2f} {(see[b]-ent[b])/1e3:8.2f} {(pub[b]-ent[b])/1e3:8.2f}")
+    print("  block  saw-all(us)  published(us)  compute(us)  hand-off to next(us)")
+    for b in range(nb - 1, -1, -1):
+        hand = (see[b - 1] - pub[b]) / 1e3 if b > 0 else float("nan")
+        print(f"  {b:5d}  {(see[b] - t0) / 1e3:10.2f}  {(pub[b] - t0) / 1e3:12.2f}  {(pub[b] - see[b]) / 1e3:10.2f}  {hand:10.2f}")
+    print(f"  total chain {(pub[0] - t0) / 1e3:.1f} us after the last block row published")
+    sys.exit(0)
+
 if mode == "chol128":
     import ctypes
     from vggsfm_b200 import _lib

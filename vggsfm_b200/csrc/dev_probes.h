@@ -24,6 +24,9 @@ int vgg_dev_chol128_probe(int leaf, int reps, const double* A_host, double* L_ho
  * 128-column row block rb of Zt is exactly zero (count = 2 * Dpad/128; count = 0 clears it).  vgg_ba_solve computes the
  * same thing from the visibility mask and clears it when it returns. */
 int vgg_dev_set_syrk_ranges(const int* ranges_host, int count);
+/* Backward substitution (csrc/trsv.cu) with per-block-row timestamps (ns): stamps_host[2 b] = block row b (64 rows) has
+ * consumed every x_j it needs, [2 b + 1] = x_b published.  A_dev: row-major upper triangle, lda columns. */
+int vgg_dev_trsv_probe(int n, int lda, const double* A_dev, const double* y_dev, double* x_dev, long long* stamps_host);
 
 #ifdef __cplusplus
 }

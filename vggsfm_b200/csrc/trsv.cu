@@ -35,6 +35,20 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
   const int rows = min(TS_NB, n - r0);
   const int tid = threadIdx.x;
   const int r = tid >> 2, seg = tid & 3;      // row of the block, 16-column segment
+  // use_flag == 2 (tools/microbench.py trsv): globaltimer stamps into flags (as int64, 5 per block row): kernel entry,
+  // diagonal block loaded, inverse ready, every x_j consumed, x_b published
+  long long* stamps = reinterpret_cast<long long*>(flags);
+  auto now_ns = []() {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+  };
+  if (use_flag == 2 && tid == 0) stamps[6 * b] = now_ns();
+  // this block row's right-hand side, requested FIRST: r02 timestamps showed this one 8-byte load per thread taking
+  // ~19 us when it was issued after the inversion (every block row, same absolute completion time) -- and the whole
+  // chain waits for the last block row.  Issued here it completes under the block load and the inversion.
+  double y_mine = 0.0;
+  if (tid < TS_NB && tid < rows) y_mine = __ldcg(&y[(size_t)(r0 + tid) * y_stride]);
 
   // ---- diagonal block and its inverse (upper triangular; padded rows/cols = identity)
   for (int e = tid; e < TS_NB * TS_NB; e += TS_THREADS) {
@@ -44,30 +58,32 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     Ud[i][j] = v;
   }
   __syncthreads();
+  if (use_flag == 2 && tid == 0) stamps[6 * b + 1] = now_ns();
   if (tid < TS_NB) xs[tid] = 1.0 / Ud[tid][tid];       // reciprocal pivots (xs is free until the first hop)
   __syncthreads();
-  if (tid < TS_NB) {
-    // column tid of inv(U): back substitution U v = e_tid (entries below the diagonal are zero); two partial sums
-    const int c = tid;
+  {
+    // column c = tid / 4 of inv(U) by back substitution U v = e_c (entries below the diagonal are zero); the four threads
+    // of a column split every row's dot product over k (one warp holds 8 columns, so a __syncwarp orders the rows).
+    // r02 timestamps (tools/microbench.py trsv): with ONE thread per column this start-up took ~50 us of the kernel's
+    // 150 -- the chain through the 38 block rows cannot begin before the last block row has its inverse.
+    const int c = tid >> 2, part = tid & 3;
     for (int i = TS_NB - 1; i >= 0; --i) {
-      double v = 0.0;
-      if (i <= c) {
-        double s0 = (i == c) ? 1.0 : 0.0, s1 = 0.0;
-        int k = i + 1;
-        for (; k + 1 <= c; k += 2) {
-          s0 = fma(-Ud[i][k], Vi[k][c], s0);
-          s1 = fma(-Ud[i][k + 1], Vi[k + 1][c], s1);
-        }
-        if (k <= c) s0 = fma(-Ud[i][k], Vi[k][c], s0);
-        v = (s0 + s1) * xs[i];
+      double s = 0.0;
+      if (i < c) {
+        for (int k = i + 1 + part; k <= c; k += 4) s = fma(-Ud[i][k], Vi[k][c], s);
       }
-      Vi[i][c] = v;
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      if (part == 0) Vi[i][c] = i > c ? 0.0 : (i == c ? xs[i] : s * xs[i]);
+      __syncwarp();
     }
   }
   __syncthreads();
+  if (use_flag == 2 && tid == 0) stamps[6 * b + 2] = now_ns();
   // ---- right-hand side rows of this block
-  if (tid < TS_NB) accs[tid] = (tid < rows) ? y[(size_t)(r0 + tid) * y_stride] : 0.0;
+  if (tid < TS_NB) accs[tid] = y_mine;
   __syncthreads();
+  if (use_flag == 2 && tid == 0) stamps[6 * b + 5] = now_ns();
 
   // ---- block columns to the right, last first; tile j+... prefetched into registers before its x is awaited
   // three tiles are kept in flight in registers (tiles do not depend on x, only x_j does)
@@ -82,7 +98,7 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
   auto hop = [&](const double (&tile)[16], int j) {
     // x_j arrives as data: the buffer was pre-filled with a sentinel NaN pattern, every element is polled by one thread
     // (8-byte stores are single-copy atomic, so no flag, no fence and no second round trip are needed)
-    if (use_flag) {
+    if (use_flag == 1) {
       // ONE thread of the CTA watches block j's flag (with a short back-off), then 64 threads fetch the block through L2.
       // The data-as-flag variant below has every waiting CTA poll 64 elements: up to 37 CTAs x 64 threads hammer the
       // four L2 lines of the newest block, and the producer's stores queue behind them.
@@ -123,6 +139,10 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     __syncthreads();                           // xs is rewritten in the next round
   };
   int j = nb - 1;
+  // The last block row has no block column to its right.  It must not even WALK the (long, straight-line) prefetch and
+  // hop code below: r02 timestamps showed it spending 20 us between "inverse ready" and its publication with nothing to
+  // compute -- 11 KB of cold instructions fetched line by line -- and every other block row waits for it.
+  if (b < nb - 1) {
   load_tile(t0, j);
   load_tile(t1, j - 1);
   load_tile(t2, j - 2);
@@ -137,6 +157,8 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
     load_tile(t2, j - 3);
     --j;
   }
+  }
+  if (use_flag == 2 && tid == 0) stamps[6 * b + 3] = now_ns();      // every x_j this block row needs has been consumed
   // reduce the four segments of a row, subtract from the right-hand side
   acc += __shfl_xor_sync(0xffffffffu, acc, 1);
   acc += __shfl_xor_sync(0xffffffffu, acc, 2);
@@ -161,6 +183,11 @@ __global__ void __launch_bounds__(TS_THREADS, 1)
       if (s != s) bits = 0x7ff8000000000000ull;        // never publish the sentinel pattern
       *reinterpret_cast<volatile unsigned long long*>(&x[r0 + r]) = bits;
     }
+  }
+  if (use_flag == 2) {
+    __syncthreads();
+    if (tid == 0) stamps[6 * b + 4] = now_ns();
+    return;
   }
   if (use_flag) {
     __syncthreads();                                    // all 64 stores issued
@@ -187,9 +214,10 @@ int launch_trsv_upper(int n, int lda, const double* A, const double* y, size_t y
     VGG_CUDA_CHECK(cudaFuncSetAttribute(trsv_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
-  // VGG_TRSV_POLL=data: every waiting thread polls the solution elements themselves (the r01 hand-off); default: one flag
-  // per block row, one polling thread per CTA.
-  static const bool use_flag = [] { const char* e = getenv("VGG_TRSV_POLL"); return !(e && e[0] == 'd'); }();
+  // VGG_TRSV_POLL=flag: one flag per block row and one polling thread per CTA instead of polling the solution elements
+  // themselves.  Measured r02: 160.6 us against 150.6 us for the data hand-off -- the fence + flag round trip costs more
+  // than the 64-thread polling it removes, so the default stays the data hand-off.
+  static const bool use_flag = [] { const char* e = getenv("VGG_TRSV_POLL"); return e && e[0] == 'f'; }();
   if (use_flag) {
     VGG_REQUIRE(flags, "trsv_upper: flag workspace missing");
     epoch = 1;
@@ -203,3 +231,22 @@ int launch_trsv_upper(int n, int lda, const double* A, const double* y, size_t y
 }
 
 }  // namespace vgg
+
+// tools/microbench.py trsv: the backward substitution on a random well-conditioned upper triangle, with per-block-row
+// timestamps (ns, globaltimer): stamps_host[2 b] = block row b has consumed every x_j it needs, [2 b + 1] = x_b published
+extern "C" int vgg_dev_trsv_probe(int n, int lda, const double* A_dev, const double* y_dev, double* x_dev, long long* stamps_host) {
+  using namespace vgg;
+  const int nb = (n + TS_NB - 1) / TS_NB;
+  long long* d = nullptr;
+  VGG_CUDA_CHECK(cudaMalloc(&d, sizeof(long long) * 6 * nb));
+  VGG_CUDA_CHECK(cudaMemset(d, 0, sizeof(long long) * 6 * nb));
+  const size_t smem = sizeof(double) * (2 * TS_NB * (TS_NB + 1) + 2 * TS_NB);
+  VGG_CUDA_CHECK(cudaFuncSetAttribute(trsv_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  VGG_CUDA_CHECK(cudaMemset(x_dev, 0xFF, sizeof(double) * (size_t)n));
+  trsv_upper_kernel<<<nb, TS_THREADS, smem>>>(n, lda, A_dev, y_dev, 1, x_dev, reinterpret_cast<int*>(d), 1, 2);
+  VGG_LAUNCH_CHECK();
+  VGG_CUDA_CHECK(cudaDeviceSynchronize());
+  VGG_CUDA_CHECK(cudaMemcpy(stamps_host, d, sizeof(long long) * 6 * nb, cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  return VGG_OK;
+}
