@@ -85,10 +85,12 @@ if mode == "trsv":
     lda = (n + 2 + 127) // 128 * 128
     rng = np.random.default_rng(0)
     U = np.triu(rng.normal(size=(n, n)) * 0.05) + np.eye(n)
-    A = np.zeros((n, lda))
-    A[:, :n] = U
+    A = np.zeros((n + 1, lda))
+    A[:n, :n] = U
     y = rng.normal(size=n)
-    Ad, yd = torch.from_numpy(A).to(dev), torch.from_numpy(y).to(dev)
+    A[n, :n] = y                                     # like the LM: the right-hand side is the row below the triangle
+    Ad = torch.from_numpy(A).to(dev)
+    yd = Ad[n]
     xd = torch.empty(n, dtype=torch.float64, device=dev)
     nb = (n + 63) // 64
     st = np.zeros(6 * nb, dtype=np.int64)

@@ -237,8 +237,13 @@ int launch_trsv_upper(int n, int lda, const double* A, const double* y, size_t y
 extern "C" int vgg_dev_trsv_probe(int n, int lda, const double* A_dev, const double* y_dev, double* x_dev, long long* stamps_host) {
   using namespace vgg;
   const int nb = (n + TS_NB - 1) / TS_NB;
-  long long* d = nullptr;
-  VGG_CUDA_CHECK(cudaMalloc(&d, sizeof(long long) * 6 * nb));
+  static long long* d = nullptr;                      // allocated once: a cudaMalloc / cudaFree pair per call would put
+  static int d_cap = 0;                                // allocator work (and its TLB effects) right in front of the kernel
+  if (d_cap < 6 * nb) {
+    if (d) cudaFree(d);
+    VGG_CUDA_CHECK(cudaMalloc(&d, sizeof(long long) * 6 * nb));
+    d_cap = 6 * nb;
+  }
   VGG_CUDA_CHECK(cudaMemset(d, 0, sizeof(long long) * 6 * nb));
   const size_t smem = sizeof(double) * (2 * TS_NB * (TS_NB + 1) + 2 * TS_NB);
   VGG_CUDA_CHECK(cudaFuncSetAttribute(trsv_upper_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -247,6 +252,5 @@ extern "C" int vgg_dev_trsv_probe(int n, int lda, const double* A_dev, const dou
   VGG_LAUNCH_CHECK();
   VGG_CUDA_CHECK(cudaDeviceSynchronize());
   VGG_CUDA_CHECK(cudaMemcpy(stamps_host, d, sizeof(long long) * 6 * nb, cudaMemcpyDeviceToHost));
-  cudaFree(d);
   return VGG_OK;
 }
