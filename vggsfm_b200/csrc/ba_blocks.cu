@@ -391,6 +391,12 @@ static int launch_blocks(const vgg_ba_problem* p, double* cost, double* camrec, 
   const bool tma_ok = ((reinterpret_cast<uintptr_t>(W) & 15) == 0);
   const int ngroups = (S + 31) / 32;
   static const int minb = [] { const char* e = getenv("VGG_K1_MINB"); return (e && e[0] == '3') ? 3 : 2; }();
+  if (tracks_per_warp <= 0 && g_band_dev.fg_tracks) {
+    // banded (sequential) problems: most (frame group, track chunk) warps return at once, so the chunks must be small
+    // enough for the few that do not to spread over the machine (r02 launch list at 1000 frames x 32 k points: with the
+    // dense sizing ~220 warps of 500 tracks each did all the work, 0.43 ms; the visible part is 0.5 GB)
+    tracks_per_warp = 64;
+  }
   if (tracks_per_warp <= 0) {
     // Every warp does the same amount of work, so the grid must be a whole number of waves: resident warps =
     // SMs x CTAs/SM (occupancy query) x BW.  Pick the smallest wave count that keeps >= 32 tracks per warp
