@@ -1,4 +1,4 @@
-# usage: bash tools/_run_ngpu.sh N   (inside gpurun --gpus N)
+# usage: bash tools/bench_ngpu.sh N   (inside gpurun --gpus N)
 N=$1
 set -x
 nvidia-smi -L | head -8
