@@ -259,3 +259,40 @@ def test_cholesky_matches_lapack(cuda_dev, n):
     _lib.check(L.vgg_cholesky_lower(n, lda, buf.data_ptr(), ws.data_ptr(), ws.numel(), ctypes.byref(info),
                                     torch.cuda.current_stream().cuda_stream), "vgg_cholesky_lower")
     assert info.value == (70 % n) + 1
+
+
+@pytest.mark.parametrize("nblk,bw,tail", [(12, 2, 0), (20, 3, 77), (9, 1, 5)])
+def test_cholesky_band_plus_arrow_matches_lapack(cuda_dev, nblk, bw, tail):
+    """The band-aware schedule of csrc/chol.cu (sequential / video problems: block band + dense arrow; panels and
+    trailing tiles restricted to the structure, f64 REDs) against numpy on a random matrix WITH that structure."""
+    import ctypes
+    import torch
+    from vggsfm_b200 import _lib
+    n = nblk * 128 + tail                      # the arrow is the last full block (+ the partial tail)
+    arrow = nblk - 1
+    rng = np.random.default_rng(nblk * 10 + bw)
+    G = rng.normal(size=(n, n)) * 0.05
+    blk = np.arange(n) // 128
+    keep = (np.abs(blk[:, None] - blk[None, :]) <= bw) | (blk[:, None] >= arrow) | (blk[None, :] >= arrow)
+    A = (G + G.T) * keep
+    A += np.diag(np.abs(A).sum(1) + 1.0)       # diagonally dominant: SPD with the same structure
+    nb_all = (n + 127) // 128
+    end = np.array([nb_all if b >= arrow else min(arrow, max(b + bw + 1, b + 2)) for b in range(nb_all)], dtype=np.int32)
+    lda = nb_all * 128
+    buf = torch.zeros(n, lda, dtype=torch.float64, device=cuda_dev)
+    buf[:, :n] = torch.from_numpy(np.tril(A)).to(cuda_dev)
+    ws = torch.empty(nb_all * 131072 + 1024, dtype=torch.uint8, device=cuda_dev)
+    info = ctypes.c_int(-1)
+    L = _lib.lib()
+    _lib.check(L.vgg_dev_set_chol_band(end.ctypes.data, end.size, arrow), "band")
+    try:
+        _lib.check(L.vgg_cholesky_lower(n, lda, buf.data_ptr(), ws.data_ptr(), ws.numel(), ctypes.byref(info),
+                                        torch.cuda.current_stream().cuda_stream), "vgg_cholesky_lower")
+    finally:
+        L.vgg_dev_set_chol_band(None, 0, 0)
+    assert info.value == 0
+    ref = np.linalg.cholesky(A)
+    got = np.tril(buf.cpu().numpy()[:, :n])
+    assert np.abs(got - ref).max() <= 1e-10 * np.abs(ref).max()
+    # the factor keeps the structure (no fill outside band + arrow), which is what the schedule relies on
+    assert not np.abs(ref * ~keep).max() > 1e-12

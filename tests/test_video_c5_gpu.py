@@ -37,3 +37,19 @@ def test_band_hint_does_not_change_the_joint_ba(cuda_dev):
     for band in ("2", "1"):
         assert res["0"][0] > 5 and res[band][0] > 5
         assert abs(res["0"][1] - res[band][1]) <= 1e-9 * abs(res["0"][1]), band
+
+
+def test_band_detection_is_safe_for_unordered_points(cuda_dev):
+    """Points in random order: every frame's [first, last] visible point spans almost everything, the hint must either
+    stay off or change nothing."""
+    import video_c5
+    from vggsfm_b200 import video
+    res = {}
+    for band in ("0", "1"):
+        os.environ["VGG_BAND"] = band
+        try:
+            video_c5.final_problem(frames=256, new_per_window=128, dev=cuda_dev, reps=1, shuffle=True)
+            res[band] = float(video.last_joint_summary.final_cost)
+        finally:
+            os.environ.pop("VGG_BAND", None)
+    assert abs(res["0"] - res["1"]) <= 1e-9 * abs(res["0"])

@@ -167,7 +167,7 @@ def run(frames=1000, new_per_window=512, joint_every=6, seed=0, dev=None, verbos
             "trajectory_length": float(np.linalg.norm(Cg[-1] - Cg[0])), "store_points": store.num_points}
 
 
-def final_problem(frames=1000, new_per_window=512, seed=0, dev=None, reps=1):
+def final_problem(frames=1000, new_per_window=512, seed=0, dev=None, reps=1, shuffle=False):
     """Only the LAST joint BA of the sequence, built directly from the synthetic scene (ground truth + noise instead of
     the sequential estimates): the problem the launch lists and the multi-GPU leg look at."""
     dev = dev or torch.device("cuda:0")
@@ -191,7 +191,11 @@ def final_problem(frames=1000, new_per_window=512, seed=0, dev=None, reps=1):
     extr[:, :, 3] += rng.normal(size=(frames, 3)) * 0.005
     pts = sc.points3d[keep] + rng.normal(size=(int(keep.sum()), 3)) * 0.01
     K = torch.tensor([[[sc.focal, 0.0, sc.pp[0]], [0.0, sc.focal, sc.pp[1]], [0.0, 0.0, 1.0]]], dtype=torch.float64, device=dev)
-    tracks, masks = T(uv[:, keep]), T(ok[:, keep])
+    uvk, okk = uv[:, keep], ok[:, keep]
+    if shuffle:                                              # points in random order: the band detection finds nothing to skip
+        perm = rng.permutation(pts.shape[0])
+        uvk, okk, pts = uvk[:, perm], okk[:, perm], pts[perm]
+    tracks, masks = T(uvk), T(okk)
     xyz, ex0 = T(pts), T(extr)
     times, its = [], []
     for _ in range(reps):

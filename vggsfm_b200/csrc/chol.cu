@@ -1020,3 +1020,13 @@ extern "C" int vgg_dev_chol128_probe(int leaf, int reps, const double* A_host, d
   cudaFree(dP);
   return VGG_OK;
 }
+
+// tests: install / clear (count = 0) the block structure the next factorisations assume (csrc/ba_solve.cu sets the same
+// globals from the visibility mask for the duration of a solve)
+extern "C" int vgg_dev_set_chol_band(const int* end_blk_host, int count, int arrow_blk) {
+  using namespace vgg;
+  g_chol_band_end.assign(end_blk_host, end_blk_host + (count > 0 ? count : 0));
+  g_chol_arrow_blk = count > 0 ? arrow_blk : 0;
+  return VGG_OK;
+}
+

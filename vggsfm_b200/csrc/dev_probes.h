@@ -27,6 +27,9 @@ int vgg_dev_set_syrk_ranges(const int* ranges_host, int count);
 /* Backward substitution (csrc/trsv.cu) with per-block-row timestamps (ns): stamps_host[2 b] = block row b (64 rows) has
  * consumed every x_j it needs, [2 b + 1] = x_b published.  A_dev: row-major upper triangle, lda columns. */
 int vgg_dev_trsv_probe(int n, int lda, const double* A_dev, const double* y_dev, double* x_dev, long long* stamps_host);
+/* Block structure for the in-repo Cholesky (tests): end_blk_host[b] = one past the last band block (128 rows) of block
+ * column b, arrow_blk = first block of the dense arrow; count = 0 clears it (dense). */
+int vgg_dev_set_chol_band(const int* end_blk_host, int count, int arrow_blk);
 
 #ifdef __cplusplus
 }
