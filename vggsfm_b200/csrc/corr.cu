@@ -193,6 +193,122 @@ __global__ void __launch_bounds__(256) corr_sample_kernel(int BS, int N, int L, 
   }
 }
 
+// C = 32 (the fine tracker's patch pyramids): lanes over FOOTPRINT POSITIONS instead of channels.  With one channel per
+// lane every position was one 64-byte load per warp instruction (half pyramid) followed by a 32-lane reduce-scatter --
+// r02 ncu: 146 registers, one CTA per SM, issue slots 46 %, 2 TB/s.  Here a lane owns positions lane, lane + 32, ...:
+// it loads the position's whole 32-channel vector with 16-byte loads (8 neighbouring positions = 512 contiguous bytes),
+// keeps the 32 target values in registers and writes the finished dot product -- no shuffles at all.
+template <typename T> struct Vec32;
+template <> struct Vec32<float> {
+  static __device__ __forceinline__ float dot(const float* __restrict__ p, const float (&tg)[32]) {
+    float acc = 0.f;
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      const float4 f = *reinterpret_cast<const float4*>(p + 4 * v);
+      acc = fmaf(tg[4 * v], f.x, acc);
+      acc = fmaf(tg[4 * v + 1], f.y, acc);
+      acc = fmaf(tg[4 * v + 2], f.z, acc);
+      acc = fmaf(tg[4 * v + 3], f.w, acc);
+    }
+    return acc;
+  }
+};
+template <> struct Vec32<__half> {
+  static __device__ __forceinline__ float dot(const __half* __restrict__ p, const float (&tg)[32]) {
+    float acc = 0.f;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(p + 8 * v);
+      const __half2* h = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(h[i]);
+        acc = fmaf(tg[8 * v + 2 * i], f.x, acc);         // same summation order as the channel-per-lane kernel is NOT
+        acc = fmaf(tg[8 * v + 2 * i + 1], f.y, acc);     // kept (that one reduces across lanes); both are fp32 sums
+      }
+    }
+    return acc;
+  }
+};
+
+template <typename T, int R>
+__global__ void __launch_bounds__(256, 2) corr_sample_c32_kernel(int BS, int N, int L, CorrLevels lv,
+                                                                 const float* __restrict__ targets /*[BS,N,32]*/,
+                                                                 const float* __restrict__ coords /*[BS,N,2]*/, int border,
+                                                                 float* __restrict__ out /*[BS,N,L*(2R+1)^2]*/) {
+  constexpr int C = 32;
+  constexpr int FP = 2 * R + 2;          // footprint side
+  constexpr int NF = FP * FP;            // footprint positions
+  constexpr int NPL = (NF + 31) / 32;    // positions per lane
+  constexpr int K = 2 * R + 1;
+  __shared__ float dsm[8][NPL * 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t q = (size_t)blockIdx.x * 8 + warp;
+  if (q >= (size_t)BS * N) return;
+  const size_t img = q / N;
+  float tg[C];
+  {
+    const float4* tp = reinterpret_cast<const float4*>(targets + q * C);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) {
+      const float4 t = tp[v];
+      tg[4 * v] = (float)(T)t.x;          // round to the pyramid precision like autocast does
+      tg[4 * v + 1] = (float)(T)t.y;
+      tg[4 * v + 2] = (float)(T)t.z;
+      tg[4 * v + 3] = (float)(T)t.w;
+    }
+  }
+  const float cx0 = coords[q * 2], cy0 = coords[q * 2 + 1];
+  const float inv_sqrt_c = rsqrtf((float)C);
+  float* orow = out + q * (size_t)L * K * K;
+  for (int l = 0; l < L; ++l) {
+    const int H = lv.H[l], W = lv.W[l];
+    const T* fm = reinterpret_cast<const T*>(lv.fmap[l]) + img * (size_t)H * W * C;
+    const float scale = 1.0f / (float)(1 << l);
+    const float cx = cx0 * scale, cy = cy0 * scale;
+    const float fxf = floorf(cx), fyf = floorf(cy);
+    const int fx = (int)fxf, fy = (int)fyf;
+#pragma unroll
+    for (int s = 0; s < NPL; ++s) {
+      const int p = s * 32 + lane;
+      const int iy = p / FP, ix = p - iy * FP;
+      const int Y = fy - R + iy, X = fx - R + ix;
+      const bool in = p < NF && (border || (Y >= 0 && Y < H && X >= 0 && X < W));
+      const int Yc = min(max(Y, 0), H - 1), Xc = min(max(X, 0), W - 1);     // unconditional load from a clamped address
+      const float acc = Vec32<T>::dot(fm + ((size_t)Yc * W + Xc) * C, tg);
+      dsm[warp][p] = in ? acc * inv_sqrt_c : 0.f;
+    }
+    __syncwarp();
+    // bilinear interpolation of the K*K taps (identical to corr_sample_kernel)
+    for (int o = lane; o < K * K; o += 32) {
+      const int a = o / K, b = o % K;
+      float x = cx + (float)(a - R), y = cy + (float)(b - R);
+      float val;
+      if (!border) {
+        const float wx = cx - fxf, wy = cy - fyf;
+        const int ix = a, iy = b;
+        const float d00 = dsm[warp][iy * FP + ix], d01 = dsm[warp][iy * FP + ix + 1];
+        const float d10 = dsm[warp][(iy + 1) * FP + ix], d11 = dsm[warp][(iy + 1) * FP + ix + 1];
+        val = d00 * (1.f - wx) * (1.f - wy) + d01 * wx * (1.f - wy) + d10 * (1.f - wx) * wy + d11 * wx * wy;
+      } else {
+        x = fminf(fmaxf(x, 0.f), (float)(W - 1));
+        y = fminf(fmaxf(y, 0.f), (float)(H - 1));
+        const float x0f = floorf(x), y0f = floorf(y);
+        const float wx = x - x0f, wy = y - y0f;
+        const int x0 = (int)x0f, y0 = (int)y0f;
+        const int x1 = min(x0 + 1, W - 1), y1 = min(y0 + 1, H - 1);
+        auto slotx = [&](int X) { return min(max(X - (fx - R), 0), FP - 1); };
+        auto sloty = [&](int Y) { return min(max(Y - (fy - R), 0), FP - 1); };
+        const float d00 = dsm[warp][sloty(y0) * FP + slotx(x0)], d01 = dsm[warp][sloty(y0) * FP + slotx(x1)];
+        const float d10 = dsm[warp][sloty(y1) * FP + slotx(x0)], d11 = dsm[warp][sloty(y1) * FP + slotx(x1)];
+        val = d00 * (1.f - wx) * (1.f - wy) + d01 * wx * (1.f - wy) + d10 * (1.f - wx) * wy + d11 * wx * wy;
+      }
+      orow[(size_t)l * K * K + o] = val;
+    }
+    __syncwarp();
+  }
+}
+
 template <typename T>
 static int launch_corr(int BS, int N, int C, int L, int R, const CorrLevels& lv, const float* targets,
                        const float* coords, int border, float* out, cudaStream_t st) {
@@ -203,6 +319,19 @@ static int launch_corr(int BS, int N, int C, int L, int R, const CorrLevels& lv,
     corr_sample_kernel<T, CPLV, RV><<<grid, 256, 0, st>>>(BS, N, L, lv, targets, coords, border, out);             \
     VGG_LAUNCH_CHECK();                                                                                            \
     return VGG_OK;                                                                                                 \
+  }
+  // C = 32: position-per-lane kernel (VGG_CORR_C32=0 keeps the channel-per-lane one for A/B); pointers must be 16-byte
+  // aligned, which every level of an NHWC pyramid with C = 32 is
+  static const bool c32 = [] { const char* e = getenv("VGG_CORR_C32"); return !(e && e[0] == '0'); }();
+  if (C == 32 && c32 && (R == 3 || R == 4) && (reinterpret_cast<uintptr_t>(targets) & 15) == 0) {
+    bool aligned = true;
+    for (int l = 0; l < L; ++l) aligned = aligned && (reinterpret_cast<uintptr_t>(lv.fmap[l]) & 15) == 0;
+    if (aligned) {
+      if (R == 3) corr_sample_c32_kernel<T, 3><<<grid, 256, 0, st>>>(BS, N, L, lv, targets, coords, border, out);
+      else corr_sample_c32_kernel<T, 4><<<grid, 256, 0, st>>>(BS, N, L, lv, targets, coords, border, out);
+      VGG_LAUNCH_CHECK();
+      return VGG_OK;
+    }
   }
   VGG_CORR_CASE(4, 4)   // coarse tracker: C=128, r=4
   VGG_CORR_CASE(4, 3)
