@@ -637,15 +637,19 @@ constexpr int CUD = 68;
 template <int TM>
 __global__ void __launch_bounds__(C_THREADS, 2) chol_update_kernel(int n, int lda, int k0, int t0, int mode,
                                                                     double* __restrict__ A, int band_end, int arrow_lo,
-                                                                    int all_red) {
+                                                                    int all_red, int ntiles) {
   constexpr int WN = TM == 64 ? 4 : 8;            // warps along the 64 tile columns
   constexpr int NJ = 64 / WN / 8;                 // 8-column MMA tiles per warp: 2 or 1
   extern __shared__ __align__(16) double cu_smem[];
   double* As = cu_smem;                         // [TM][CUD]
   double* Bs = cu_smem + TM * CUD;              // [64][CUD]
+  // gridDim.x == ntiles: one tile per CTA (default); gridDim.x < ntiles (VGG_CHOL_PERSIST=1): a persistent CTA per SM walks
+  // the tiles, so that never more than one update CTA sits on an SM and a panel CTA of the next step always finds room.
+  // Measured r02: 0.920 ms against 0.890 -- one update CTA per SM hides its own latencies worse than it helps the panels.
+  for (int tile_t = blockIdx.x; tile_t < ntiles; tile_t += gridDim.x) {
   int bi, bj;
   {
-    int t = blockIdx.x;
+    int t = tile_t;
     if (TM == 32) {
       const int T = (n - t0 + 31) / 32;           // 32-row tiles; tile column 1 starts at row tile 2
       if (t < T) { bi = t; bj = 0; }
@@ -738,7 +742,10 @@ __global__ void __launch_bounds__(C_THREADS, 2) chol_update_kernel(int n, int ld
       }
     }
   }
+  __syncthreads();                                  // the next tile's loads overwrite the operand buffers
+  }
 }
+
 
 size_t chol_workspace_doubles(int n) {
   const int nblk = (n + CB - 1) / CB;
@@ -828,6 +835,15 @@ int chol_enqueue(int n, int lda, double* A, double* Ldiag, int* info, int* flags
   const size_t smem_p = sizeof(double) * (CB + C_RPC) * CLD;
   const size_t smem_u = sizeof(double) * 2 * CT * CUD;
   const bool fuse = lookahead && chol_fuse();
+  static const int persist_ctas = [] {
+    const char* e = getenv("VGG_CHOL_PERSIST");
+    if (!(e && e[0] == '1')) return 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms;
+  }();
+  auto upd_grid = [&](int tiles) { return persist_ctas > 0 ? std::min(tiles, persist_ctas) : tiles; };
   static const bool split = [] { const char* e = getenv("VGG_CHOL_SPLIT"); return !(e && e[0] == '0'); }();
   // the band structure is honoured by the default (fused + split) schedule only; the A/B schedules treat the matrix as dense
   const bool banded = fuse && split && (int)g_chol_band_end.size() >= nblk && g_chol_arrow_blk > 0;
@@ -880,20 +896,20 @@ int chol_enqueue(int n, int lda, double* A, double* Ldiag, int* info, int* flags
           VGG_CUDA_CHECK(cudaStreamWaitEvent(cs->side_mid, cs->ev_col, 0));
           // U2(b-2) still writes block column b+2 with plain read-modify-writes (only its first block column uses REDs)
           if (b >= 2 && have_u2[(b - 2) % 3]) VGG_CUDA_CHECK(cudaStreamWaitEvent(cs->side_mid, cs->ev_bulk[(b - 2) % 3], 0));
-          chol_update_kernel<64><<<n_u1, C_THREADS, smem_u, cs->side_mid>>>(n, lda, k0, t0, 4, A, band_end, arrow_lo, all_red);
+          chol_update_kernel<64><<<upd_grid(n_u1), C_THREADS, smem_u, cs->side_mid>>>(n, lda, k0, t0, 4, A, band_end, arrow_lo, all_red, n_u1);
           VGG_LAUNCH_CHECK();
           VGG_CUDA_CHECK(cudaEventRecord(cs->ev_upd[b & 1], cs->side_mid));
           have_u1[b & 1] = true;
           if (n_u2 > 0) {
             VGG_CUDA_CHECK(cudaStreamWaitEvent(cs->side_lo, cs->ev_col, 0));
-            chol_update_kernel<64><<<n_u2, C_THREADS, smem_u, cs->side_lo>>>(n, lda, k0, t0, 5, A, band_end, arrow_lo, all_red);
+            chol_update_kernel<64><<<upd_grid(n_u2), C_THREADS, smem_u, cs->side_lo>>>(n, lda, k0, t0, 5, A, band_end, arrow_lo, all_red, n_u2);
             VGG_LAUNCH_CHECK();
             VGG_CUDA_CHECK(cudaEventRecord(cs->ev_bulk[b % 3], cs->side_lo));
             have_u2[b % 3] = true;
           }
         } else {
           VGG_CUDA_CHECK(cudaStreamWaitEvent(cs->side_lo, cs->ev_col, 0));
-          chol_update_kernel<64><<<n_rest, C_THREADS, smem_u, cs->side_lo>>>(n, lda, k0, t0, 3, A, n, n, 0);
+          chol_update_kernel<64><<<upd_grid(n_rest), C_THREADS, smem_u, cs->side_lo>>>(n, lda, k0, t0, 3, A, n, n, 0, n_rest);
           VGG_LAUNCH_CHECK();
           VGG_CUDA_CHECK(cudaEventRecord(cs->ev_upd[b & 1], cs->side_lo));
           have_u1[b & 1] = true;
@@ -918,19 +934,19 @@ int chol_enqueue(int n, int lda, double* A, double* Ldiag, int* info, int* flags
     const int n_col = T32 + (T32 > 2 ? T32 - 2 : 0);       // 32-row tiles of tile columns 0 and 1
     const int n_rest = T > 2 ? (T - 2) * (T - 1) / 2 : 0;
     if (!lookahead) {
-      chol_update_kernel<64><<<T * (T + 1) / 2, C_THREADS, smem_u, st>>>(n, lda, k0, t0, 0, A, n, n, 0);
+      chol_update_kernel<64><<<upd_grid(T * (T + 1) / 2), C_THREADS, smem_u, st>>>(n, lda, k0, t0, 0, A, n, n, 0, T * (T + 1) / 2);
       VGG_LAUNCH_CHECK();
       if ((rc = panel(b + 1, st))) return rc;
       continue;
     }
-    chol_update_kernel<32><<<n_col, C_THREADS, sizeof(double) * (32 + CT) * CUD, st>>>(n, lda, k0, t0, 1, A, n, n, 0);
+    chol_update_kernel<32><<<n_col, C_THREADS, sizeof(double) * (32 + CT) * CUD, st>>>(n, lda, k0, t0, 1, A, n, n, 0, n_col);
     VGG_LAUNCH_CHECK();
     VGG_CUDA_CHECK(cudaEventRecord(cs->ev_col, st));
     VGG_CUDA_CHECK(cudaStreamWaitEvent(cs->side, cs->ev_col, 0));
     if ((rc = panel(b + 1, cs->side))) return rc;
     VGG_CUDA_CHECK(cudaEventRecord(cs->ev_panel, cs->side));
     if (n_rest > 0) {
-      chol_update_kernel<64><<<n_rest, C_THREADS, smem_u, st>>>(n, lda, k0, t0, 2, A, n, n, 0);
+      chol_update_kernel<64><<<upd_grid(n_rest), C_THREADS, smem_u, st>>>(n, lda, k0, t0, 2, A, n, n, 0, n_rest);
       VGG_LAUNCH_CHECK();
     }
     VGG_CUDA_CHECK(cudaStreamWaitEvent(st, cs->ev_panel, 0));
