@@ -232,7 +232,7 @@ template <> struct Vec32<__half> {
 };
 
 template <typename T, int R>
-__global__ void __launch_bounds__(256, 2) corr_sample_c32_kernel(int BS, int N, int L, CorrLevels lv,
+__global__ void __launch_bounds__(256, 4) corr_sample_c32_kernel(int BS, int N, int L, CorrLevels lv,
                                                                  const float* __restrict__ targets /*[BS,N,32]*/,
                                                                  const float* __restrict__ coords /*[BS,N,2]*/, int border,
                                                                  float* __restrict__ out /*[BS,N,L*(2R+1)^2]*/) {
