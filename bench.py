@@ -308,7 +308,9 @@ def corr_section(dev, hbm_peak):
                             "tensor_peak_source": tsrc, "frac_of_tensor_peak": fl / (ms * 1e-3) / 1e12 / tpk,
                             "ncu": "profiles/r02_ncu_corr_tc8.txt: sm__pipe_tensor_subpipe_hmma_cycles_active 38.7 %"})
             else:
-                rec.update({"kernel": "corr_sample footprint kernel (CUDA cores)", "bound": "hbm", "algorithmic_bytes": ab,
+                rec.update({"kernel": ("corr_sample_c32_kernel (CUDA cores, one footprint position per lane)" if C == 32
+                                       else "corr_sample_kernel (CUDA cores, channels across lanes)"),
+                            "bound": "hbm", "algorithmic_bytes": ab,
                             "achieved_gbs": ab / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": ab / (ms * 1e-3) / 1e9 / hbm_peak})
             res = run_ours()
             del ours
